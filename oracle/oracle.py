@@ -1,0 +1,399 @@
+"""CPU oracle for the SLN-Amodal detection-head hot path.
+
+TEST INFRASTRUCTURE ONLY.  Importable from ``tests/``, from
+``__graft_entry__.smoke()`` and from ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs -- never from ``sln_amodal_b200`` (the product).
+
+Two layers:
+
+* ``ref_*``  -- the reference's own unmodified C (``oracle/_ref/*.so`` built by
+  ``oracle/Makefile`` from ``/root/reference/roialign/roi_align/src/crop_and_resize.c``
+  and ``/root/reference/nms/src/nms.c`` against ``oracle/th_shim``).  Available
+  wherever the prebuilt ``.so`` files are present (they travel to the GPU box).
+* everything else -- our restatement (``oracle/sln_oracle.c`` + numpy/torch-CPU
+  below), each function citing the reference file:line it follows.
+  ``tests/test_oracle_pin.py`` pins the restatement to ``ref_*`` bit for bit,
+  to the reference's Python (golden fixtures made by
+  ``tests/golden/make_golden.py``) and, for the EDT only, to scipy
+  ("parity unpinned" by the reference: it has no EDT).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORC_SO = os.path.join(_HERE, "_build", "libsln_oracle.so")
+_REF_CROP_SO = os.path.join(_HERE, "_ref", "libref_crop.so")
+_REF_NMS_SO = os.path.join(_HERE, "_ref", "libref_nms.so")
+
+
+def build(quiet: bool = True) -> None:
+    """(Re)build the oracle libraries with oracle/Makefile (make is a no-op when fresh)."""
+    subprocess.run(["make", "-C", _HERE], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _lptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+_orc = None
+
+
+def _lib():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(_ORC_SO):
+            build()
+        lib = C.CDLL(_ORC_SO)
+        lib.orc_crop_and_resize_fwd.restype = C.c_int
+        lib.orc_crop_and_resize_bwd.restype = C.c_int
+        lib.orc_nms.restype = C.c_int
+        lib.orc_layer_decode.restype = C.c_int
+        lib.orc_edt_sq.restype = None
+        _orc = lib
+    return _orc
+
+
+# ---------------------------------------------------------------------------
+# restatement: crop_and_resize (crop_and_resize.c:6-154, 157-252)
+# ---------------------------------------------------------------------------
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+
+
+def crop_and_resize_fwd(image, boxes, box_ind, ph, pw, ext=0.0):
+    """image f32[B,C,H,W] (NCHW), boxes f32[N,4] (y1,x1,y2,x2 normalised), box_ind i32[N]
+    -> crops f32[N,C,ph,pw].  Raises on an out-of-range box_ind (reference: exit(-1))."""
+    image, boxes, box_ind = _f32(image), _f32(boxes).reshape(-1, 4), _i32(box_ind)
+    B, Cc, H, W = image.shape
+    N = boxes.shape[0]
+    out = np.empty((N, Cc, ph, pw), np.float32)
+    rc = _lib().orc_crop_and_resize_fwd(_fptr(image), B, Cc, H, W, _fptr(boxes), _iptr(box_ind),
+                                        N, ph, pw, C.c_float(ext), _fptr(out))
+    if rc != 0:
+        raise ValueError("box_ind out of range")
+    return out
+
+
+def crop_and_resize_bwd(grads, boxes, box_ind, image_shape):
+    """grads f32[N,C,ph,pw] -> grad_image f32[B,C,H,W] (dense, zero-filled)."""
+    grads, boxes, box_ind = _f32(grads), _f32(boxes).reshape(-1, 4), _i32(box_ind)
+    B, Cc, H, W = image_shape
+    N, Cg, ph, pw = grads.shape
+    assert Cg == Cc
+    out = np.empty((B, Cc, H, W), np.float32)
+    rc = _lib().orc_crop_and_resize_bwd(_fptr(grads), _fptr(boxes), _iptr(box_ind), N, Cc, ph, pw,
+                                        _fptr(out), B, H, W)
+    if rc != 0:
+        raise ValueError("box_ind out of range")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# restatement: NMS (nms.c:4-69 behind pth_nms.py:10-24)
+# ---------------------------------------------------------------------------
+def stable_order(scores):
+    """The build's sort contract (SURVEY.md section 7 'Sort tie-breaking'): score descending,
+    index ascending among ties.  (pth_nms.py:17 uses torch's default sort, which is
+    implementation-defined on ties.)"""
+    scores = np.asarray(scores, dtype=np.float32)
+    return np.argsort(-scores.astype(np.float64), kind="stable").astype(np.int64)
+
+
+def nms_areas(dets):
+    """pth_nms.py:10-16: areas = (x2 - x1 + 1) * (y2 - y1 + 1), fp32, un-fused."""
+    d = _f32(dets)
+    return ((d[:, 3] - d[:, 1] + np.float32(1)) * (d[:, 2] - d[:, 0] + np.float32(1))).astype(np.float32)
+
+
+def nms_given_order(dets, order, areas, thresh):
+    """cpu_nms (nms.c:4-69) on explicit `order` and `areas`.  Returns kept indices int64[k]."""
+    dets = _f32(dets)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    areas = _f32(areas)
+    n = dets.shape[0]
+    keep = np.empty(max(n, 1), np.int64)
+    num = np.zeros(1, np.int64)
+    _lib().orc_nms(_fptr(dets), dets.shape[1], _lptr(order), _fptr(areas), C.c_int64(n),
+                   C.c_float(thresh), _lptr(keep), _lptr(num))
+    return keep[: int(num[0])].copy()
+
+
+def nms(dets, thresh):
+    """nms(dets, thresh) (nms_wrapper.py:14-17 -> pth_nms.py:5-24, CPU branch) with the stable
+    sort contract.  dets f32[n,5] = (y1,x1,y2,x2,score)."""
+    dets = _f32(dets)
+    if dets.shape[0] == 0:
+        return np.empty(0, np.int64)
+    return nms_given_order(dets, stable_order(dets[:, 4]), nms_areas(dets), thresh)
+
+
+# ---------------------------------------------------------------------------
+# restatement: layer codec (Functions.py:1012-1095, amodal_train.py:236-271)
+# ---------------------------------------------------------------------------
+def layer_decode(label, L, n_max=32):
+    """Closed-form decode (oracle/sln_oracle.c:orc_layer_decode).
+    label u64[H,W] -> (u8[n_max,L,H,W], n_obj)."""
+    label = np.ascontiguousarray(label, dtype=np.uint64)
+    H, W = label.shape
+    out = np.empty((n_max, L, H, W), np.uint8)
+    n_obj = _lib().orc_layer_decode(label.ctypes.data_as(C.POINTER(C.c_uint64)), H, W, L, n_max,
+                                    out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out, int(n_obj)
+
+
+def layer_decode_loops(label, num_classes):
+    """Loop-for-loop restatement of AmodalDataset.load_layer2 (amodal_train.py:236-271) and the
+    codec helpers it drives (Functions.py:1012-1095).  Slow (one full-image compare per label
+    piece); small cases only.  Returns bool[H,W,L,n_obj] like the reference, or None when the
+    reference would fall through to the empty-mask path (n_obj == 0)."""
+    label = np.asarray(label, dtype=np.uint64)
+    H, W = label.shape
+    L = num_classes - 1
+    ids = np.unique(label)                       # get_image_labals, Functions.py:1012-1016
+    if ids.size and ids[0] == 0:
+        ids = ids[1:]
+    lo = ids & np.uint64(0xFFFFFFFF)             # max_objectID, Functions.py:1074-1079
+    n_obj = 0
+    while np.any((lo >> np.uint64(n_obj)) == 1):
+        n_obj += 1
+    planes = []
+    for i in range(n_obj):
+        m = np.zeros((H, W, L), bool)
+        for v in ids:                            # objectID_to_masks, Functions.py:1020-1033
+            if (int(v) >> i) & 1:
+                m[..., 0] |= (label == v)        # amodal_train.py:249-250
+        for v in ids:
+            if (int(v) >> (i + 32)) & 1:
+                hi = int(v) >> 32                # maskID_to_objectIDs, Functions.py:1084-1095
+                bits = [k for k in range(32) if (hi >> k) & 1]   # number_to_index :1050-1060
+                d = bits.index(i) + 1            # objIDs_to_sindistanceLayer :1063-1064 (+1 at amodal_train.py:255)
+                if d >= num_classes - 1 - 1:     # amodal_train.py:256-259
+                    m[..., -1] |= (label == v)
+                else:
+                    m[..., d] |= (label == v)
+        planes.append(m)
+    if not planes:
+        return None
+    return np.stack(planes, axis=3)
+
+
+# ---------------------------------------------------------------------------
+# restatement: exact squared EDT (not in the reference; pinned to scipy)
+# ---------------------------------------------------------------------------
+def edt_sq(mask):
+    """mask u8[H,W] -> i32[H,W] squared distance to the nearest zero pixel; (H+W)^2 if none."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    H, W = mask.shape
+    out = np.empty((H, W), np.int32)
+    _lib().orc_edt_sq(mask.ctypes.data_as(C.POINTER(C.c_ubyte)), H, W,
+                      out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# restatement: proposal_layer / pyramid level routing (torch-CPU arithmetic)
+# ---------------------------------------------------------------------------
+def apply_box_deltas(boxes, deltas):
+    """Functions.py:77-98 in numpy fp32, one rounding per operation (exp from torch CPU so the
+    transcendental is the reference's)."""
+    import torch
+    b = _f32(boxes)
+    d = _f32(deltas)
+    f = np.float32
+    height = b[:, 2] - b[:, 0]
+    width = b[:, 3] - b[:, 1]
+    cy = b[:, 0] + f(0.5) * height
+    cx = b[:, 1] + f(0.5) * width
+    cy = cy + d[:, 0] * height
+    cx = cx + d[:, 1] * width
+    height = height * torch.exp(torch.from_numpy(d[:, 2].copy())).numpy()
+    width = width * torch.exp(torch.from_numpy(d[:, 3].copy())).numpy()
+    y1 = cy - f(0.5) * height
+    x1 = cx - f(0.5) * width
+    y2 = y1 + height
+    x2 = x1 + width
+    return np.stack([y1, x1, y2, x2], axis=1).astype(np.float32)
+
+
+def clip_boxes(boxes, window):
+    """Functions.py:101-111."""
+    b = _f32(boxes).copy()
+    w = [np.float32(v) for v in window]
+    b[:, 0] = np.clip(b[:, 0], w[0], w[2])
+    b[:, 1] = np.clip(b[:, 1], w[1], w[3])
+    b[:, 2] = np.clip(b[:, 2], w[0], w[2])
+    b[:, 3] = np.clip(b[:, 3], w[1], w[3])
+    return b
+
+
+def proposal_layer(rpn_probs, rpn_bbox, anchors, proposal_count, nms_threshold,
+                   image_hw=(1024, 1024), std_dev=(0.1, 0.1, 0.2, 0.2), pre_nms_limit=6000,
+                   return_aux=False):
+    """Functions.py:114-178 for one image.  rpn_probs f32[A,2], rpn_bbox f32[A,4], anchors f32[A,4]
+    (pixels) -> normalised boxes f32[k,4], k <= proposal_count (no padding)."""
+    probs, bbox, anchors = _f32(rpn_probs), _f32(rpn_bbox), _f32(anchors)
+    scores = probs[:, 1]
+    deltas = bbox * np.asarray(std_dev, np.float32).reshape(1, 4)      # :137-140
+    limit = min(pre_nms_limit, anchors.shape[0])                        # :144
+    order = stable_order(scores)[:limit]                                # :145-146 (stable contract)
+    top_scores = scores[order]
+    boxes = apply_box_deltas(anchors[order], deltas[order])             # :153
+    H, W = image_hw
+    boxes = clip_boxes(boxes, (0, 0, H, W))                             # :156-158
+    dets = np.concatenate([boxes, top_scores[:, None]], axis=1)
+    keep = nms(dets, nms_threshold)[:proposal_count]                    # :165-166
+    out = boxes[keep] / np.asarray([H, W, H, W], np.float32)            # :170-173
+    if return_aux:
+        return out.astype(np.float32), dict(order=order, boxes=boxes, keep=keep)
+    return out.astype(np.float32)
+
+
+def roi_levels(boxes, image_hw=(1024, 1024)):
+    """modals.py:53-64 evaluated with torch CPU ops (log/sqrt/round are the reference's)."""
+    import torch
+    b = torch.from_numpy(_f32(boxes).reshape(-1, 4))
+    y1, x1, y2, x2 = b.chunk(4, dim=1)
+    h = y2 - y1
+    w = x2 - x1
+    image_area = torch.FloatTensor([float(image_hw[0] * image_hw[1])])
+    ln2 = torch.log(torch.FloatTensor([2.0]))
+    lvl = 4 + torch.log(torch.sqrt(h * w) / (224.0 / torch.sqrt(image_area))) / ln2
+    lvl = lvl.round().int().clamp(2, 5)
+    return lvl.view(-1).numpy().astype(np.int32)
+
+
+def pyramid_roi_align(boxes, feature_maps, pool, image_hw=(1024, 1024), levels=None):
+    """modals.py:20-110 for one image: boxes f32[N,4] normalised, feature_maps = [P2..P5] each
+    f32[1,C,H_l,W_l] -> f32[N,C,pool,pool] in the original ROI order."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    if levels is None:
+        levels = roi_levels(boxes, image_hw)
+    Cc = feature_maps[0].shape[1]
+    out = np.zeros((boxes.shape[0], Cc, pool, pool), np.float32)
+    for i, lvl in enumerate(range(2, 6)):
+        ix = np.nonzero(levels == lvl)[0]
+        if ix.size == 0:
+            continue
+        out[ix] = crop_and_resize_fwd(feature_maps[i], boxes[ix], np.zeros(ix.size, np.int32), pool, pool, 0.0)
+    return out
+
+
+def per_class_nms(boxes, class_ids, scores, thresh):
+    """The per-class loop of refine_detections (Functions.py:506-525): for every class id run
+    nms() on that class's detections (sorted by score) and union the kept indices.  Returns the
+    sorted union of kept indices (intersect1d/unique1d give ascending order, :524-525)."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    class_ids = np.asarray(class_ids)
+    scores = _f32(scores)
+    kept = []
+    for c in np.unique(class_ids):
+        ixs = np.nonzero(class_ids == c)[0]
+        order = stable_order(scores[ixs])
+        dets = np.concatenate([boxes[ixs][order], scores[ixs][order][:, None]], axis=1)
+        k = nms(dets, thresh)
+        kept.append(ixs[order[k]])
+    if not kept:
+        return np.empty(0, np.int64)
+    return np.unique(np.concatenate(kept)).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------
+# the reference's own C, unmodified (oracle/_ref)
+# ---------------------------------------------------------------------------
+class _TH(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_long * 4), ("nd", C.c_int)]
+
+
+def _th(a):
+    t = _TH()
+    t.data = a.ctypes.data
+    for i in range(4):
+        t.size[i] = a.shape[i] if i < a.ndim else 1
+    t.nd = a.ndim
+    return t
+
+
+_ref_crop = None
+_ref_nms = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_CROP_SO) and os.path.exists(_REF_NMS_SO)
+
+
+def _ref_crop_lib():
+    global _ref_crop
+    if _ref_crop is None:
+        _ref_crop = C.CDLL(_REF_CROP_SO)
+        _ref_crop.crop_and_resize_forward.restype = None
+        _ref_crop.crop_and_resize_backward.restype = None
+    return _ref_crop
+
+
+def _ref_nms_lib():
+    global _ref_nms
+    if _ref_nms is None:
+        _ref_nms = C.CDLL(_REF_NMS_SO)
+        _ref_nms.cpu_nms.restype = C.c_int
+    return _ref_nms
+
+
+def ref_crop_and_resize_fwd(image, boxes, box_ind, ph, pw, ext=0.0):
+    """crop_and_resize_forward (crop_and_resize.c:115-154), the reference's own object code.
+    box_ind must be in range: the reference exit(-1)s otherwise."""
+    image, boxes, box_ind = _f32(image), _f32(boxes).reshape(-1, 4), _i32(box_ind)
+    assert box_ind.size == 0 or (box_ind.min() >= 0 and box_ind.max() < image.shape[0])
+    out = np.empty((boxes.shape[0], image.shape[1], ph, pw), np.float32)
+    ti, tb, tx, to = _th(image), _th(boxes), _th(box_ind), _th(out)
+    _ref_crop_lib().crop_and_resize_forward(C.byref(ti), C.byref(tb), C.byref(tx), C.c_float(ext),
+                                            C.c_int(ph), C.c_int(pw), C.byref(to))
+    return out
+
+
+def ref_crop_and_resize_bwd(grads, boxes, box_ind, image_shape):
+    """crop_and_resize_backward (crop_and_resize.c:157-252), the reference's own object code."""
+    grads, boxes, box_ind = _f32(grads), _f32(boxes).reshape(-1, 4), _i32(box_ind)
+    assert box_ind.size == 0 or (box_ind.min() >= 0 and box_ind.max() < image_shape[0])
+    out = np.empty(tuple(image_shape), np.float32)
+    tg, tb, tx, to = _th(grads), _th(boxes), _th(box_ind), _th(out)
+    _ref_crop_lib().crop_and_resize_backward(C.byref(tg), C.byref(tb), C.byref(tx), C.byref(to))
+    return out
+
+
+def ref_nms_given_order(dets, order, areas, thresh):
+    """cpu_nms (nms.c:4-69), the reference's own object code."""
+    dets = _f32(dets)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    areas = _f32(areas)
+    n = dets.shape[0]
+    keep = np.empty(max(n, 1), np.int64)
+    num = np.zeros(1, np.int64)
+    tk, tn, td, to, ta = _th(keep), _th(num), _th(dets), _th(order), _th(areas)
+    _ref_nms_lib().cpu_nms(C.byref(tk), C.byref(tn), C.byref(td), C.byref(to), C.byref(ta),
+                           C.c_float(thresh))
+    return keep[: int(num[0])].copy()
+
+
+def ref_nms(dets, thresh):
+    dets = _f32(dets)
+    if dets.shape[0] == 0:
+        return np.empty(0, np.int64)
+    return ref_nms_given_order(dets, stable_order(dets[:, 4]), nms_areas(dets), thresh)

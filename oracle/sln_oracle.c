@@ -1,0 +1,260 @@
+/*
+ * sln_oracle.c -- CPU restatement of the SLN-Amodal detection-head hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA
+ * library in sln_amodal_b200/csrc.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * path never links, imports or calls anything under oracle/.
+ *
+ * Each function restates the arithmetic of one reference routine (file:line
+ * under /root/reference given at each function) with plain pointers instead of
+ * TH tensors.  The restatement is pinned by tests/test_oracle_pin.py, which
+ * compares it bit-for-bit with the reference's own unmodified C sources
+ * compiled into oracle/_ref/ (see oracle/Makefile), and with scipy for the EDT
+ * (the reference has no EDT: "parity unpinned" for that one op).
+ *
+ * Build: gcc -O2 -std=c99 -ffp-contract=off (no -march, no fast-math): fp32
+ * operations stay un-fused, which is what defines the reference bit pattern.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* One axis of the crop sampling grid.
+ * Follows crop_and_resize.c:44-56 (scale, sample position), :58 / :80 (range
+ * test), :71-73 / :89-91 (floorf/ceilf taps and lerp weight). */
+typedef struct {
+    int valid; /* sample inside [0, extent-1] */
+    int lo;    /* floorf(pos) */
+    int hi;    /* ceilf(pos)  */
+    float lerp;
+} orc_tap;
+
+static void orc_axis(float a1, float a2, int extent, int crop, orc_tap *taps)
+{
+    const float scale = (crop > 1) ? (a2 - a1) * (extent - 1) / (crop - 1) : 0;
+    for (int k = 0; k < crop; ++k) {
+        const float pos = (crop > 1) ? a1 * (extent - 1) + k * scale
+                                     : 0.5 * (a1 + a2) * (extent - 1);
+        orc_tap t;
+        t.valid = !(pos < 0 || pos > extent - 1);
+        t.lo = t.hi = 0;
+        t.lerp = 0.f;
+        if (t.valid) {
+            t.lo = (int)floorf(pos);
+            t.hi = (int)ceilf(pos);
+            t.lerp = pos - t.lo;
+        }
+        taps[k] = t;
+    }
+}
+
+/* crop_and_resize forward, NCHW in / NCHW out.
+ * Reference: CropAndResizePerBox + crop_and_resize_forward,
+ * roialign/roi_align/src/crop_and_resize.c:6-112, 115-154.
+ * Returns 0, or -1 if a box_ind is out of range (the reference exit(-1)s at
+ * crop_and_resize.c:39-42). */
+int orc_crop_and_resize_fwd(const float *image, int B, int C, int H, int W,
+                            const float *boxes, const int *box_ind, int N,
+                            int ph, int pw, float ext, float *crops)
+{
+    orc_tap *ty = (orc_tap *)malloc(sizeof(orc_tap) * (size_t)(ph + pw));
+    orc_tap *tx = ty + ph;
+    const size_t plane = (size_t)H * W;
+    for (int r = 0; r < N; ++r) {
+        const int b = box_ind[r];
+        if (b < 0 || b >= B) { free(ty); return -1; }
+        orc_axis(boxes[4 * r + 0], boxes[4 * r + 2], H, ph, ty);
+        orc_axis(boxes[4 * r + 1], boxes[4 * r + 3], W, pw, tx);
+        for (int c = 0; c < C; ++c) {
+            const float *src = image + ((size_t)b * C + c) * plane;
+            float *dst = crops + ((size_t)r * C + c) * ph * pw;
+            for (int y = 0; y < ph; ++y) {
+                for (int x = 0; x < pw; ++x) {
+                    float v = ext;
+                    if (ty[y].valid && tx[x].valid) {
+                        const float tl = src[(size_t)ty[y].lo * W + tx[x].lo];
+                        const float tr = src[(size_t)ty[y].lo * W + tx[x].hi];
+                        const float bl = src[(size_t)ty[y].hi * W + tx[x].lo];
+                        const float br = src[(size_t)ty[y].hi * W + tx[x].hi];
+                        const float top = tl + (tr - tl) * tx[x].lerp;
+                        const float bot = bl + (br - bl) * tx[x].lerp;
+                        v = top + (bot - top) * ty[y].lerp;
+                    }
+                    dst[y * pw + x] = v;
+                }
+            }
+        }
+    }
+    free(ty);
+    return 0;
+}
+
+/* crop_and_resize backward w.r.t. the image, NCHW.
+ * Reference: crop_and_resize_backward, crop_and_resize.c:157-252.  The
+ * accumulation order per destination pixel is (box, y, x, tap TL/TR/BL/BR),
+ * exactly the reference's serial loop order (:190-250), so the fp32 sums are
+ * reproducible bit for bit. */
+int orc_crop_and_resize_bwd(const float *grads, const float *boxes,
+                            const int *box_ind, int N, int C, int ph, int pw,
+                            float *grad_image, int B, int H, int W)
+{
+    orc_tap *ty = (orc_tap *)malloc(sizeof(orc_tap) * (size_t)(ph + pw));
+    orc_tap *tx = ty + ph;
+    const size_t plane = (size_t)H * W;
+    memset(grad_image, 0, sizeof(float) * (size_t)B * C * plane);
+    for (int r = 0; r < N; ++r) {
+        const int b = box_ind[r];
+        if (b < 0 || b >= B) { free(ty); return -1; }
+        orc_axis(boxes[4 * r + 0], boxes[4 * r + 2], H, ph, ty);
+        orc_axis(boxes[4 * r + 1], boxes[4 * r + 3], W, pw, tx);
+        for (int y = 0; y < ph; ++y) {
+            if (!ty[y].valid) continue;
+            const float yl = ty[y].lerp;
+            for (int x = 0; x < pw; ++x) {
+                if (!tx[x].valid) continue;
+                const float xl = tx[x].lerp;
+                for (int c = 0; c < C; ++c) {
+                    float *dst = grad_image + ((size_t)b * C + c) * plane;
+                    const float g = grads[(((size_t)r * C + c) * ph + y) * pw + x];
+                    const float dtop = (1 - yl) * g;
+                    dst[(size_t)ty[y].lo * W + tx[x].lo] += (1 - xl) * dtop;
+                    dst[(size_t)ty[y].lo * W + tx[x].hi] += xl * dtop;
+                    const float dbot = yl * g;
+                    dst[(size_t)ty[y].hi * W + tx[x].lo] += (1 - xl) * dbot;
+                    dst[(size_t)ty[y].hi * W + tx[x].hi] += xl * dbot;
+                }
+            }
+        }
+    }
+    free(ty);
+    return 0;
+}
+
+/* Greedy NMS over a caller-supplied visiting order and precomputed areas.
+ * Reference: cpu_nms, nms/src/nms.c:4-69.  "+1" pixel convention (:55-56),
+ * un-fused fp32, IEEE divide, suppress when ovr >= thresh (:58-61).  Kept
+ * original indices are written in visiting order; *num_out gets the count. */
+int orc_nms(const float *boxes, int stride, const int64_t *order,
+            const float *areas, int64_t n, float thresh, int64_t *keep,
+            int64_t *num_out)
+{
+    unsigned char *dead = (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int64_t kept = 0;
+    for (int64_t pi = 0; pi < n; ++pi) {
+        const int64_t i = order[pi];
+        if (dead[i]) continue;
+        keep[kept++] = i;
+        const float *bi = boxes + i * stride;
+        const float ia = areas[i];
+        for (int64_t pj = pi + 1; pj < n; ++pj) {
+            const int64_t j = order[pj];
+            if (dead[j]) continue;
+            const float *bj = boxes + j * stride;
+            const float xx1 = fmaxf(bi[0], bj[0]);
+            const float yy1 = fmaxf(bi[1], bj[1]);
+            const float xx2 = fminf(bi[2], bj[2]);
+            const float yy2 = fminf(bi[3], bj[3]);
+            const float w = fmaxf(0.0, xx2 - xx1 + 1);
+            const float h = fmaxf(0.0, yy2 - yy1 + 1);
+            const float inter = w * h;
+            const float ovr = inter / (ia + areas[j] - inter);
+            if (ovr >= thresh) dead[j] = 1;
+        }
+    }
+    *num_out = kept;
+    free(dead);
+    return 0;
+}
+
+/* Exact squared Euclidean distance transform of one binary map: for every
+ * pixel, the squared distance to the nearest ZERO pixel (0 on zero pixels).
+ * Not in the reference; semantics pinned to
+ * scipy.ndimage.distance_transform_edt(map)**2 by tests/test_oracle_pin.py.
+ * A map with no zero pixel yields `big` = (H+W)^2 everywhere (documented
+ * saturation; scipy is undefined there).
+ * Method: column pass (distance to nearest zero along y), then for each pixel
+ * an outward search along x that stops once d*d >= best.  All integer. */
+void orc_edt_sq(const unsigned char *map, int H, int W, int32_t *out)
+{
+    const int32_t inf = H + W;
+    int32_t *g = (int32_t *)malloc(sizeof(int32_t) * (size_t)H * W);
+    for (int x = 0; x < W; ++x) {
+        int32_t d = inf;
+        for (int y = 0; y < H; ++y) {
+            d = map[(size_t)y * W + x] ? (d < inf ? d + 1 : inf) : 0;
+            g[(size_t)y * W + x] = d;
+        }
+        d = inf;
+        for (int y = H - 1; y >= 0; --y) {
+            d = map[(size_t)y * W + x] ? (d < inf ? d + 1 : inf) : 0;
+            if (d < g[(size_t)y * W + x]) g[(size_t)y * W + x] = d;
+        }
+    }
+    for (int y = 0; y < H; ++y) {
+        const int32_t *gr = g + (size_t)y * W;
+        for (int x = 0; x < W; ++x) {
+            int64_t best = (int64_t)gr[x] * gr[x];
+            for (int d = 1; (int64_t)d * d < best; ++d) {
+                if (x - d < 0 && x + d >= W) break;
+                if (x - d >= 0) {
+                    const int64_t v = (int64_t)d * d + (int64_t)gr[x - d] * gr[x - d];
+                    if (v < best) best = v;
+                }
+                if (x + d < W) {
+                    const int64_t v = (int64_t)d * d + (int64_t)gr[x + d] * gr[x + d];
+                    if (v < best) best = v;
+                }
+            }
+            const int64_t cap = (int64_t)inf * inf;
+            out[(size_t)y * W + x] = (int32_t)(best < cap ? best : cap);
+        }
+    }
+    free(g);
+}
+
+/* Layer ("sem-dist") target decode in closed form.
+ * Reference: amodal_train.py:236-271 (load_layer2) driving
+ * modal/Functions.py:1012-1095 (get_image_labals, objectID_to_masks,
+ * max_objectID, maskID_to_objectIDs, objIDs_to_sindistanceLayer).
+ *   label bit i (i<32)   : object i visible at this pixel
+ *   label bit 32+i       : object i present but occluded at this pixel
+ *   n_obj = first shift s such that no non-zero label has its low word's top
+ *           set bit at s (max_objectID, Functions.py:1074-1079)
+ *   channel 0 of object i      |= bit i
+ *   channel min(d, L-1)        |= bit 32+i,  d = 1 + #set bits of the high
+ *                                 word below position i (Functions.py:1050-1064,
+ *                                 amodal_train.py:253-259)
+ * out is u8 [n_max][L][H][W]; planes for i >= n_obj are zero.  Returns n_obj
+ * (not clamped to n_max).  The python restatement that loops exactly like the
+ * reference lives in oracle/oracle.py; tests pin this closed form to it. */
+int orc_layer_decode(const uint64_t *label, int H, int W, int L, int n_max,
+                     unsigned char *out)
+{
+    const size_t px = (size_t)H * W;
+    uint32_t top_seen = 0;
+    for (size_t p = 0; p < px; ++p) {
+        const uint32_t lo = (uint32_t)(label[p] & 0xffffffffu);
+        if (lo) top_seen |= 1u << (31 - __builtin_clz(lo));
+    }
+    int n_obj = 0;
+    while (n_obj < 32 && ((top_seen >> n_obj) & 1u)) ++n_obj;
+    memset(out, 0, (size_t)n_max * L * px);
+    const int n_eff = n_obj < n_max ? n_obj : n_max;
+    for (size_t p = 0; p < px; ++p) {
+        const uint64_t v = label[p];
+        if (!v) continue;
+        const uint32_t lo = (uint32_t)(v & 0xffffffffu);
+        const uint32_t hi = (uint32_t)(v >> 32);
+        for (int i = 0; i < n_eff; ++i) {
+            if ((lo >> i) & 1u) out[((size_t)i * L + 0) * px + p] = 1;
+            if ((hi >> i) & 1u) {
+                int d = 1 + __builtin_popcount(hi & ((1u << i) - 1u));
+                if (d > L - 1) d = L - 1;
+                out[((size_t)i * L + d) * px + p] = 1;
+            }
+        }
+    }
+    return n_obj;
+}

@@ -1,0 +1,139 @@
+"""Pins the oracle restatement (oracle/sln_oracle.c + oracle/oracle.py) before anything trusts it:
+  * bit-for-bit against the reference's own unmodified C (oracle/_ref, built from
+    /root/reference/roialign/roi_align/src/crop_and_resize.c and /root/reference/nms/src/nms.c);
+  * the closed-form layer decode against the loop-for-loop restatement of load_layer2;
+  * the EDT against scipy.ndimage.distance_transform_edt (the reference has no EDT).
+The reference ships no golden vectors for this path, so its compiled
+sources are the pin."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from sln_amodal_b200 import synth
+
+needs_ref = pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+
+
+def _crop_case(seed, B, C, H, W, N, outside=0.1, degenerate=0.05):
+    rng = np.random.default_rng(seed)
+    img = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    boxes = synth.roi_boxes(N, seed=seed + 1, outside_frac=outside, degenerate_frac=degenerate)
+    ind = rng.integers(0, B, N).astype(np.int32)
+    return img, boxes, ind
+
+
+@needs_ref
+@pytest.mark.parametrize("ph,pw", [(7, 7), (14, 14), (16, 16), (1, 1), (1, 5), (3, 2)])
+@pytest.mark.parametrize("C", [1, 3, 8])
+def test_crop_fwd_matches_reference_c(ph, pw, C):
+    img, boxes, ind = _crop_case(11 + ph * 3 + C, 2, C, 33, 47, 64)
+    for ext in (0.0, -2.5):
+        a = oracle.crop_and_resize_fwd(img, boxes, ind, ph, pw, ext)
+        b = oracle.ref_crop_and_resize_fwd(img, boxes, ind, ph, pw, ext)
+        assert a.tobytes() == b.tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("ph,pw", [(7, 7), (14, 14), (1, 1), (2, 5)])
+def test_crop_bwd_matches_reference_c(ph, pw):
+    img, boxes, ind = _crop_case(5 + ph, 3, 4, 29, 31, 80)
+    rng = np.random.default_rng(99)
+    g = rng.standard_normal((boxes.shape[0], 4, ph, pw), dtype=np.float32)
+    a = oracle.crop_and_resize_bwd(g, boxes, ind, img.shape)
+    b = oracle.ref_crop_and_resize_bwd(g, boxes, ind, img.shape)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_crop_integral_and_edge_samples():
+    # boxes landing exactly on pixel centres: floor == ceil, lerp == 0
+    img = np.arange(2 * 1 * 5 * 5, dtype=np.float32).reshape(2, 1, 5, 5)
+    boxes = np.array([[0, 0, 1, 1], [0.25, 0.25, 0.75, 0.75], [1, 1, 1, 1], [-0.5, 0, 0.5, 1]], np.float32)
+    ind = np.array([0, 1, 1, 0], np.int32)
+    out = oracle.crop_and_resize_fwd(img, boxes, ind, 5, 5, -1.0)
+    assert np.array_equal(out[0, 0], img[0, 0])
+    assert np.array_equal(out[1, 0, ::2, ::2], img[1, 0, 1:4, 1:4])
+    assert np.all(out[2] == img[1, 0, 4, 4])
+    assert np.all(out[3, 0, :2] == -1.0) and np.array_equal(out[3, 0, 2], img[0, 0, 0])
+    with pytest.raises(ValueError):
+        oracle.crop_and_resize_fwd(img, boxes, np.array([0, 2, 0, 0], np.int32), 2, 2)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["rpn", "uniform"])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 500, 1500])
+@pytest.mark.parametrize("ties", [False, True])
+def test_nms_matches_reference_c(kind, n, ties):
+    boxes = synth.nms_boxes(n, seed=7 + n, kind=kind)
+    scores = synth.nms_scores(n, seed=8 + n, ties=ties)
+    dets = np.concatenate([boxes, scores[:, None]], 1)
+    for thr in (0.7, 0.3):
+        a = oracle.nms(dets, thr)
+        b = oracle.ref_nms(dets, thr)
+        assert np.array_equal(a, b)
+        assert a.size >= 1
+
+
+def test_nms_rounded_boxes_and_empty():
+    assert oracle.nms(np.zeros((0, 5), np.float32), 0.5).size == 0
+    boxes = synth.nms_boxes(300, seed=3, rounded=True)
+    dets = np.concatenate([boxes, synth.nms_scores(300)[:, None]], 1)
+    k = oracle.nms(dets, 0.3)
+    assert len(set(k.tolist())) == k.size
+    # kept boxes are pairwise below threshold under the +1 convention
+    kb = boxes[k]
+    for i in range(min(20, k.size)):
+        yy1 = np.maximum(kb[i, 0], kb[:, 0]); xx1 = np.maximum(kb[i, 1], kb[:, 1])
+        yy2 = np.minimum(kb[i, 2], kb[:, 2]); xx2 = np.minimum(kb[i, 3], kb[:, 3])
+        inter = np.maximum(0, yy2 - yy1 + 1) * np.maximum(0, xx2 - xx1 + 1)
+        area = (kb[:, 2] - kb[:, 0] + 1) * (kb[:, 3] - kb[:, 1] + 1)
+        iou = inter / (area[i] + area - inter)
+        iou[i] = 0
+        assert np.all(iou < 0.3)
+
+
+@pytest.mark.parametrize("num_classes", [2, 3, 4, 6])
+def test_layer_closed_form_matches_loops(num_classes):
+    label = synth.label_map(96, 128, n=9, seed=2024 + num_classes, min_piece=16)
+    L = num_classes - 1
+    ref = oracle.layer_decode_loops(label, num_classes)     # bool [H,W,L,n]
+    out, n_obj = oracle.layer_decode(label, L, n_max=32)
+    assert ref is not None and ref.shape[3] == n_obj
+    assert np.array_equal(out[:n_obj].transpose(2, 3, 1, 0).astype(bool), ref)
+    assert not out[n_obj:].any()
+
+
+def test_layer_edge_labels():
+    # overlapping annotations: a label with two visible bits, a label that is occluded-only,
+    # and an object that is never the top visible bit (truncates n_obj, Functions.py:1074-1079)
+    label = np.zeros((8, 8), np.uint64)
+    label[0, :4] = (1 << 0) | (1 << 1)              # objects 0 and 1 both "visible"
+    label[1, :4] = (1 << 0)
+    label[2, :4] = (1 << 0) | (1 << (32 + 1)) | (1 << (32 + 3))
+    label[3, :4] = (1 << (32 + 2))                  # occluded-only piece
+    label[4, :4] = (1 << 3)                         # object 3 visible, object 2 never visible
+    for nc in (2, 3, 5):
+        ref = oracle.layer_decode_loops(label, nc)
+        out, n_obj = oracle.layer_decode(label, nc - 1, n_max=8)
+        assert n_obj == 2 and ref.shape[3] == 2
+        assert np.array_equal(out[:n_obj].transpose(2, 3, 1, 0).astype(bool), ref)
+    assert oracle.layer_decode_loops(np.zeros((4, 4), np.uint64), 3) is None
+    assert oracle.layer_decode(np.zeros((4, 4), np.uint64), 2, n_max=4)[1] == 0
+
+
+def test_edt_matches_scipy():
+    ndi = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(5)
+    cases = []
+    for H, W, p in [(1, 1, 0.5), (1, 17, 0.7), (19, 1, 0.7), (37, 53, 0.9), (64, 64, 0.995), (128, 96, 0.5)]:
+        cases.append((rng.random((H, W)) < p).astype(np.uint8))
+    lab = synth.label_map(160, 200, n=6, seed=9, min_piece=16)
+    cases.append(((lab & np.uint64(1)) != 0).astype(np.uint8))
+    cases.append(((lab >> np.uint64(33)) & np.uint64(1)).astype(np.uint8))
+    for m in cases:
+        if m.all():
+            m.flat[0] = 0
+        want = np.rint(ndi.distance_transform_edt(m) ** 2).astype(np.int64)
+        got = oracle.edt_sq(m)
+        assert np.array_equal(got.astype(np.int64), want)
+    full = np.ones((5, 7), np.uint8)
+    assert np.all(oracle.edt_sq(full) == (5 + 7) ** 2)
