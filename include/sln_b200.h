@@ -1,0 +1,157 @@
+/*
+ * sln_b200.h -- C ABI of libsln_b200.so: the B200 (sm_100a) implementation of the
+ * SLN-Amodal detection-head hot path.
+ *
+ * This is the drop-in boundary.  It replaces the reference's dead pytorch-0.4
+ * cffi builds:
+ *     roialign/roi_align/src/crop_and_resize.h:1-16       (crop_and_resize_forward/backward)
+ *     roialign/roi_align/src/crop_and_resize_gpu.h:1-16   (crop_and_resize_gpu_forward/backward)
+ *     nms/src/nms.h / nms/src/nms_cuda.h                  (cpu_nms / gpu_nms)
+ * and adds entry points for the Python-level functions of the same path
+ * (proposal_layer, pyramid_roi_align, the layer codec, the EDT).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in `_host`;
+ *   - the caller owns every buffer, including outputs and workspace; the library
+ *     never allocates, frees or retains a pointer past the call and has no global
+ *     state besides a thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises with the host (counts are returned in device memory);
+ *   - return value: SLN_OK or a negative SLN_ERR_* code; sln_last_error_string()
+ *     describes the last failure on the calling thread.  The library never exits
+ *     the process (the reference printf+exit(-1)s: crop_and_resize.c:39-42,
+ *     crop_and_resize_kernel.cu:186-191);
+ *   - boxes are (y1, x1, y2, x2); crop boxes are normalised to [0,1] over
+ *     (H-1, W-1) exactly as the reference (crop_and_resize.c:44-56).
+ */
+#ifndef SLN_B200_H
+#define SLN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SLN_API __attribute__((visibility("default")))
+#else
+#define SLN_API
+#endif
+
+#define SLN_OK              0
+#define SLN_ERR_ARG        (-1)  /* null pointer, negative size, unsupported value   */
+#define SLN_ERR_LAYOUT     (-2)  /* unsupported layout combination / misaligned ptr   */
+#define SLN_ERR_WORKSPACE  (-3)  /* workspace too small (see *_workspace_bytes)       */
+#define SLN_ERR_CUDA       (-4)  /* a CUDA runtime call or kernel launch failed       */
+
+#define SLN_LAYOUT_NCHW 0        /* [B,C,H,W] contiguous                              */
+#define SLN_LAYOUT_NHWC 1        /* [B,H,W,C] contiguous (torch channels_last)        */
+
+/* ---- library ---------------------------------------------------------- */
+SLN_API int         sln_version(void);                 /* 10000*major + 100*minor + patch   */
+SLN_API const char *sln_last_error_string(void);       /* thread-local, never NULL          */
+/* sm_count / cc (major*10+minor) / opt-in smem per block / L2 bytes of the current device. */
+SLN_API int         sln_device_info(int *sm_count, int *cc, size_t *smem_optin, size_t *l2_bytes);
+
+/* ---- RoIAlign: crop_and_resize ---------------------------------------- *
+ * Replaces crop_and_resize_[gpu_]forward (crop_and_resize.c:115-154,
+ * crop_and_resize_gpu.c:7-37).  image f32 [B,C,H,W] in `layout`; boxes f32 [N,4];
+ * box_ind i32 [N]; crops f32 [N,C,ph,pw] in the SAME layout family (NCHW -> NCHW,
+ * NHWC -> [N,ph,pw,C]).  Every output element is written (no pre-zeroing needed).
+ * Rows whose box_ind is outside [0,B) are written as zeros, like the reference GPU
+ * kernel (crop_and_resize_kernel.cu:34-38); the CPU reference exits instead.       */
+SLN_API int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, int W, int layout,
+                            const float *boxes, const int *box_ind, int N,
+                            int ph, int pw, float extrapolation_value,
+                            float *crops, void *stream);
+
+/* Replaces crop_and_resize_[gpu_]backward (crop_and_resize.c:157-252,
+ * crop_and_resize_gpu.c:40-69).  grads f32 [N,C,ph,pw] and grad_image f32 [B,C,H,W]
+ * in `layout` (NHWC only in this version; NCHW callers convert with
+ * sln_nchw_to_nhwc / sln_nhwc_to_nchw).  Deterministic: no atomics; every
+ * destination pixel sums its contributions in the reference's serial order
+ * (box, y, x, tap) so the result is bit-identical to crop_and_resize.c.
+ * grad_image is fully written (zeros included); no memset needed.                 */
+SLN_API size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B);
+SLN_API int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
+                            int C, int ph, int pw,
+                            float *grad_image, int B, int H, int W, int layout,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* Multi-level (FPN) variant for pyramid_roi_align (modal/modals.py:20-110): one
+ * launch crops every ROI from the level named by level[i] in {0..n_levels-1} and
+ * writes crops in the ORIGINAL ROI order (removes the reference's per-level
+ * nonzero/cat/sort, modals.py:70-108).  maps_host / H_host / W_host are HOST arrays
+ * of n_levels (<= 8) device pointers / sizes.  NHWC only.                           */
+SLN_API int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_host, const int *W_host,
+                         int n_levels, int B, int C,
+                         const float *boxes, const int *box_ind, const int *level, int N,
+                         int ph, int pw, float extrapolation_value,
+                         float *crops, void *stream);
+/* Backward of the above for ONE level: only ROIs with level[i] == which_level
+ * contribute (level may be NULL: all ROIs).  Same contract as sln_crop_and_resize_bwd. */
+SLN_API int sln_pyramid_crop_bwd_level(const float *grads, const float *boxes, const int *box_ind,
+                               const int *level, int which_level, int N, int C, int ph, int pw,
+                               float *grad_image, int B, int H, int W,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* Layout converters (f32).  src and dst must not alias.                            */
+SLN_API int sln_nchw_to_nhwc(const float *src, float *dst, int B, int C, int H, int W, void *stream);
+SLN_API int sln_nhwc_to_nchw(const float *src, float *dst, int B, int C, int H, int W, void *stream);
+
+/* ---- NMS --------------------------------------------------------------- *
+ * Replaces cpu_nms (nms/src/nms.c:4-69) + the pth_nms front end (nms/pth_nms.py:5-24)
+ * and gpu_nms (nms/src/nms_cuda.c:17-67).  dets f32 [n,5] rows (c0,c1,c2,c3,score)
+ * (the reference passes y1,x1,y2,x2 -- the overlap test is symmetric in the axes).
+ * Semantics are the CPU extension's, bit for bit: areas = (c3-c1+1)*(c2-c0+1) and
+ * the "+1" intersection, un-fused fp32, IEEE divide, suppress when ovr >= thresh.
+ * Visiting order: score descending, index ascending among ties (stable).
+ * class_ids (i32 [n]) may be NULL; if given, boxes only suppress boxes of the same
+ * class (the per-class loop of refine_detections, modal/Functions.py:506-525, in
+ * one call).  Outputs: keep i64 [min(n,max_keep)] = indices into dets in visiting
+ * order; *num_keep (device i32).  max_keep <= 0 means n.  Everything stays on the
+ * device; there is no host round trip (the reference copies the whole mask to the
+ * host and scans it there, nms_cuda.c:33-58).                                       */
+SLN_API size_t sln_nms_workspace_bytes(int n);
+SLN_API int sln_nms(const float *dets, const int *class_ids, int n, float thresh, int max_keep,
+            int64_t *keep, int *num_keep, void *workspace, size_t workspace_bytes,
+            void *stream);
+
+/* ---- proposal_layer ----------------------------------------------------- *
+ * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
+ * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score
+ * (stable); apply_box_deltas (:77-98); clip to [0,0,img_h,img_w] (:101-111);
+ * NMS(nms_thresh); first `proposal_count` survivors; divide by [h,w,h,w].
+ * probs f32 [A,2], deltas f32 [A,4], anchors f32 [A,4] (pixels).
+ * out_boxes f32 [proposal_count,4] (rows >= *num_out are zero-filled);
+ * *num_out device i32.  std_dev_host: 4 host floats.                               */
+SLN_API size_t sln_proposal_workspace_bytes(int A, int pre_nms_limit);
+SLN_API int sln_proposal_layer(const float *probs, const float *deltas, const float *anchors, int A,
+                       int pre_nms_limit, int proposal_count, float nms_thresh,
+                       const float *std_dev_host, float img_h, float img_w,
+                       float *out_boxes, int *num_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- sem-dist target encoding ------------------------------------------- *
+ * Layer codec: replaces AmodalDataset.load_layer2 (amodal_train.py:236-271) and the
+ * codec helpers it drives (modal/Functions.py:1012-1095).  label u64 [B,H,W] (bit i =
+ * object i visible, bit 32+i = object i occluded) -> out u8 [B,n_max,L,H,W]
+ * (planes of objects >= n_obj are zero), n_obj i32 [B] (not clamped to n_max).
+ * scratch: B u32 words of device memory (overwritten).                              */
+SLN_API int sln_layer_decode(const uint64_t *label, int B, int H, int W, int L, int n_max,
+                     uint8_t *out, int *n_obj, uint32_t *scratch, void *stream);
+
+/* Exact squared Euclidean distance transform (absent from the reference; see
+ * DESIGN.md): maps u8 [M,H,W] -> out i32 [M,H,W] = squared distance to the nearest
+ * ZERO pixel of the same map, (H+W)^2 where a map has no zero pixel.               */
+SLN_API size_t sln_edt_workspace_bytes(int M, int H, int W);
+SLN_API int sln_edt_sq(const uint8_t *maps, int M, int H, int W, int32_t *out,
+               void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLN_B200_H */

@@ -1,0 +1,278 @@
+"""Functional host layer over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function here enqueues hand-written sm_100a kernels from libsln_b200.so on the
+current torch stream.  Nothing falls back to PyTorch or the CPU: non-CUDA inputs raise.
+PyTorch only provides device memory (outputs and workspaces are torch tensors owned by
+the caller side, as the ABI requires) and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, check, lib, ptr, stream_ptr
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SlnError(f"{name} must be a CUDA tensor: this path has no CPU implementation "
+                            "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i32c(t):
+    return t.detach().to(torch.int32).contiguous()
+
+
+def is_channels_last(t) -> bool:
+    """True when the 4-D tensor's memory is [B,H,W,C]-contiguous."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# layout converters
+# ---------------------------------------------------------------------------
+def to_channels_last(x):
+    """NCHW-contiguous f32 -> same logical tensor in channels_last memory (our transpose kernel)."""
+    _require_cuda(x, "x")
+    if is_channels_last(x):
+        return x
+    x = _f32c(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(lib().sln_nchw_to_nhwc(ptr(x), ptr(out), B, Cc, H, W, stream_ptr()), "sln_nchw_to_nhwc")
+        _lib.count_launches(1)
+    return out
+
+
+def to_contiguous_nchw(x):
+    """channels_last f32 -> NCHW-contiguous (our transpose kernel)."""
+    _require_cuda(x, "x")
+    if x.is_contiguous():
+        return x
+    if not is_channels_last(x):
+        return x.contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(lib().sln_nhwc_to_nchw(ptr(x), ptr(out), B, Cc, H, W, stream_ptr()), "sln_nhwc_to_nchw")
+        _lib.count_launches(1)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# crop_and_resize
+# ---------------------------------------------------------------------------
+def crop_and_resize_forward(image, boxes, box_ind, crop_height, crop_width, extrapolation_value=0.0):
+    """crops[N,C,ph,pw] = crop_and_resize(image[B,C,H,W], boxes[N,4], box_ind[N]).
+
+    The output uses the image's memory format: channels_last in -> channels_last out (the
+    NHWC gather kernel), anything else -> NCHW kernel.  Values are identical either way."""
+    _require_cuda(image, "image")
+    _require_cuda(boxes, "boxes")
+    _require_cuda(box_ind, "box_ind")
+    if image.dim() != 4:
+        raise _lib.SlnError("image must be [B,C,H,W]")
+    boxes = _f32c(boxes).view(-1, 4)
+    box_ind = _i32c(box_ind).view(-1)
+    N = boxes.shape[0]
+    if box_ind.shape[0] != N:
+        raise _lib.SlnError("box_ind and boxes disagree on N")
+    B, Cc, H, W = image.shape
+    nhwc = is_channels_last(image) and image.dtype == torch.float32
+    if nhwc:
+        img = image.detach()
+        out = torch.empty((N, Cc, crop_height, crop_width), dtype=torch.float32, device=image.device,
+                          memory_format=torch.channels_last)
+        if N and Cc and not is_channels_last(out):        # degenerate shapes: fall to NCHW kernel
+            nhwc = False
+    if not nhwc:
+        img = _f32c(image)
+        out = torch.empty((N, Cc, crop_height, crop_width), dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        check(lib().sln_crop_and_resize_fwd(ptr(img), B, Cc, H, W, LAYOUT_NHWC if nhwc else LAYOUT_NCHW,
+                                            ptr(boxes), ptr(box_ind), N, int(crop_height), int(crop_width),
+                                            float(extrapolation_value), ptr(out), stream_ptr()),
+              "sln_crop_and_resize_fwd")
+    if N and Cc:
+        _lib.count_launches(1)
+    return out
+
+
+def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_out=None, level=None, which_level=0):
+    """grad_image[B,C,H,W] of crop_and_resize w.r.t. the image (deterministic gather kernel).
+
+    channels_last_out: memory format of the returned gradient (default: follow `grads`)."""
+    _require_cuda(grads, "grads")
+    boxes = _f32c(boxes).view(-1, 4)
+    box_ind = _i32c(box_ind).view(-1)
+    B, Cc, H, W = [int(v) for v in image_size]
+    N, Cg, ph, pw = grads.shape
+    if Cg != Cc or boxes.shape[0] != N:
+        raise _lib.SlnError("grads / boxes / image_size disagree")
+    g = grads.detach()
+    if g.dtype != torch.float32:
+        g = g.float()
+    g_cl = is_channels_last(g)
+    if channels_last_out is None:
+        channels_last_out = g_cl
+    if not g_cl:
+        g = to_channels_last(g)
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grads.device, memory_format=torch.channels_last)
+    with torch.cuda.device(grads.device):
+        ws_bytes = lib().sln_crop_and_resize_bwd_workspace_bytes(N, B)
+        ws = _workspace(ws_bytes, grads.device)
+        if level is None:
+            rc = lib().sln_crop_and_resize_bwd(ptr(g), ptr(boxes), ptr(box_ind), N, Cc, ph, pw, ptr(out), B, H, W,
+                                               LAYOUT_NHWC, ptr(ws), ws.numel(), stream_ptr())
+        else:
+            level = _i32c(level).view(-1)
+            rc = lib().sln_pyramid_crop_bwd_level(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), int(which_level), N,
+                                                  Cc, ph, pw, ptr(out), B, H, W, ptr(ws), ws.numel(), stream_ptr())
+        check(rc, "sln_crop_and_resize_bwd")
+    if out.numel():
+        _lib.count_launches(3 if N else 1)
+    if not channels_last_out:
+        out = to_contiguous_nchw(out)
+    return out
+
+
+def pyramid_crop_forward(feature_maps, boxes, box_ind, level, crop_height, crop_width, extrapolation_value=0.0):
+    """One launch for all FPN levels: feature_maps = list of channels_last [B,C,H_l,W_l] tensors,
+    level[i] in [0, len(feature_maps)) names the source map of ROI i.  Output channels_last
+    [N,C,ph,pw] in the original ROI order."""
+    maps = []
+    for m in feature_maps:
+        _require_cuda(m, "feature map")
+        maps.append(m.detach() if (is_channels_last(m) and m.dtype == torch.float32) else to_channels_last(m))
+    boxes = _f32c(boxes).view(-1, 4)
+    box_ind = _i32c(box_ind).view(-1)
+    level = _i32c(level).view(-1)
+    N = boxes.shape[0]
+    B, Cc = maps[0].shape[0], maps[0].shape[1]
+    for m in maps:
+        if m.shape[0] != B or m.shape[1] != Cc:
+            raise _lib.SlnError("feature maps disagree on batch / channels")
+    nl = len(maps)
+    out = torch.empty((N, Cc, crop_height, crop_width), dtype=torch.float32, device=boxes.device,
+                      memory_format=torch.channels_last)
+    mp = (C.c_void_p * nl)(*[m.data_ptr() for m in maps])
+    hs = (C.c_int * nl)(*[m.shape[2] for m in maps])
+    ws_ = (C.c_int * nl)(*[m.shape[3] for m in maps])
+    with torch.cuda.device(boxes.device):
+        check(lib().sln_pyramid_crop_fwd(mp, hs, ws_, nl, B, Cc, ptr(boxes), ptr(box_ind), ptr(level), N,
+                                         int(crop_height), int(crop_width), float(extrapolation_value), ptr(out),
+                                         stream_ptr()), "sln_pyramid_crop_fwd")
+    if N and Cc:
+        _lib.count_launches(1)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# NMS
+# ---------------------------------------------------------------------------
+def nms_device(dets, thresh, class_ids=None, max_keep=0):
+    """Greedy NMS fully on the device.  Returns (keep int64[n] padded, num_keep int32[1]) -- both
+    device tensors, no host sync.  keep[:num_keep] are indices into dets, score-descending."""
+    _require_cuda(dets, "dets")
+    dets = _f32c(dets)
+    if dets.dim() != 2 or dets.shape[1] != 5:
+        raise _lib.SlnError("dets must be [n,5] (y1,x1,y2,x2,score)")
+    n = dets.shape[0]
+    cls = None
+    if class_ids is not None:
+        cls = _i32c(class_ids).view(-1)
+        if cls.shape[0] != n:
+            raise _lib.SlnError("class_ids and dets disagree on n")
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=dets.device)
+    num = torch.empty(1, dtype=torch.int32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        ws = _workspace(lib().sln_nms_workspace_bytes(n), dets.device)
+        check(lib().sln_nms(ptr(dets), ptr(cls), n, float(thresh), int(max_keep), ptr(keep), ptr(num), ptr(ws),
+                            ws.numel(), stream_ptr()), "sln_nms")
+    if n:
+        _lib.count_launches(4)
+    return keep, num
+
+
+# ---------------------------------------------------------------------------
+# proposal_layer
+# ---------------------------------------------------------------------------
+def proposal_device(probs, deltas, anchors, proposal_count, nms_threshold, std_dev, image_hw, pre_nms_limit=6000):
+    """One image.  probs [A,2], deltas [A,4], anchors [A,4] (pixels).  Returns
+    (boxes f32[proposal_count,4] normalised, zero padded; num int32[1]) on the device."""
+    for t, nm in ((probs, "probs"), (deltas, "deltas"), (anchors, "anchors")):
+        _require_cuda(t, nm)
+    probs, deltas, anchors = _f32c(probs), _f32c(deltas), _f32c(anchors)
+    A = anchors.shape[0]
+    if probs.shape != (A, 2) or deltas.shape != (A, 4):
+        raise _lib.SlnError("probs/deltas/anchors shapes disagree")
+    out = torch.empty((max(int(proposal_count), 1), 4), dtype=torch.float32, device=probs.device)
+    num = torch.empty(1, dtype=torch.int32, device=probs.device)
+    sd = (C.c_float * 4)(*[float(v) for v in std_dev])
+    with torch.cuda.device(probs.device):
+        ws = _workspace(lib().sln_proposal_workspace_bytes(A, int(pre_nms_limit)), probs.device)
+        check(lib().sln_proposal_layer(ptr(probs), ptr(deltas), ptr(anchors), A, int(pre_nms_limit),
+                                       int(proposal_count), float(nms_threshold), sd, float(image_hw[0]),
+                                       float(image_hw[1]), ptr(out), ptr(num), ptr(ws), ws.numel(), stream_ptr()),
+              "sln_proposal_layer")
+    if A and proposal_count:
+        _lib.count_launches(14 if A > pre_nms_limit else 6)
+    return out[:proposal_count], num
+
+
+# ---------------------------------------------------------------------------
+# sem-dist target encoding
+# ---------------------------------------------------------------------------
+def layer_decode_device(label, L, n_max):
+    """label [B,H,W] (int64/uint64 bit patterns) -> (u8 [B,n_max,L,H,W], n_obj int32[B])."""
+    _require_cuda(label, "label")
+    if label.dtype not in (torch.int64, torch.uint64):
+        raise _lib.SlnError("label must hold 64-bit patterns (int64 or uint64)")
+    label = label.contiguous()
+    if label.dim() == 2:
+        label = label.unsqueeze(0)
+    B, H, W = label.shape
+    out = torch.empty((B, n_max, L, H, W), dtype=torch.uint8, device=label.device)
+    n_obj = torch.empty(B, dtype=torch.int32, device=label.device)
+    scratch = torch.empty(max(B, 1), dtype=torch.int32, device=label.device)
+    with torch.cuda.device(label.device):
+        check(lib().sln_layer_decode(ptr(label), B, H, W, int(L), int(n_max), ptr(out), ptr(n_obj), ptr(scratch),
+                                     stream_ptr()), "sln_layer_decode")
+    if B and H * W:
+        _lib.count_launches(2)
+    return out, n_obj
+
+
+def edt_sq_device(maps):
+    """maps u8 [...,H,W] -> i32 same shape: squared distance to the nearest zero pixel of each map."""
+    _require_cuda(maps, "maps")
+    if maps.dtype == torch.bool:
+        maps = maps.to(torch.uint8)
+    if maps.dtype != torch.uint8:
+        raise _lib.SlnError("maps must be uint8 or bool")
+    maps = maps.contiguous()
+    H, W = maps.shape[-2], maps.shape[-1]
+    M = maps.numel() // max(H * W, 1) if H * W else 0
+    out = torch.empty(maps.shape, dtype=torch.int32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        nbytes = lib().sln_edt_workspace_bytes(M, H, W)
+        ws = _workspace(nbytes, maps.device)
+        check(lib().sln_edt_sq(ptr(maps), M, H, W, ptr(out), ptr(ws), ws.numel(), stream_ptr()), "sln_edt_sq")
+    if M and H * W:
+        per = 2 * H * W
+        chunk = max(1, min(M, (48 << 20) // per))
+        _lib.count_launches(2 * ((M + chunk - 1) // chunk))
+    return out

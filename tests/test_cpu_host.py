@@ -1,0 +1,184 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/sln_b200.h declares
+(no compute calls without a GPU), the host logic of the operator mirror, the import-path shadows,
+and the multi-process sharding / gather logic over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from sln_amodal_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "sln_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sln_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 17
+    handle = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in sln_b200.h but not exported"
+    from sln_amodal_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == declared, "ctypes prototypes and header disagree"
+    assert _lib.lib().sln_version() >= 100
+    assert _lib.lib().sln_last_error_string() is not None
+
+
+def test_workspace_queries_and_arg_errors(built_lib):
+    """Pure host-side entry points: sizes and argument validation (no kernel is launched)."""
+    from sln_amodal_b200 import _lib
+    L = _lib.lib()
+    assert L.sln_nms_workspace_bytes(0) >= 0
+    n = 12000
+    assert L.sln_nms_workspace_bytes(n) >= n * ((n + 63) // 64) * 8
+    assert L.sln_crop_and_resize_bwd_workspace_bytes(8000, 8) >= 8000 * 12
+    assert L.sln_edt_workspace_bytes(320, 1024, 1024) <= (48 << 20) + 2 * 1024 * 1024
+    assert L.sln_proposal_workspace_bytes(261888, 6000) == L.sln_proposal_workspace_bytes(10 ** 6, 6000)
+    # argument validation happens before any CUDA call
+    rc = L.sln_crop_and_resize_fwd(None, 1, 1, 4, 4, 0, None, None, 1, 0, 7, 0.0, None, None)
+    assert rc == -1 and b"crop size" in L.sln_last_error_string()
+    rc = L.sln_crop_and_resize_bwd(None, None, None, 1, 1, 7, 7, None, 1, 4, 4, 0, None, 0, None)
+    assert rc == -2 and b"NHWC" in L.sln_last_error_string()
+    rc = L.sln_nms(None, None, -1, 0.5, 0, None, None, None, 0, None)
+    assert rc == -1
+    rc = L.sln_layer_decode(None, 1, 4, 4, 0, 4, None, None, None, None)
+    assert rc == -1
+
+
+def test_product_path_refuses_cpu_tensors():
+    """No CPU fallback: CPU tensors raise instead of silently running somewhere else."""
+    from sln_amodal_b200 import CropAndResizeFunction, nms, _lib
+    with pytest.raises(_lib.SlnError):
+        CropAndResizeFunction(7, 7, 0)(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4), torch.zeros(1).int())
+    with pytest.raises(_lib.SlnError):
+        nms(torch.zeros(4, 5), 0.5)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under sln_amodal_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "sln_amodal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/_ref" not in src and "libsln_oracle" not in src, f
+
+
+def test_import_path_shadows():
+    import roialign.roi_align.crop_and_resize as a
+    import roialign.roi_align.roi_align as b
+    import nms.nms_wrapper as c
+    import nms.pth_nms as d
+    import sln_amodal_b200 as s
+    assert a.CropAndResizeFunction is s.CropAndResizeFunction and a.CropAndResize is s.CropAndResize
+    assert b.RoIAlign is s.RoIAlign
+    assert c.nms is s.nms and d.pth_nms is s.pth_nms
+    f = a.CropAndResizeFunction(7, 14, 0.5)
+    assert (f.crop_height, f.crop_width, f.extrapolation_value) == (7, 14, 0.5)
+
+
+def test_install_rebinds_named_functions():
+    import types
+    import sln_amodal_b200 as s
+    model = types.ModuleType("model")
+    fn = types.ModuleType("modal.Functions")
+    md = types.ModuleType("modal.modals")
+    for m in (model, fn):
+        m.proposal_layer = m.refine_detections = m.pyramid_roi_align_image = lambda *a, **k: None
+    md.pyramid_roi_align = md.pyramid_roi_align_image = lambda *a, **k: None
+
+    class DS:
+        pass
+    done = s.install(model, fn, md, dataset_class=DS)
+    assert model.proposal_layer is s.proposal_layer and fn.proposal_layer is s.proposal_layer
+    assert md.pyramid_roi_align is s.pyramid_roi_align
+    assert model.pyramid_roi_align_image is s.pyramid_roi_align_image
+    assert DS.load_layer2 is s.load_layer2
+    assert "model.proposal_layer" in done and "DS.load_layer2" in done
+
+
+def test_roi_level_matches_oracle_on_cpu():
+    """pyramid.roi_level is plain torch; check it against the oracle's restatement of modals.py:53-64."""
+    from oracle import oracle
+    from sln_amodal_b200 import synth
+    from sln_amodal_b200.pyramid import roi_level
+    boxes = synth.roi_boxes(5000, seed=3)
+    got = roi_level(torch.from_numpy(boxes), (1024, 1024, 3)).numpy()
+    assert np.array_equal(got, oracle.roi_levels(boxes))
+    hist = np.bincount(got, minlength=6)[2:]
+    assert hist.sum() == 5000 and (hist > 0).all()
+
+
+def test_synth_generators_are_deterministic():
+    from sln_amodal_b200 import synth
+    a, b = synth.roi_boxes(100, seed=4321), synth.roi_boxes(100, seed=4321)
+    assert a.tobytes() == b.tobytes() and a.dtype == np.float32 and (a >= 0).all() and (a <= 1).all()
+    lab = synth.label_map(64, 64, n=5, seed=1, min_piece=8)
+    assert lab.dtype == np.uint64 and lab.any()
+    # writer rule: a pixel has at most one visible owner; occluded bits only under a visible one
+    lo = lab & np.uint64(0xFFFFFFFF)
+    assert np.all((lo & (lo - np.uint64(1))) == 0)
+    s = synth.nms_scores(1000, seed=8)
+    assert np.unique(s).size == 1000
+    assert np.unique(synth.nms_scores(1000, seed=8, ties=True)).size <= 256
+
+
+def test_shard_range_partitions():
+    from sln_amodal_b200.dist import shard_range
+    for n in (0, 1, 7, 16, 17):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["SLN_ROOT"])
+import torch.distributed as dist
+from sln_amodal_b200 import dist as sdist
+rank, world = sdist.init(backend="gloo")
+assert world == 2
+n_images = 5
+lo, hi = sdist.shard_range(n_images, rank, world)
+torch.manual_seed(0)
+box_ind = torch.randint(0, n_images, (200,))
+boxes = torch.rand(200, 4)
+b, ind, span = sdist.shard_rois(boxes, box_ind, n_images, rank, world)
+assert span == (lo, hi) and ((ind >= 0) & (ind < hi - lo)).all()
+total = sdist.sum_over_ranks(float(b.shape[0]))
+assert total == 200.0, total
+# per-image "detections": image i has i+1 rows filled with i
+local = [torch.full((i + 1, 6), float(i)) for i in range(lo, hi)]
+allv = sdist.gather_detections(local, max_per_image=10, width=6)
+assert len(allv) == n_images
+for i, d in enumerate(allv):
+    assert d.shape == (i + 1, 6) and (d == i).all()
+assert sdist.max_over_ranks(float(rank)) == 1.0
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, SLN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2
