@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SLN-Amodal detection-head hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (reference CPU arm)
+
+Headline metric (BASELINE.json configs[1]): RoIAlign crop_and_resize fwd+bwd ROIs/s on
+256-channel FPN P2-P5, batch 8 per GPU, 1000 ROIs/img, 7x7 and 14x14, fp32.  A "step" is one
+pass of that path over one batch: for each pool size, one pyramid forward launch plus the
+deterministic backward of every level.  `value` counts ROI crops (fwd+bwd) per second with
+inputs resident in HBM; `e2e` is the same work through the reference-facing operator
+(CropAndResizeFunction) with HOST buffers, H2D/D2H copies inside the timed region.
+The line also carries `roofline` (dominant kernel vs the measured HBM copy peak),
+`cpu_baseline` (the reference's own C ops on this host) and `extra` (NMS us @12k, proposal
+layer, layer decode, EDT) so every number of BASELINE.json's metric appears in one run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sln_amodal_b200 import synth  # noqa: E402
+
+IMAGES_PER_GPU = 8
+ROIS_PER_IMAGE = 1000
+CHANNELS = 256
+POOLS = (7, 14)
+LEVEL_SIDES = (256, 128, 64, 32)
+CPU_SAMPLE_ROIS = 500             # bounded CPU sample: the first 500 ROIs of image 0, both pools
+WORKLOAD = ("config2: RoIAlign crop_and_resize fwd+bwd, %d imgs/GPU, C=%d, FPN P2-P5 (256^2..32^2), "
+            "%d ROIs/img, pools 7x7+14x14, fp32" % (IMAGES_PER_GPU, CHANNELS, ROIS_PER_IMAGE))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(seed_shift=0):
+    n = IMAGES_PER_GPU * ROIS_PER_IMAGE
+    boxes = synth.roi_boxes(n, seed=4321 + seed_shift)
+    level = synth.fpn_level(boxes) - 2
+    box_ind = np.repeat(np.arange(IMAGES_PER_GPU, dtype=np.int32), ROIS_PER_IMAGE)
+    return boxes, box_ind, level.astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# algorithmic bytes
+# --------------------------------------------------------------------------------------
+def _distinct_taps(a1, a2, extent, crop):
+    """Per ROI: number of distinct source rows (or columns) its valid samples touch."""
+    f = np.float32
+    a1, a2 = a1.astype(f), a2.astype(f)
+    em1 = f(extent - 1)
+    scale = (a2 - a1) * em1 / f(crop - 1)
+    k = np.arange(crop, dtype=f)[None, :]
+    pos = (a1 * em1)[:, None] + k * scale[:, None]
+    valid = (pos >= 0) & (pos <= em1)
+    lo = np.floor(pos).astype(np.int64)
+    hi = np.ceil(pos).astype(np.int64)
+    vals = np.concatenate([np.where(valid, lo, -1), np.where(valid, hi, -1)], 1)
+    vals.sort(axis=1)
+    distinct = (np.diff(vals, axis=1) != 0).sum(1) + 1
+    distinct -= (vals[:, 0] == -1)          # the -1 placeholder is not a tap
+    return np.maximum(distinct, 0)
+
+
+def fwd_bytes(boxes, box_ind, level, pool):
+    total_r = 0
+    for l, side in enumerate(LEVEL_SIDES):
+        sel = level == l
+        if not sel.any():
+            continue
+        b = boxes[sel]
+        u = _distinct_taps(b[:, 0], b[:, 2], side, pool) * _distinct_taps(b[:, 1], b[:, 3], side, pool)
+        total_r += 4 * CHANNELS * min(int(u.sum()), IMAGES_PER_GPU * side * side)
+    n = boxes.shape[0]
+    return 4 * n * CHANNELS * pool * pool + total_r + 20 * n
+
+
+def bwd_bytes(n_level, side, pool):
+    return 4 * n_level * CHANNELS * pool * pool + 20 * n_level + 4 * IMAGES_PER_GPU * CHANNELS * side * side
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.t = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in o.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.05)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=10)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for nm, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from sln_amodal_b200 import _lib, ops, dist as sdist
+    from sln_amodal_b200.crop_and_resize import CropAndResizeFunction
+
+    rank, world = sdist.init()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.lib()
+
+    boxes_np, ind_np, level_np = make_workload(seed_shift=rank)
+    n_rois = boxes_np.shape[0]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    maps = [torch.randn((IMAGES_PER_GPU, CHANNELS, s, s), device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+            for s in LEVEL_SIDES]
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    box_ind = torch.from_numpy(ind_np).to(dev)
+    level = torch.from_numpy(level_np).to(dev)
+    grads = {p: torch.randn((n_rois, CHANNELS, p, p), device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+             for p in POOLS}
+    sizes = [tuple(m.shape) for m in maps]
+
+    def step():
+        for p in POOLS:
+            ops.pyramid_crop_forward(maps, boxes, box_ind, level, p, p, 0.0)
+            for l in range(4):
+                ops.crop_and_resize_backward(grads[p], boxes, box_ind, sizes[l], channels_last_out=True,
+                                             level=level, which_level=l)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launches()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = _lib.launches() - l0
+    ms_total = sdist.max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    crops_per_step = n_rois * len(POOLS) * world
+    value = crops_per_step / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timings for the roofline (separate pass, same buffers; working set >> L2)
+    def time_op(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peak, peak_src = measured_peak_gbs()
+    kernels = []
+    for p in POOLS:
+        ms = time_op(lambda: ops.pyramid_crop_forward(maps, boxes, box_ind, level, p, p, 0.0))
+        by = fwd_bytes(boxes_np, ind_np, level_np, p)
+        kernels.append({"kernel": "crop_fwd_nhwc_kernel", "what": "pyramid fwd %dx%d" % (p, p), "ms": ms,
+                        "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6})
+        for l, side in enumerate(LEVEL_SIDES):
+            ms = time_op(lambda: ops.crop_and_resize_backward(grads[p], boxes, box_ind, sizes[l], channels_last_out=True,
+                                                              level=level, which_level=l))
+            by = bwd_bytes(int((level_np == l).sum()), side, p)
+            kernels.append({"kernel": "crop_bwd_nhwc_kernel", "what": "bwd %dx%d P%d (incl. 2 prep launches)" % (p, p, l + 2),
+                            "ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6})
+    for k in kernels:
+        k["frac"] = k["achieved_gbs"] / peak
+    dom = max(kernels, key=lambda k: k["ms"])
+    step_bytes = sum(k["algorithmic_bytes"] for k in kernels)
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "what": dom["what"], "achieved": round(dom["achieved_gbs"], 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(dom["frac"], 4),
+                "traffic": None,
+                "step": {"algorithmic_bytes": step_bytes, "achieved": round(step_bytes / ms_per_step / 1e6, 1),
+                         "frac": round(step_bytes / ms_per_step / 1e6 / peak, 4),
+                         "frac_of_8TBs_nominal": round(step_bytes / ms_per_step / 1e6 / 8000.0, 4)}}
+
+    # ---- e2e: reference-facing operator with HOST buffers (pinned), copies inside the timed region
+    def pinned_like(t):
+        return torch.empty(t.shape, dtype=torch.float32, memory_format=torch.channels_last).pin_memory()
+
+    lvl_sel = [np.nonzero(level_np == l)[0] for l in range(4)]
+    h_maps = [pinned_like(m) for m in maps]
+    for hm, m in zip(h_maps, maps):
+        hm.copy_(m)
+    h_boxes = [boxes[torch.from_numpy(ix).to(dev)].cpu().pin_memory() for ix in lvl_sel]
+    h_ind = [box_ind[torch.from_numpy(ix).to(dev)].cpu().pin_memory() for ix in lvl_sel]
+    h_grads = {p: [pinned_like(grads[p][: len(ix)]) for ix in lvl_sel] for p in POOLS}
+    for p in POOLS:
+        for l, ix in enumerate(lvl_sel):
+            h_grads[p][l].copy_(grads[p][: len(ix)])
+    h_out = {p: [pinned_like(grads[p][: len(ix)]) for ix in lvl_sel] for p in POOLS}
+    h_gmaps = [pinned_like(m) for m in maps]
+    h2d = (sum(hm.numel() for hm in h_maps) + sum(t.numel() for t in h_boxes) + sum(t.numel() for t in h_ind)
+           + sum(t.numel() for p in POOLS for t in h_grads[p])) * 4
+    d2h = (sum(t.numel() for p in POOLS for t in h_out[p]) + len(POOLS) * sum(hm.numel() for hm in h_gmaps)) * 4
+
+    def e2e_step():
+        # the call a reference user makes (modals.py:96): CropAndResizeFunction(ph,pw,0)(P_l, boxes_l, ind_l), then backward
+        d_maps = [hm.to(dev, non_blocking=True).requires_grad_(True) for hm in h_maps]
+        d_boxes = [t.to(dev, non_blocking=True) for t in h_boxes]
+        d_ind = [t.to(dev, non_blocking=True) for t in h_ind]
+        for p in POOLS:
+            for l in range(4):
+                d_g = h_grads[p][l].to(dev, non_blocking=True)
+                out = CropAndResizeFunction(p, p, 0)(d_maps[l], d_boxes[l], d_ind[l])
+                out.backward(d_g)
+                h_out[p][l].copy_(out.detach(), non_blocking=True)
+                h_gmaps[l].copy_(d_maps[l].grad, non_blocking=True)
+                d_maps[l].grad = None
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    e2e_ms = sdist.max_over_ranks(a.elapsed_time(b)) / e2e_steps
+    e2e = {"value": round(crops_per_step / (e2e_ms * 1e-3), 1), "unit": "roi_crops/s", "ms_per_step": round(e2e_ms, 3),
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+           "api": "CropAndResizeFunction(ph,pw,0)(image,boxes,box_ind) + .backward per FPN level; pinned host buffers in and out"}
+    del h_maps, h_grads, h_out, h_gmaps
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0:
+        extra = side_metrics(dev, peak)
+        if world == 1:
+            cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
+
+    if rank == 0:
+        line = {
+            "metric": "roialign_fwd_bwd_roi_crops_per_s", "value": round(value, 1), "unit": "roi_crops/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "layout": "channels_last (NHWC kernels)", "rois_per_step_per_gpu": n_rois,
+                       "l2_policy": "working set 4.7 GB per step >> 126 MB L2 (no flush needed)",
+                       "sharding": "images (box_ind) across ranks; no data-path collective"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kernels],
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def side_metrics(dev, peak):
+    """The other numbers BASELINE.json's metric names: NMS us @ n boxes, proposal layer, layer decode, EDT."""
+    import torch
+    from sln_amodal_b200 import ops
+
+    def time_us(fn, reps=20, flush=None):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts)), float(np.min(ts))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    out = {"nms": [], "note": "median / min over 20 runs, CUDA events; L2 flushed between runs"}
+    for n in (1000, 2000, 4000, 6000, 8000, 12000):
+        for kind, thr in (("rpn", 0.7), ("uniform", 0.7)):
+            dets = torch.from_numpy(np.concatenate([synth.nms_boxes(n, seed=7, kind=kind), synth.nms_scores(n, seed=8)[:, None]], 1)).to(dev)
+            keep, num = ops.nms_device(dets, thr)
+            med, mn = time_us(lambda: ops.nms_device(dets, thr), flush=flush)
+            out["nms"].append({"n": n, "boxes": kind, "thresh": thr, "kept": int(num.item()), "us_median": round(med, 1),
+                               "us_min": round(mn, 1), "pairs_per_s": round(n * (n - 1) / 2 / (med * 1e-6), 0)})
+    for K in (81, 61):
+        n = 12000
+        rng = np.random.default_rng(K)
+        dets = torch.from_numpy(np.concatenate([synth.nms_boxes(n, seed=9, rounded=True), synth.nms_scores(n, seed=8)[:, None]], 1)).to(dev)
+        cls = torch.from_numpy(rng.integers(1, K, n).astype(np.int32)).to(dev)
+        med, mn = time_us(lambda: ops.nms_device(dets, 0.3, class_ids=cls), flush=flush)
+        out["nms"].append({"n": n, "boxes": "per-class K=%d rounded" % K, "thresh": 0.3, "us_median": round(med, 1), "us_min": round(mn, 1)})
+    # proposal layer, 261 888 anchors
+    A = 261888
+    rng = np.random.default_rng(31)
+    an = torch.from_numpy(synth.nms_boxes(A, seed=4, kind="rpn")).to(dev)
+    fg = rng.permutation(np.linspace(0, 1, A)).astype(np.float32)
+    probs = torch.from_numpy(np.stack([1 - fg, fg], 1).astype(np.float32)).to(dev)
+    dl = torch.from_numpy((rng.standard_normal((A, 4)) * 0.5).astype(np.float32)).to(dev)
+    med, mn = time_us(lambda: ops.proposal_device(probs, dl, an, 1000, 0.7, (0.1, 0.1, 0.2, 0.2), (1024, 1024)), flush=flush)
+    out["proposal_layer"] = {"anchors": A, "pre_nms": 6000, "post_nms": 1000, "us_median": round(med, 1), "us_min": round(mn, 1)}
+    # sem-dist encode: config 4 = 16 images x 20 instances x L planes of 1024^2
+    Bn, n_inst, L = 16, 20, 1
+    labels = np.stack([synth.label_map(1024, 1024, n=n_inst, seed=2024 + (i % 4)) for i in range(4)])
+    labels = torch.from_numpy(np.tile(labels, (Bn // 4, 1, 1)).view(np.int64)).to(dev)
+    planes, n_obj = ops.layer_decode_device(labels, L, n_inst)
+    med, mn = time_us(lambda: ops.layer_decode_device(labels, L, n_inst), reps=5)
+    by = Bn * 1024 * 1024 * (8 + n_inst * L)
+    out["layer_decode"] = {"images": Bn, "n_max": n_inst, "L": L, "us_median": round(med, 1), "algorithmic_bytes": by,
+                           "achieved_gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, 4)}
+    med, mn = time_us(lambda: ops.edt_sq_device(planes), reps=5)
+    M = Bn * n_inst * L
+    by = M * 1024 * 1024 * 5
+    out["edt"] = {"maps": M, "us_median": round(med, 1), "maps_per_s": round(M / (med * 1e-6), 1),
+                  "mpx_per_s": round(M * 1.048576 / (med * 1e-6), 1), "algorithmic_bytes": by,
+                  "achieved_gbs": round(by / med / 1e3, 1), "frac": round(by / med / 1e3 / peak, 4)}
+    del flush
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref when present: the reference's own C, unmodified)
+# --------------------------------------------------------------------------------------
+def _cpu_sample(boxes_np, ind_np, level_np):
+    sel = np.nonzero(ind_np == 0)[0][:CPU_SAMPLE_ROIS]
+    return boxes_np[sel], level_np[sel]
+
+
+def _cpu_pass(oracle, use_ref, maps_np, boxes, level, grads):
+    fwd = oracle.ref_crop_and_resize_fwd if use_ref else oracle.crop_and_resize_fwd
+    bwd = oracle.ref_crop_and_resize_bwd if use_ref else oracle.crop_and_resize_bwd
+    for p in POOLS:
+        for l in range(4):
+            ix = np.nonzero(level == l)[0]
+            if ix.size == 0:
+                continue
+            z = np.zeros(ix.size, np.int32)
+            fwd(maps_np[l], boxes[ix], z, p, p, 0.0)
+            bwd(grads[p][ix], boxes[ix], z, maps_np[l].shape)
+
+
+def cpu_reference_sample(boxes_np, ind_np, level_np, maps=None, steps=1, warmup=1):
+    from oracle import oracle
+    use_ref = oracle.ref_available()
+    if not use_ref:
+        oracle.build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    boxes, level = _cpu_sample(boxes_np, ind_np, level_np)
+    rng = np.random.default_rng(99)
+    if maps is not None:
+        maps_np = [m[:1].contiguous().cpu().numpy() for m in maps]
+    else:
+        maps_np = [rng.standard_normal((1, CHANNELS, s, s), dtype=np.float32) for s in LEVEL_SIDES]
+    grads = {p: rng.standard_normal((boxes.shape[0], CHANNELS, p, p), dtype=np.float32) for p in POOLS}
+    for _ in range(warmup):
+        _cpu_pass(oracle, use_ref, maps_np, boxes[:64], level[:64], {p: grads[p][:64] for p in POOLS})
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _cpu_pass(oracle, use_ref, maps_np, boxes, level, grads)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    crops = boxes.shape[0] * len(POOLS)
+    return {"value": round(crops / t, 1), "unit": "roi_crops/s", "cores": cores,
+            "kind": "reference" if use_ref else "port", "seconds_per_sample": round(t, 3),
+            "sample": "first %d ROIs of image 0 over P2-P5, pools 7x7+14x14, fwd+bwd through the reference's "
+                      "crop_and_resize.c (fwd OpenMP over boxes, bwd single-threaded by construction)" % boxes.shape[0],
+            "all_step_times_s": [round(x, 3) for x in ts]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    boxes_np, ind_np, level_np = make_workload()
+    warm = max(args.warmup, 1)
+    res = cpu_reference_sample(boxes_np, ind_np, level_np, None, steps=args.steps, warmup=min(warm, 2))
+    t = res["seconds_per_sample"]
+    line = {"impl": "reference", "metric": "roialign_fwd_bwd_roi_crops_per_s", "value": res["value"], "unit": "roi_crops/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": res["sample"]},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "roi_crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

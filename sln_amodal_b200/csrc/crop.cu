@@ -507,12 +507,13 @@ static int launch_transpose(const float *src, float *dst, int batch, int rows, i
 // ===========================================================================
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// max_crop: 255 for the backward (sample ranges are packed in bytes), 4096 for the forward
 static int check_crop_args(const void *image, const void *boxes, const void *box_ind, const void *out,
-                           int B, int C, int H, int W, int N, int ph, int pw)
+                           int B, int C, int H, int W, int N, int ph, int pw, int max_crop = 255)
 {
     SLN_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0 && N >= 0, SLN_ERR_ARG, "negative size");
-    SLN_REQUIRE(ph >= 1 && pw >= 1 && ph <= 255 && pw <= 255, SLN_ERR_ARG,
-                "crop size %dx%d outside [1,255]", ph, pw);
+    SLN_REQUIRE(ph >= 1 && pw >= 1 && ph <= max_crop && pw <= max_crop, SLN_ERR_ARG,
+                "crop size %dx%d outside [1,%d]", ph, pw, max_crop);
     SLN_REQUIRE(H <= 32767 && W <= 32767, SLN_ERR_ARG, "map side > 32767");
     if (N > 0 && C > 0) {
         SLN_REQUIRE(boxes && box_ind && out, SLN_ERR_ARG, "null pointer");
@@ -626,7 +627,7 @@ extern "C" int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, 
                                        const float *boxes, const int *box_ind, int N, int ph, int pw,
                                        float ext, float *crops, void *stream)
 {
-    int rc = check_crop_args(image, boxes, box_ind, crops, B, C, H, W, N, ph, pw);
+    int rc = check_crop_args(image, boxes, box_ind, crops, B, C, H, W, N, ph, pw, 4096);
     if (rc != SLN_OK) return rc;
     if (N == 0 || C == 0) return SLN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -680,7 +681,7 @@ extern "C" int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_
     SLN_REQUIRE(maps_host && H_host && W_host && level, SLN_ERR_ARG, "null pointer");
     PyramidMaps pm{};
     for (int l = 0; l < n_levels; ++l) {
-        int rc = check_crop_args(maps_host[l], boxes, box_ind, crops, B, C, H_host[l], W_host[l], N, ph, pw);
+        int rc = check_crop_args(maps_host[l], boxes, box_ind, crops, B, C, H_host[l], W_host[l], N, ph, pw, 4096);
         if (rc != SLN_OK) return rc;
         pm.map[l] = maps_host[l]; pm.H[l] = H_host[l]; pm.W[l] = W_host[l];
     }
