@@ -73,12 +73,16 @@ SLN_API int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, int
  * in `layout` (NHWC only in this version; NCHW callers convert with
  * sln_nchw_to_nhwc / sln_nhwc_to_nchw).  Deterministic: no atomics; every
  * destination pixel sums its contributions in the reference's serial order
- * (box, y, x, tap) so the result is bit-identical to crop_and_resize.c.
+ * (box, y, x, tap).  flags = 0: each term is fma(wy*wx, g, sum) -- within 1 ulp
+ * per term of the reference, bit-reproducible run to run.  flags = SLN_BWD_EXACT:
+ * each term is rounded exactly like crop_and_resize.c:241-247, which makes the
+ * result bit-identical to the reference CPU backward (about 3x the arithmetic).
  * grad_image is fully written (zeros included); no memset needed.                 */
+#define SLN_BWD_EXACT 1          /* flags bit: round every product/sum like crop_and_resize.c:241-247 */
 SLN_API size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B);
 SLN_API int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
                             int C, int ph, int pw,
-                            float *grad_image, int B, int H, int W, int layout,
+                            float *grad_image, int B, int H, int W, int layout, int flags,
                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* Multi-level (FPN) variant for pyramid_roi_align (modal/modals.py:20-110): one
@@ -95,7 +99,7 @@ SLN_API int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_hos
  * contribute (level may be NULL: all ROIs).  Same contract as sln_crop_and_resize_bwd. */
 SLN_API int sln_pyramid_crop_bwd_level(const float *grads, const float *boxes, const int *box_ind,
                                const int *level, int which_level, int N, int C, int ph, int pw,
-                               float *grad_image, int B, int H, int W,
+                               float *grad_image, int B, int H, int W, int flags,
                                void *workspace, size_t workspace_bytes, void *stream);
 
 /* Layout converters (f32).  src and dst must not alias.                            */

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsln_b200.so")
 OK = 0
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
+BWD_EXACT = 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -24,10 +25,10 @@ PROTOTYPES = {
     "sln_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "sln_crop_and_resize_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "sln_crop_and_resize_bwd_workspace_bytes": (_sz, [_i, _i]),
-    "sln_crop_and_resize_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sln_crop_and_resize_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sln_pyramid_crop_fwd": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, _vp, _vp, _vp, _i,
                                   _i, _i, _f, _vp, _vp]),
-    "sln_pyramid_crop_bwd_level": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "sln_pyramid_crop_bwd_level": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sln_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sln_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sln_nms_workspace_bytes": (_sz, [_i]),

@@ -283,21 +283,53 @@ crop_bwd_lists_kernel(const int *__restrict__ box_ind, const RoiWin *__restrict_
     }
 }
 
-constexpr int BWD_TILE = 8;            // 8x8 destination pixels per CTA
-constexpr int BWD_THREADS = 256;       // 8 warps: warp w owns tile row w
-constexpr int BWD_MAX_ROUND = 128;     // list entries examined per round (<= BWD_THREADS)
+template <bool EXACT>
+__device__ __forceinline__ float accum1(float s, float g, float wy, float wx)
+{
+    if (EXACT) return __fadd_rn(s, __fmul_rn(wx, __fmul_rn(wy, g)));   // crop_and_resize.c:241-247
+    return __fmaf_rn(__fmul_rn(wy, wx), g, s);
+}
+template <bool EXACT>
+__device__ __forceinline__ float accum(float s, float g, float wy, float wx) { return accum1<EXACT>(s, g, wy, wx); }
+template <bool EXACT>
+__device__ __forceinline__ float4 accum(float4 s, float4 g, float wy, float wx)
+{
+    return make_float4(accum1<EXACT>(s.x, g.x, wy, wx), accum1<EXACT>(s.y, g.y, wy, wx),
+                       accum1<EXACT>(s.z, g.z, wy, wx), accum1<EXACT>(s.w, g.w, wy, wx));
+}
 
-// Shared memory per round of `CH` examined list entries (dynamic):
+constexpr int BWD_TILE = 8;            // 8x8 destination pixels per CTA
+constexpr int BWD_PIX = BWD_TILE * BWD_TILE;
+constexpr int BWD_THREADS = 256;       // 8 warps: warp w owns tile row w
+constexpr int BWD_MAX_ROUND = 64;      // list entries examined per ROI round (<= BWD_THREADS)
+constexpr int BWD_CAP = 32;            // visit entries per destination pixel per visit round
+
+// Shared memory per ROI round of `CH` examined list entries (dynamic):
 //   Tap ytab[CH][ph], xtab[CH][pw]     tap tables of the accepted ROIs
 //   int roi[CH]                        accepted ROI ids, original order
 //   u16 yr[CH][8], xr[CH][8]           per tile row / column: sample range lo | hi<<8
+//   visit lists, entry-major so the 64 pixel threads write conflict-free:
+//   u32 v_sid[CAP][64]; float v_wy[CAP][64], v_wx[CAP][64]; int v_cnt[64]
 static size_t bwd_smem_bytes(int CH, int ph, int pw)
 {
-    return (size_t)CH * ((size_t)(ph + pw) * sizeof(Tap) + sizeof(int) + 2 * BWD_TILE * sizeof(unsigned short));
+    return (size_t)CH * ((size_t)(ph + pw) * sizeof(Tap) + sizeof(int) + 2 * BWD_TILE * sizeof(unsigned short)) +
+           (size_t)BWD_CAP * BWD_PIX * 12 + BWD_PIX * sizeof(int);
 }
 
-// NV = channel vectors per lane (a CTA covers 32*NV vectors; gridDim.y covers the rest).
-template <int VEC, int NV>
+// Backward kernel.  Three kinds of work, all deterministic:
+//   A  (CTA)          examine the next CH entries of this image's ROI list, keep (in order) those
+//                     whose pixel window meets the tile
+//   B  (CTA)          tap tables of the kept ROIs; per tile row/column the contiguous range of
+//                     samples that touch it
+//   B' (64 threads)   one thread per destination pixel walks the kept ROIs in order and emits
+//                     its "visits" (sample id, wy, wx) in the reference's order (ROI, y, x, tap)
+//   C  (8 warps)      warp = tile row; for each of its 8 pixels it streams the pixel's visit list:
+//                     loads issued four visits ahead, lanes = channel vectors, accumulation in
+//                     registers; every pixel is written exactly once at the end.
+// EXACT: sum += wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247 (bit-
+// identical to the reference CPU backward); otherwise sum = fma(wy*wx, g, sum) (<= 1 ulp per
+// term away, same order, still deterministic).
+template <int VEC, bool EXACT>
 __global__ void __launch_bounds__(BWD_THREADS)
 crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                      const RoiWin *__restrict__ win, const int *__restrict__ lists,
@@ -308,7 +340,11 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
     extern __shared__ __align__(16) unsigned char s_raw[];
     Tap *ytab = reinterpret_cast<Tap *>(s_raw);                          // [CH][ph]
     Tap *xtab = ytab + (size_t)CH * ph;                                  // [CH][pw]
-    int *s_roi = reinterpret_cast<int *>(xtab + (size_t)CH * pw);        // [CH]
+    unsigned *v_sid = reinterpret_cast<unsigned *>(xtab + (size_t)CH * pw);   // [CAP][64]
+    float *v_wy = reinterpret_cast<float *>(v_sid + BWD_CAP * BWD_PIX);  // [CAP][64]
+    float *v_wx = v_wy + BWD_CAP * BWD_PIX;                              // [CAP][64]
+    int *v_cnt = reinterpret_cast<int *>(v_wx + BWD_CAP * BWD_PIX);      // [64]
+    int *s_roi = v_cnt + BWD_PIX;                                        // [CH]
     unsigned short *s_yr = reinterpret_cast<unsigned short *>(s_roi + CH);   // [CH][8]
     unsigned short *s_xr = s_yr + (size_t)CH * BWD_TILE;                 // [CH][8]
     __shared__ int s_warp[8];
@@ -321,25 +357,26 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
     const int ty0 = ty_i * BWD_TILE, tx0 = tx_i * BWD_TILE;
     const int ty1 = min(ty0 + BWD_TILE, H) - 1, tx1 = min(tx0 + BWD_TILE, W) - 1;
     const int CV = C / VEC;
-    const int cvbase = blockIdx.y * (32 * NV);
+    const int cv = blockIdx.y * 32 + lane;       // this lane's channel vector
+    const bool cv_ok = cv < CV;
 
-    V acc[BWD_TILE][NV];
+    V acc[BWD_TILE];
 #pragma unroll
-    for (int p = 0; p < BWD_TILE; ++p)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[p][v] = make_splat(0.f, (V *)nullptr);
+    for (int p = 0; p < BWD_TILE; ++p) acc[p] = make_splat(0.f, (V *)nullptr);
 
     // this image's ROI list (original box order) inside the compact list array
     int list_off = 0;
     for (int i = 0; i < b; ++i) list_off += counts[i];
     const int n_list = counts[b];
     const int *__restrict__ list = lists + list_off;
-    const V *__restrict__ g = reinterpret_cast<const V *>(grads);
+    const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cv;
     const int S = ph * pw;
-    const int py = ty0 + warp;    // this warp's destination row
+    // pixel-thread role (threads 0..63): destination pixel (prow, pcol) of the tile
+    const int prow = tid >> 3, pcol = tid & 7;
+    const int ppy = ty0 + prow, ppx = tx0 + pcol;
 
     for (int scan = 0; scan < n_list; scan += CH) {
-        // ---- phase A: examine list[scan, scan+CH); keep, in order, ROIs whose window meets the tile
+        // ---- A: examine list[scan, scan+CH)
         const int li = scan + tid;
         bool take = false;
         int r = -1;
@@ -362,7 +399,7 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
         __syncthreads();
         if (n_chunk == 0) continue;     // uniform: every thread read the same s_warp values
 
-        // ---- phase B: tap tables, then per-row / per-column sample ranges of the kept ROIs
+        // ---- B: tap tables, then per-row / per-column sample ranges of the kept ROIs
         for (int i = tid; i < n_chunk * (ph + pw); i += BWD_THREADS) {
             const int q = i / (ph + pw), k = i - q * (ph + pw);
             const int rr = s_roi[q];
@@ -399,72 +436,90 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
         }
         __syncthreads();
 
-        // ---- phase C: accumulate.  warp = destination row, lanes = channel vectors.
-        // Order per destination pixel: ROI (original order), y, x, tap TL/TR/BL/BR --
-        // the reference's serial order (crop_and_resize.c:190-250).
-        if (py <= ty1) {
-            for (int q = 0; q < n_chunk; ++q) {
-                const unsigned yrng = s_yr[q * BWD_TILE + warp];
-                const int ylo = yrng & 0xff, yhi = yrng >> 8;
-                if (ylo > yhi) continue;
-                const Tap *yt = ytab + q * ph;
-                const Tap *xt = xtab + q * pw;
-                const V *gr = g + (size_t)s_roi[q] * S * CV + cvbase + lane;
+        // ---- B' / C: visit rounds.  Cursor of the pixel thread: (q, y, x, tap)
+        int cq = 0, cy = -1, cx = -1, ctap = 0;
+        for (;;) {
+            int more = 0;
+            if (tid < BWD_PIX) {
+                int cnt = 0;
+                while (cq < n_chunk) {
+                    const unsigned yrng = s_yr[cq * BWD_TILE + prow], xrng = s_xr[cq * BWD_TILE + pcol];
+                    const int ylo = yrng & 0xff, yhi = yrng >> 8, xlo = xrng & 0xff, xhi = xrng >> 8;
+                    if (ylo > yhi || xlo > xhi) { ++cq; cy = -1; continue; }
+                    if (cy < 0) { cy = ylo; cx = xlo; ctap = 0; }
+                    const unsigned sid0 = (unsigned)s_roi[cq] * (unsigned)S;
+                    bool full = false;
+                    for (; cy <= yhi && !full; ++cy) {
+                        const Tap tyy = ytab[cq * ph + cy];
+                        const bool top = (tyy.lo == ppy), bot = (tyy.lo + (tyy.lerp != 0.f) == ppy);
+                        for (; cx <= xhi && !full; ++cx) {
+                            const Tap txx = xtab[cq * pw + cx];
+                            const bool lft = (txx.lo == ppx), rgt = (txx.lo + (txx.lerp != 0.f) == ppx);
+                            for (; ctap < 4; ++ctap) {         // reference tap order TL, TR, BL, BR
+                                const bool useb = ctap >> 1, user = ctap & 1;
+                                if (!((useb ? bot : top) && (user ? rgt : lft))) continue;
+                                if (cnt == BWD_CAP) { full = true; break; }
+                                v_sid[cnt * BWD_PIX + tid] = sid0 + (unsigned)(cy * pw + cx);
+                                v_wy[cnt * BWD_PIX + tid] = useb ? tyy.lerp : __fsub_rn(1.f, tyy.lerp);
+                                v_wx[cnt * BWD_PIX + tid] = user ? txx.lerp : __fsub_rn(1.f, txx.lerp);
+                                ++cnt;
+                            }
+                            if (full) break;
+                            ctap = 0;
+                        }
+                        if (full) break;
+                        cx = xlo;
+                    }
+                    if (full) { more = 1; break; }
+                    ++cq; cy = -1;
+                }
+                v_cnt[tid] = cnt;
+            }
+            more = __syncthreads_or(more);
+
+            // ---- C: stream the visit lists.  warp = tile row, lanes = channel vectors
+            if (cv_ok) {
 #pragma unroll
                 for (int p = 0; p < BWD_TILE; ++p) {
-                    const int px = tx0 + p;
-                    const unsigned xrng = s_xr[q * BWD_TILE + p];
-                    const int xlo = xrng & 0xff, xhi = xrng >> 8;
-                    if (xlo > xhi) continue;
-                    for (int y = ylo; y <= yhi; ++y) {
-                        const Tap tyy = yt[y];
-                        const bool top = (tyy.lo == py);
-                        const bool bot = (tyy.lo + (tyy.lerp != 0.f) == py);
-                        const float wy_t = __fsub_rn(1.f, tyy.lerp), wy_b = tyy.lerp;
-                        for (int x = xlo; x <= xhi; ++x) {
-                            const Tap txx = xt[x];
-                            const bool lft = (txx.lo == px);
-                            const bool rgt = (txx.lo + (txx.lerp != 0.f) == px);
-                            const float wx_l = __fsub_rn(1.f, txx.lerp), wx_r = txx.lerp;
+                    const int pix = warp * BWD_TILE + p;
+                    const int cnt = v_cnt[pix];
+                    V a = acc[p];
+                    int i = 0;
+                    for (; i + 4 <= cnt; i += 4) {
+                        V gv[4];
+                        float wy[4], wx[4];
 #pragma unroll
-                            for (int v = 0; v < NV; ++v) {
-                                if (cvbase + lane + 32 * v < CV) {
-                                    const V gv = ldg_vec(gr + (size_t)(y * pw + x) * CV + 32 * v);
-                                    float *a = reinterpret_cast<float *>(&acc[p][v]);
-                                    const float *gg = reinterpret_cast<const float *>(&gv);
-#pragma unroll
-                                    for (int e = 0; e < VEC; ++e) {
-                                        const float dtop = __fmul_rn(wy_t, gg[e]);
-                                        const float dbot = __fmul_rn(wy_b, gg[e]);
-                                        float s = a[e];
-                                        if (top && lft) s = __fadd_rn(s, __fmul_rn(wx_l, dtop));
-                                        if (top && rgt) s = __fadd_rn(s, __fmul_rn(wx_r, dtop));
-                                        if (bot && lft) s = __fadd_rn(s, __fmul_rn(wx_l, dbot));
-                                        if (bot && rgt) s = __fadd_rn(s, __fmul_rn(wx_r, dbot));
-                                        a[e] = s;
-                                    }
-                                }
-                            }
+                        for (int u = 0; u < 4; ++u) {
+                            const unsigned sid = v_sid[(i + u) * BWD_PIX + pix];
+                            wy[u] = v_wy[(i + u) * BWD_PIX + pix];
+                            wx[u] = v_wx[(i + u) * BWD_PIX + pix];
+                            gv[u] = ldg_vec(g + (size_t)sid * CV);
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) a = accum<EXACT>(a, gv[u], wy[u], wx[u]);
                     }
+                    for (; i < cnt; ++i) {
+                        const unsigned sid = v_sid[i * BWD_PIX + pix];
+                        const V gv = ldg_vec(g + (size_t)sid * CV);
+                        a = accum<EXACT>(a, gv, v_wy[i * BWD_PIX + pix], v_wx[i * BWD_PIX + pix]);
+                    }
+                    acc[p] = a;
                 }
             }
+            if (!more) break;
+            __syncthreads();        // lists are rewritten by the next visit round
         }
-        __syncthreads();
+        __syncthreads();            // tables / lists are rewritten by the next ROI round
     }
 
     // ---- write every pixel of the tile exactly once (zeros included)
-    if (py <= ty1) {
+    const int py = ty0 + warp;
+    if (py <= ty1 && cv_ok) {
         V *__restrict__ o = reinterpret_cast<V *>(grad_image);
 #pragma unroll
         for (int p = 0; p < BWD_TILE; ++p) {
             const int px = tx0 + p;
-            if (px <= tx1) {
-                const size_t base = (((size_t)b * H + py) * W + px) * CV + cvbase + lane;
-#pragma unroll
-                for (int v = 0; v < NV; ++v)
-                    if (cvbase + lane + 32 * v < CV) __stcs(o + base + 32 * v, acc[p][v]);
-            }
+            if (px <= tx1) __stcs(o + (((size_t)b * H + py) * W + px) * CV + cv, acc[p]);
         }
     }
 }
@@ -553,18 +608,19 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
     return SLN_OK;
 }
 
-template <int VEC, int NV>
+template <int VEC, bool EXACT>
 static int launch_bwd(const float *grads, const float *boxes, const RoiWin *win, const int *lists,
                       const int *counts, int C, int ph, int pw, float *grad_image, int B, int H,
-                      int W, int chunks, cudaStream_t st)
+                      int W, cudaStream_t st)
 {
     const int tiles_x = cdiv(W, BWD_TILE), tiles_y = cdiv(H, BWD_TILE);
-    // list entries examined per round: as many as fit in ~48 KB of shared memory
-    int CH = (int)((48 * 1024) / bwd_smem_bytes(1, ph, pw));
-    if (CH > BWD_MAX_ROUND) CH = BWD_MAX_ROUND;
-    if (CH < 1) CH = 1;
+    const int chunks = cdiv(C / VEC, 32);
+    // list entries examined per ROI round: keep the CTA under ~56 KB of shared memory
+    int CH = BWD_MAX_ROUND;
+    while (CH > 1 && bwd_smem_bytes(CH, ph, pw) > 56 * 1024) CH /= 2;
     const size_t smem = bwd_smem_bytes(CH, ph, pw);
-    auto kern = crop_bwd_nhwc_kernel<VEC, NV>;
+    SLN_REQUIRE(smem <= 200 * 1024, SLN_ERR_ARG, "crop %dx%d too large for the backward kernel", ph, pw);
+    auto kern = crop_bwd_nhwc_kernel<VEC, EXACT>;
     if (smem > 48 * 1024)
         SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
@@ -583,7 +639,7 @@ static size_t bwd_ws_bytes(int N, int B)
 
 static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *level,
                          int which_level, int N, int C, int ph, int pw, float *grad_image, int B, int H,
-                         int W, void *ws, size_t ws_bytes, cudaStream_t st)
+                         int W, bool exact, void *ws, size_t ws_bytes, cudaStream_t st)
 {
     if (B == 0 || C == 0 || H == 0 || W == 0) return SLN_OK;
     SLN_REQUIRE((size_t)cdiv(W, BWD_TILE) * cdiv(H, BWD_TILE) * B < (1ull << 31), SLN_ERR_ARG, "too many tiles");
@@ -606,14 +662,12 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         SLN_LAUNCH_OK("crop_bwd_lists_kernel");
     }
     const bool vec4 = (C % 4 == 0) && aligned16(grads) && aligned16(grad_image);
-    const int CV = vec4 ? C / 4 : C;
-    // channel vectors per lane: 1, or 2 with further chunks of 64 vectors over gridDim.y
     if (vec4) {
-        if (CV <= 32) return launch_bwd<4, 1>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, 1, st);
-        return launch_bwd<4, 2>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, cdiv(CV, 64), st);
+        if (exact) return launch_bwd<4, true>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
+        return launch_bwd<4, false>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
     }
-    if (CV <= 32) return launch_bwd<1, 1>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, 1, st);
-    return launch_bwd<1, 2>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, cdiv(CV, 64), st);
+    if (exact) return launch_bwd<1, true>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
+    return launch_bwd<1, false>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
 }
 
 }  // namespace sln
@@ -661,15 +715,15 @@ extern "C" size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B)
 
 extern "C" int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
                                        int C, int ph, int pw, float *grad_image, int B, int H, int W,
-                                       int layout, void *workspace, size_t workspace_bytes, void *stream)
+                                       int layout, int flags, void *workspace, size_t workspace_bytes, void *stream)
 {
     SLN_REQUIRE(layout == SLN_LAYOUT_NHWC, SLN_ERR_LAYOUT,
                 "crop backward is NHWC-only; convert with sln_nchw_to_nhwc / sln_nhwc_to_nchw");
     int rc = check_crop_args(grad_image, boxes, box_ind, grad_image, B, C, H, W, N, ph, pw);
     if (rc != SLN_OK) return rc;
     SLN_REQUIRE(N == 0 || C == 0 || grads, SLN_ERR_ARG, "null grads");
-    return crop_bwd_nhwc(grads, boxes, box_ind, nullptr, 0, N, C, ph, pw, grad_image, B, H, W, workspace,
-                         workspace_bytes, static_cast<cudaStream_t>(stream));
+    return crop_bwd_nhwc(grads, boxes, box_ind, nullptr, 0, N, C, ph, pw, grad_image, B, H, W,
+                         (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_host, const int *W_host,
@@ -692,14 +746,14 @@ extern "C" int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_
 
 extern "C" int sln_pyramid_crop_bwd_level(const float *grads, const float *boxes, const int *box_ind,
                                           const int *level, int which_level, int N, int C, int ph, int pw,
-                                          float *grad_image, int B, int H, int W, void *workspace,
+                                          float *grad_image, int B, int H, int W, int flags, void *workspace,
                                           size_t workspace_bytes, void *stream)
 {
     int rc = check_crop_args(grad_image, boxes, box_ind, grad_image, B, C, H, W, N, ph, pw);
     if (rc != SLN_OK) return rc;
     SLN_REQUIRE(N == 0 || C == 0 || grads, SLN_ERR_ARG, "null grads");
     return crop_bwd_nhwc(grads, boxes, box_ind, level, which_level, N, C, ph, pw, grad_image, B, H, W,
-                         workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                         (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sln_nchw_to_nhwc(const float *src, float *dst, int B, int C, int H, int W, void *stream)

@@ -15,6 +15,11 @@ from . import _lib
 from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, check, lib, ptr, stream_ptr
 
 
+# Default rounding mode of the RoIAlign backward: False = fma per term (fast, <= 1e-6 relative of
+# the reference, deterministic); True = the reference's exact rounding sequence (bit-identical).
+EXACT_BACKWARD = False
+
+
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.SlnError(f"{name} must be a CUDA tensor: this path has no CPU implementation "
@@ -111,10 +116,16 @@ def crop_and_resize_forward(image, boxes, box_ind, crop_height, crop_width, extr
     return out
 
 
-def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_out=None, level=None, which_level=0):
+def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_out=None, level=None, which_level=0,
+                             exact=None):
     """grad_image[B,C,H,W] of crop_and_resize w.r.t. the image (deterministic gather kernel).
 
-    channels_last_out: memory format of the returned gradient (default: follow `grads`)."""
+    channels_last_out: memory format of the returned gradient (default: follow `grads`).
+    exact: True -> round every term like crop_and_resize.c (bit-identical to the reference CPU
+    backward); False -> fused multiply-add per term (default; see EXACT_BACKWARD)."""
+    if exact is None:
+        exact = EXACT_BACKWARD
+    flags = _lib.BWD_EXACT if exact else 0
     _require_cuda(grads, "grads")
     boxes = _f32c(boxes).view(-1, 4)
     box_ind = _i32c(box_ind).view(-1)
@@ -136,11 +147,11 @@ def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_ou
         ws = _workspace(ws_bytes, grads.device)
         if level is None:
             rc = lib().sln_crop_and_resize_bwd(ptr(g), ptr(boxes), ptr(box_ind), N, Cc, ph, pw, ptr(out), B, H, W,
-                                               LAYOUT_NHWC, ptr(ws), ws.numel(), stream_ptr())
+                                               LAYOUT_NHWC, flags, ptr(ws), ws.numel(), stream_ptr())
         else:
             level = _i32c(level).view(-1)
             rc = lib().sln_pyramid_crop_bwd_level(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), int(which_level), N,
-                                                  Cc, ph, pw, ptr(out), B, H, W, ptr(ws), ws.numel(), stream_ptr())
+                                                  Cc, ph, pw, ptr(out), B, H, W, flags, ptr(ws), ws.numel(), stream_ptr())
         check(rc, "sln_crop_and_resize_bwd")
     if out.numel():
         _lib.count_launches(3 if N else 1)

@@ -46,7 +46,7 @@ def test_workspace_queries_and_arg_errors(built_lib):
     # argument validation happens before any CUDA call
     rc = L.sln_crop_and_resize_fwd(None, 1, 1, 4, 4, 0, None, None, 1, 0, 7, 0.0, None, None)
     assert rc == -1 and b"crop size" in L.sln_last_error_string()
-    rc = L.sln_crop_and_resize_bwd(None, None, None, 1, 1, 7, 7, None, 1, 4, 4, 0, None, 0, None)
+    rc = L.sln_crop_and_resize_bwd(None, None, None, 1, 1, 7, 7, None, 1, 4, 4, 0, 0, None, 0, None)
     assert rc == -2 and b"NHWC" in L.sln_last_error_string()
     rc = L.sln_nms(None, None, -1, 0.5, 0, None, None, None, 0, None)
     assert rc == -1
