@@ -224,11 +224,31 @@ __device__ __forceinline__ void axis_window(float a1, float a2, int extent, int 
     w1 = (int)ceilf(fminf(hi, em1));
 }
 
-// prep 1: per-ROI windows
+// Supertiles: the destination map is cut into at most 8x8 supertiles per image (side a
+// multiple of the 8-pixel tile); the prep kernels build, per supertile, the ordered list
+// of ROIs whose window meets it, so a tile CTA scans tens of entries instead of the
+// whole image's ROI list.
+struct SuperGrid {
+    int side;      // pixels per supertile side
+    int nx, ny;    // supertiles per image
+};
+
+static SuperGrid super_grid(int H, int W)
+{
+    SuperGrid g;
+    int side = 32;
+    while (cdiv(H, side) > 8 || cdiv(W, side) > 8) side *= 2;
+    g.side = side;
+    g.nx = cdiv(W, side);
+    g.ny = cdiv(H, side);
+    return g;
+}
+
+// prep 1: per-ROI windows + per-supertile counts (integer atomics: order-independent)
 __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind,
                                         const int *__restrict__ level, int which_level, int N, int B,
-                                        int H, int W, int ph, int pw, RoiWin *__restrict__ win,
-                                        int *__restrict__ counts)
+                                        int H, int W, int ph, int pw, SuperGrid sg, RoiWin *__restrict__ win,
+                                        int *__restrict__ st_count)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= N) return;
@@ -242,162 +262,206 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
         axis_window(boxes[4 * r + 1], boxes[4 * r + 3], W, pw, c0, c1);
         if (a0 <= a1 && c0 <= c1) {
             w.y0 = (short)a0; w.y1 = (short)a1; w.x0 = (short)c0; w.x1 = (short)c1;
-            atomicAdd(counts + b, 1);     // integer count: order-independent
+            for (int sy = a0 / sg.side; sy <= a1 / sg.side; ++sy)
+                for (int sx = c0 / sg.side; sx <= c1 / sg.side; ++sx)
+                    atomicAdd(st_count + ((size_t)b * sg.ny + sy) * sg.nx + sx, 1);
         }
     }
     win[r] = w;
 }
 
-// prep 2: per-image ROI lists in original box order (stable partition by box_ind).
-// One CTA per image; ordered ballot compaction into one compact array: image b's
-// list starts at sum(counts[0..b-1]) (counts come from the windows kernel).
+// prep 2: exclusive scan of the supertile counts (single CTA; n_st = B*ny*nx)
+__global__ void __launch_bounds__(1024) crop_bwd_scan_kernel(const int *__restrict__ st_count, int n_st,
+                                                             int *__restrict__ st_off)
+{
+    __shared__ int s[1024];
+    __shared__ int s_carry;
+    const int t = threadIdx.x;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_st; base += 1024) {
+        const int v = base + t < n_st ? st_count[base + t] : 0;
+        s[t] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const int add = t >= off ? s[t - off] : 0;
+            __syncthreads();
+            s[t] += add;
+            __syncthreads();
+        }
+        const int carry = s_carry;
+        if (base + t < n_st) st_off[base + t] = carry + s[t] - v;
+        __syncthreads();
+        if (t == 1023) s_carry = carry + s[1023];
+        __syncthreads();
+    }
+    if (t == 0) st_off[n_st] = s_carry;
+}
+
+// prep 3: ordered fill.  One CTA per supertile scans all ROIs in index order (ballot
+// compaction keeps the original box order) and stores each hit's window.
+struct ListEntry {
+    RoiWin win;
+    int roi;
+};
+
 __global__ void __launch_bounds__(256)
-crop_bwd_lists_kernel(const int *__restrict__ box_ind, const RoiWin *__restrict__ win, int N,
-                      const int *__restrict__ counts, int *__restrict__ lists)
+crop_bwd_fill_kernel(const int *__restrict__ box_ind, const RoiWin *__restrict__ win, int N, SuperGrid sg,
+                     const int *__restrict__ st_off, ListEntry *__restrict__ entries)
 {
     __shared__ int s_warp[8];
-    const int b = blockIdx.x;
+    const int st = blockIdx.x;
+    const int sx = st % sg.nx, sy = (st / sg.nx) % sg.ny, b = st / (sg.nx * sg.ny);
+    const int y0 = sy * sg.side, y1 = y0 + sg.side - 1, x0 = sx * sg.side, x1 = x0 + sg.side - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int base = 0;
-    for (int i = 0; i < b; ++i) base += counts[i];
+    int base = st_off[st];
+    if (st_off[st + 1] == base) return;
     for (int start = 0; start < N; start += 256) {
         const int r = start + tid;
         bool take = false;
-        if (r < N) {
-            const RoiWin w = win[r];
-            take = (box_ind[r] == b) && (w.y0 <= w.y1);
+        RoiWin w;
+        if (r < N && box_ind[r] == b) {
+            w = win[r];
+            take = (w.y0 <= w.y1) && !(w.y1 < y0 || w.y0 > y1 || w.x1 < x0 || w.x0 > x1);
         }
         const unsigned m = __ballot_sync(0xffffffffu, take);
         if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
         int off = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const int c = s_warp[w];
-            if (w < warp) off += c;
+        for (int k = 0; k < 8; ++k) {
+            const int c = s_warp[k];
+            if (k < warp) off += c;
             total += c;
         }
-        if (take) lists[base + off + __popc(m & ((1u << lane) - 1u))] = r;
+        if (take) {
+            ListEntry e;
+            e.win = w;
+            e.roi = r;
+            entries[base + off + __popc(m & ((1u << lane) - 1u))] = e;
+        }
         base += total;
         __syncthreads();
     }
 }
 
 template <bool EXACT>
-__device__ __forceinline__ float accum1(float s, float g, float wy, float wx)
+__device__ __forceinline__ float accum1(float s, float g, float wy, float wx, float w)
 {
     if (EXACT) return __fadd_rn(s, __fmul_rn(wx, __fmul_rn(wy, g)));   // crop_and_resize.c:241-247
-    return __fmaf_rn(__fmul_rn(wy, wx), g, s);
+    return __fmaf_rn(w, g, s);
 }
 template <bool EXACT>
-__device__ __forceinline__ float accum(float s, float g, float wy, float wx) { return accum1<EXACT>(s, g, wy, wx); }
+__device__ __forceinline__ float accum(float s, float g, float wy, float wx, float w) { return accum1<EXACT>(s, g, wy, wx, w); }
 template <bool EXACT>
-__device__ __forceinline__ float4 accum(float4 s, float4 g, float wy, float wx)
+__device__ __forceinline__ float4 accum(float4 s, float4 g, float wy, float wx, float w)
 {
-    return make_float4(accum1<EXACT>(s.x, g.x, wy, wx), accum1<EXACT>(s.y, g.y, wy, wx),
-                       accum1<EXACT>(s.z, g.z, wy, wx), accum1<EXACT>(s.w, g.w, wy, wx));
+    return make_float4(accum1<EXACT>(s.x, g.x, wy, wx, w), accum1<EXACT>(s.y, g.y, wy, wx, w),
+                       accum1<EXACT>(s.z, g.z, wy, wx, w), accum1<EXACT>(s.w, g.w, wy, wx, w));
 }
 
-constexpr int BWD_TILE = 8;            // 8x8 destination pixels per CTA
-constexpr int BWD_PIX = BWD_TILE * BWD_TILE;
-constexpr int BWD_THREADS = 256;       // 8 warps: warp w owns tile row w
-constexpr int BWD_MAX_ROUND = 64;      // list entries examined per ROI round (<= BWD_THREADS)
-constexpr int BWD_CAP = 32;            // visit entries per destination pixel per visit round
+constexpr int BWD_ROWS = 8;            // tile rows = warps per CTA
+constexpr int BWD_THREADS = 32 * BWD_ROWS;
+constexpr int BWD_MAX_CH = 64;         // accepted ROIs staged in shared memory per round
 
-// Shared memory per ROI round of `CH` examined list entries (dynamic):
-//   Tap ytab[CH][ph], xtab[CH][pw]     tap tables of the accepted ROIs
+// Shared memory per round of at most CH accepted ROIs (dynamic):
+//   Tap ytab[CH][ph], xtab[CH][pw]     tap tables
 //   int roi[CH]                        accepted ROI ids, original order
 //   u16 yr[CH][8], xr[CH][8]           per tile row / column: sample range lo | hi<<8
-//   visit lists, entry-major so the 64 pixel threads write conflict-free:
-//   u32 v_sid[CAP][64]; float v_wy[CAP][64], v_wx[CAP][64]; int v_cnt[64]
 static size_t bwd_smem_bytes(int CH, int ph, int pw)
 {
-    return (size_t)CH * ((size_t)(ph + pw) * sizeof(Tap) + sizeof(int) + 2 * BWD_TILE * sizeof(unsigned short)) +
-           (size_t)BWD_CAP * BWD_PIX * 12 + BWD_PIX * sizeof(int);
+    return (size_t)CH * ((size_t)(ph + pw) * sizeof(Tap) + sizeof(int) + 2 * 8 * sizeof(unsigned short));
 }
 
-// Backward kernel.  Three kinds of work, all deterministic:
-//   A  (CTA)          examine the next CH entries of this image's ROI list, keep (in order) those
-//                     whose pixel window meets the tile
-//   B  (CTA)          tap tables of the kept ROIs; per tile row/column the contiguous range of
-//                     samples that touch it
-//   B' (64 threads)   one thread per destination pixel walks the kept ROIs in order and emits
-//                     its "visits" (sample id, wy, wx) in the reference's order (ROI, y, x, tap)
-//   C  (8 warps)      warp = tile row; for each of its 8 pixels it streams the pixel's visit list:
-//                     loads issued four visits ahead, lanes = channel vectors, accumulation in
-//                     registers; every pixel is written exactly once at the end.
-// EXACT: sum += wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247 (bit-
-// identical to the reference CPU backward); otherwise sum = fma(wy*wx, g, sum) (<= 1 ulp per
-// term away, same order, still deterministic).
-template <int VEC, bool EXACT>
+// Backward kernel: gather form, no atomics, every destination pixel written exactly once.
+//   CTA  = tile of 8 rows x TW columns of one image (x a channel chunk of 32*NV vectors)
+//   A    scan the supertile's ordered ROI list, keep (in order) up to CH ROIs whose window meets the tile
+//   B    tap tables of the kept ROIs; per tile row/column the contiguous range of samples touching it
+//   C    warp = tile row, lanes = channel vectors: for each kept ROI (original order), each of its
+//        samples touching the row, each pixel of the row: acc += w * g, in the reference's serial
+//        order (ROI, y, x, tap TL/TR/BL/BR; crop_and_resize.c:190-250), accumulators in registers.
+// EXACT: each term is wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247 (bit-
+// identical to the reference CPU backward); otherwise fma(wy*wx, g, acc) (<= 1 ulp per term).
+template <int VEC, int NV, int TW, bool EXACT>
 __global__ void __launch_bounds__(BWD_THREADS)
 crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
-                     const RoiWin *__restrict__ win, const int *__restrict__ lists,
-                     const int *__restrict__ counts, int C, int ph, int pw,
-                     float *__restrict__ grad_image, int B, int H, int W, int tiles_x, int tiles_y, int CH)
+                     const ListEntry *__restrict__ entries, const int *__restrict__ st_off, SuperGrid sg,
+                     int C, int ph, int pw, float *__restrict__ grad_image, int B, int H, int W,
+                     int tiles_x, int tiles_y, int CH)
 {
     using V = typename VecT<VEC>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];
     Tap *ytab = reinterpret_cast<Tap *>(s_raw);                          // [CH][ph]
     Tap *xtab = ytab + (size_t)CH * ph;                                  // [CH][pw]
-    unsigned *v_sid = reinterpret_cast<unsigned *>(xtab + (size_t)CH * pw);   // [CAP][64]
-    float *v_wy = reinterpret_cast<float *>(v_sid + BWD_CAP * BWD_PIX);  // [CAP][64]
-    float *v_wx = v_wy + BWD_CAP * BWD_PIX;                              // [CAP][64]
-    int *v_cnt = reinterpret_cast<int *>(v_wx + BWD_CAP * BWD_PIX);      // [64]
-    int *s_roi = v_cnt + BWD_PIX;                                        // [CH]
+    int *s_roi = reinterpret_cast<int *>(xtab + (size_t)CH * pw);        // [CH]
     unsigned short *s_yr = reinterpret_cast<unsigned short *>(s_roi + CH);   // [CH][8]
-    unsigned short *s_xr = s_yr + (size_t)CH * BWD_TILE;                 // [CH][8]
-    __shared__ int s_warp[8];
+    unsigned short *s_xr = s_yr + (size_t)CH * 8;                        // [CH][8]
+    __shared__ int s_warp[BWD_ROWS];
+    __shared__ int s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int t = blockIdx.x;
     const int tx_i = t % tiles_x; t /= tiles_x;
     const int ty_i = t % tiles_y; t /= tiles_y;
     const int b = t;
-    const int ty0 = ty_i * BWD_TILE, tx0 = tx_i * BWD_TILE;
-    const int ty1 = min(ty0 + BWD_TILE, H) - 1, tx1 = min(tx0 + BWD_TILE, W) - 1;
+    const int ty0 = ty_i * BWD_ROWS, tx0 = tx_i * TW;
+    const int ty1 = min(ty0 + BWD_ROWS, H) - 1, tx1 = min(tx0 + TW, W) - 1;
     const int CV = C / VEC;
-    const int cv = blockIdx.y * 32 + lane;       // this lane's channel vector
-    const bool cv_ok = cv < CV;
+    const int cvbase = blockIdx.y * (32 * NV) + lane;
 
-    V acc[BWD_TILE];
+    V acc[TW][NV];
 #pragma unroll
-    for (int p = 0; p < BWD_TILE; ++p) acc[p] = make_splat(0.f, (V *)nullptr);
+    for (int p = 0; p < TW; ++p)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[p][v] = make_splat(0.f, (V *)nullptr);
 
-    // this image's ROI list (original box order) inside the compact list array
-    int list_off = 0;
-    for (int i = 0; i < b; ++i) list_off += counts[i];
-    const int n_list = counts[b];
-    const int *__restrict__ list = lists + list_off;
-    const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cv;
+    const int st = (b * sg.ny + ty0 / sg.side) * sg.nx + tx0 / sg.side;
+    const int l0 = st_off[st], n_list = st_off[st + 1] - l0;
+    const ListEntry *__restrict__ list = entries + l0;
+    const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cvbase;
     const int S = ph * pw;
-    // pixel-thread role (threads 0..63): destination pixel (prow, pcol) of the tile
-    const int prow = tid >> 3, pcol = tid & 7;
-    const int ppy = ty0 + prow, ppx = tx0 + pcol;
+    const int py = ty0 + warp;
 
-    for (int scan = 0; scan < n_list; scan += CH) {
-        // ---- A: examine list[scan, scan+CH)
-        const int li = scan + tid;
-        bool take = false;
-        int r = -1;
-        if (tid < CH && li < n_list) {
-            r = list[li];
-            const RoiWin w = win[r];
-            take = !(w.y1 < ty0 || w.y0 > ty1 || w.x1 < tx0 || w.x0 > tx1);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int off = 0, n_chunk = 0;
+    int scan = 0;
+    while (scan < n_list) {
+        // ---- A: accumulate accepted ROIs (in order) until the round is full or the list ends
+        int n_acc = 0;
+        while (scan < n_list && n_acc < CH) {
+            const int li = scan + tid;
+            bool take = false;
+            int r = -1;
+            if (li < n_list) {
+                const ListEntry e = list[li];
+                r = e.roi;
+                take = !(e.win.y1 < ty0 || e.win.y0 > ty1 || e.win.x1 < tx0 || e.win.x0 > tx1);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (lane == 0) s_warp[warp] = __popc(m);
+            if (tid == 0) s_last = -1;
+            __syncthreads();
+            int off = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const int c = s_warp[w];
-            if (w < warp) off += c;
-            n_chunk += c;
+            for (int k = 0; k < BWD_ROWS; ++k) {
+                const int c = s_warp[k];
+                if (k < warp) off += c;
+                total += c;
+            }
+            const int slot = n_acc + off + __popc(m & ((1u << lane) - 1u));
+            if (take && slot < CH) s_roi[slot] = r;
+            const bool overflow = n_acc + total > CH;
+            if (overflow && take && slot == CH - 1) s_last = li;     // last entry that still fits
+            __syncthreads();
+            if (overflow) {
+                scan = s_last + 1;
+                n_acc = CH;
+            } else {
+                scan += BWD_THREADS;
+                n_acc += total;
+            }
+            // s_warp / s_last are rewritten next iteration only after the barrier above
         }
-        if (take) s_roi[off + __popc(m & ((1u << lane) - 1u))] = r;
-        __syncthreads();
-        if (n_chunk == 0) continue;     // uniform: every thread read the same s_warp values
+        if (n_acc == 0) break;
+        const int n_chunk = n_acc;
 
         // ---- B: tap tables, then per-row / per-column sample ranges of the kept ROIs
         for (int i = tid; i < n_chunk * (ph + pw); i += BWD_THREADS) {
@@ -412,10 +476,10 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
             }
         }
         __syncthreads();
-        for (int i = tid; i < n_chunk * 2 * BWD_TILE; i += BWD_THREADS) {
-            const int q = i / (2 * BWD_TILE), j = i - q * (2 * BWD_TILE);
-            const bool isx = j >= BWD_TILE;
-            const int jj = isx ? j - BWD_TILE : j;
+        for (int i = tid; i < n_chunk * (BWD_ROWS + TW); i += BWD_THREADS) {
+            const int q = i / (BWD_ROWS + TW), j = i - q * (BWD_ROWS + TW);
+            const bool isx = j >= BWD_ROWS;
+            const int jj = isx ? j - BWD_ROWS : j;
             const int pix = (isx ? tx0 : ty0) + jj;
             const Tap *tab = isx ? (xtab + q * pw) : (ytab + q * ph);
             const int cnt = isx ? pw : ph;
@@ -432,94 +496,75 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
                 }
             }
             const unsigned short packed = any ? (unsigned short)(lo | (hi << 8)) : (unsigned short)0x00ff;
-            (isx ? s_xr : s_yr)[q * BWD_TILE + jj] = packed;
+            (isx ? s_xr : s_yr)[q * 8 + jj] = packed;
         }
         __syncthreads();
 
-        // ---- B' / C: visit rounds.  Cursor of the pixel thread: (q, y, x, tap)
-        int cq = 0, cy = -1, cx = -1, ctap = 0;
-        for (;;) {
-            int more = 0;
-            if (tid < BWD_PIX) {
-                int cnt = 0;
-                while (cq < n_chunk) {
-                    const unsigned yrng = s_yr[cq * BWD_TILE + prow], xrng = s_xr[cq * BWD_TILE + pcol];
-                    const int ylo = yrng & 0xff, yhi = yrng >> 8, xlo = xrng & 0xff, xhi = xrng >> 8;
-                    if (ylo > yhi || xlo > xhi) { ++cq; cy = -1; continue; }
-                    if (cy < 0) { cy = ylo; cx = xlo; ctap = 0; }
-                    const unsigned sid0 = (unsigned)s_roi[cq] * (unsigned)S;
-                    bool full = false;
-                    for (; cy <= yhi && !full; ++cy) {
-                        const Tap tyy = ytab[cq * ph + cy];
-                        const bool top = (tyy.lo == ppy), bot = (tyy.lo + (tyy.lerp != 0.f) == ppy);
-                        for (; cx <= xhi && !full; ++cx) {
-                            const Tap txx = xtab[cq * pw + cx];
-                            const bool lft = (txx.lo == ppx), rgt = (txx.lo + (txx.lerp != 0.f) == ppx);
-                            for (; ctap < 4; ++ctap) {         // reference tap order TL, TR, BL, BR
-                                const bool useb = ctap >> 1, user = ctap & 1;
-                                if (!((useb ? bot : top) && (user ? rgt : lft))) continue;
-                                if (cnt == BWD_CAP) { full = true; break; }
-                                v_sid[cnt * BWD_PIX + tid] = sid0 + (unsigned)(cy * pw + cx);
-                                v_wy[cnt * BWD_PIX + tid] = useb ? tyy.lerp : __fsub_rn(1.f, tyy.lerp);
-                                v_wx[cnt * BWD_PIX + tid] = user ? txx.lerp : __fsub_rn(1.f, txx.lerp);
-                                ++cnt;
+        // ---- C: accumulate
+        if (py <= ty1) {
+            for (int q = 0; q < n_chunk; ++q) {
+                const unsigned yrng = s_yr[q * 8 + warp];
+                const int ylo = yrng & 0xff, yhi = yrng >> 8;
+                if (ylo > yhi) continue;
+                const Tap *yt = ytab + q * ph;
+                const Tap *xt = xtab + q * pw;
+                const V *gr = g + (size_t)s_roi[q] * S * CV;
+#pragma unroll
+                for (int p = 0; p < TW; ++p) {
+                    const int px = tx0 + p;
+                    const unsigned xrng = s_xr[q * 8 + p];
+                    const int xlo = xrng & 0xff, xhi = xrng >> 8;
+                    if (xlo > xhi) continue;
+                    for (int y = ylo; y <= yhi; ++y) {
+                        const Tap tyy = yt[y];
+                        const bool top = (tyy.lo == py);
+                        const bool bot = (tyy.lo + (tyy.lerp != 0.f) == py);
+                        const float wy_t = __fsub_rn(1.f, tyy.lerp), wy_b = tyy.lerp;
+                        for (int x = xlo; x <= xhi; ++x) {
+                            const Tap txx = xt[x];
+                            const bool lft = (txx.lo == px);
+                            const bool rgt = (txx.lo + (txx.lerp != 0.f) == px);
+                            const float wx_l = __fsub_rn(1.f, txx.lerp), wx_r = txx.lerp;
+                            V gv[NV];
+#pragma unroll
+                            for (int v = 0; v < NV; ++v)
+                                if (cvbase + 32 * v < CV) gv[v] = ldg_vec(gr + (size_t)(y * pw + x) * CV + 32 * v);
+                            if (top != bot && lft != rgt) {          // the generic case: exactly one tap lands here
+                                const float wy = top ? wy_t : wy_b, wx = lft ? wx_l : wx_r;
+                                const float w = __fmul_rn(wy, wx);
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) acc[p][v] = accum<EXACT>(acc[p][v], gv[v], wy, wx, w);
+                            } else {                                  // integral sample position: several taps coincide
+#pragma unroll
+                                for (int tap = 0; tap < 4; ++tap) {  // reference order TL, TR, BL, BR
+                                    const bool hit = ((tap >> 1) ? bot : top) && ((tap & 1) ? rgt : lft);
+                                    if (hit) {
+                                        const float wy = (tap >> 1) ? wy_b : wy_t, wx = (tap & 1) ? wx_r : wx_l;
+                                        const float w = __fmul_rn(wy, wx);
+#pragma unroll
+                                        for (int v = 0; v < NV; ++v) acc[p][v] = accum<EXACT>(acc[p][v], gv[v], wy, wx, w);
+                                    }
+                                }
                             }
-                            if (full) break;
-                            ctap = 0;
                         }
-                        if (full) break;
-                        cx = xlo;
                     }
-                    if (full) { more = 1; break; }
-                    ++cq; cy = -1;
-                }
-                v_cnt[tid] = cnt;
-            }
-            more = __syncthreads_or(more);
-
-            // ---- C: stream the visit lists.  warp = tile row, lanes = channel vectors
-            if (cv_ok) {
-#pragma unroll
-                for (int p = 0; p < BWD_TILE; ++p) {
-                    const int pix = warp * BWD_TILE + p;
-                    const int cnt = v_cnt[pix];
-                    V a = acc[p];
-                    int i = 0;
-                    for (; i + 4 <= cnt; i += 4) {
-                        V gv[4];
-                        float wy[4], wx[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned sid = v_sid[(i + u) * BWD_PIX + pix];
-                            wy[u] = v_wy[(i + u) * BWD_PIX + pix];
-                            wx[u] = v_wx[(i + u) * BWD_PIX + pix];
-                            gv[u] = ldg_vec(g + (size_t)sid * CV);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) a = accum<EXACT>(a, gv[u], wy[u], wx[u]);
-                    }
-                    for (; i < cnt; ++i) {
-                        const unsigned sid = v_sid[i * BWD_PIX + pix];
-                        const V gv = ldg_vec(g + (size_t)sid * CV);
-                        a = accum<EXACT>(a, gv, v_wy[i * BWD_PIX + pix], v_wx[i * BWD_PIX + pix]);
-                    }
-                    acc[p] = a;
                 }
             }
-            if (!more) break;
-            __syncthreads();        // lists are rewritten by the next visit round
         }
-        __syncthreads();            // tables / lists are rewritten by the next ROI round
+        __syncthreads();            // tables are rewritten by the next round
     }
 
     // ---- write every pixel of the tile exactly once (zeros included)
-    const int py = ty0 + warp;
-    if (py <= ty1 && cv_ok) {
+    if (py <= ty1) {
         V *__restrict__ o = reinterpret_cast<V *>(grad_image);
 #pragma unroll
-        for (int p = 0; p < BWD_TILE; ++p) {
+        for (int p = 0; p < TW; ++p) {
             const int px = tx0 + p;
-            if (px <= tx1) __stcs(o + (((size_t)b * H + py) * W + px) * CV + cv, acc[p]);
+            if (px <= tx1) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    if (cvbase + 32 * v < CV) __stcs(o + (((size_t)b * H + py) * W + px) * CV + cvbase + 32 * v, acc[p][v]);
+            }
         }
     }
 }
@@ -608,66 +653,91 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
     return SLN_OK;
 }
 
-template <int VEC, bool EXACT>
-static int launch_bwd(const float *grads, const float *boxes, const RoiWin *win, const int *lists,
-                      const int *counts, int C, int ph, int pw, float *grad_image, int B, int H,
-                      int W, cudaStream_t st)
+struct BwdWs {
+    RoiWin *win;
+    int *st_count;
+    int *st_off;
+    ListEntry *entries;
+};
+
+static size_t bwd_ws_bytes(int N, int B)
 {
-    const int tiles_x = cdiv(W, BWD_TILE), tiles_y = cdiv(H, BWD_TILE);
-    const int chunks = cdiv(C / VEC, 32);
-    // list entries examined per ROI round: keep the CTA under ~56 KB of shared memory
-    int CH = BWD_MAX_ROUND;
-    while (CH > 1 && bwd_smem_bytes(CH, ph, pw) > 56 * 1024) CH /= 2;
+    // every ROI can meet at most 64 supertiles of its image
+    return align_up(sizeof(RoiWin) * (size_t)N, 256) + 2 * align_up(sizeof(int) * ((size_t)B * 64 + 1), 256) +
+           align_up(sizeof(ListEntry) * (size_t)N * 64, 256);
+}
+
+template <int VEC, int NV, int TW, bool EXACT>
+static int launch_bwd(const float *grads, const float *boxes, const BwdWs &ws, SuperGrid sg, int C, int ph, int pw,
+                      float *grad_image, int B, int H, int W, cudaStream_t st)
+{
+    const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, BWD_ROWS);
+    const int chunks = cdiv(C / VEC, 32 * NV);
+    int CH = BWD_MAX_CH;
+    while (CH > 1 && bwd_smem_bytes(CH, ph, pw) > 40 * 1024) CH /= 2;
     const size_t smem = bwd_smem_bytes(CH, ph, pw);
     SLN_REQUIRE(smem <= 200 * 1024, SLN_ERR_ARG, "crop %dx%d too large for the backward kernel", ph, pw);
-    auto kern = crop_bwd_nhwc_kernel<VEC, EXACT>;
+    auto kern = crop_bwd_nhwc_kernel<VEC, NV, TW, EXACT>;
     if (smem > 48 * 1024)
         SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
+    SLN_REQUIRE((size_t)tiles_x * tiles_y * B < (1ull << 31), SLN_ERR_ARG, "too many tiles");
     dim3 grid((unsigned)((size_t)tiles_x * tiles_y * B), chunks);
-    kern<<<grid, BWD_THREADS, smem, st>>>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W,
+    kern<<<grid, BWD_THREADS, smem, st>>>(grads, boxes, ws.entries, ws.st_off, sg, C, ph, pw, grad_image, B, H, W,
                                            tiles_x, tiles_y, CH);
     SLN_LAUNCH_OK("crop_bwd_nhwc_kernel");
     return SLN_OK;
 }
 
-static size_t bwd_ws_bytes(int N, int B)
+template <int VEC, bool EXACT>
+static int dispatch_bwd(const float *grads, const float *boxes, const BwdWs &ws, SuperGrid sg, int C, int ph, int pw,
+                        float *grad_image, int B, int H, int W, cudaStream_t st)
 {
-    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(int) * (size_t)N, 256) +
-           align_up(sizeof(int) * (size_t)(B + 1), 256);
+    const int CV = C / VEC;
+    // two channel vectors per lane halve the control work per byte, but also the CTA count:
+    // only use them when the map alone provides enough tiles to fill the machine
+    const long long tiles4 = (long long)cdiv(W, 4) * cdiv(H, BWD_ROWS) * B;
+    if (CV > 32 && tiles4 >= 6LL * sm_count())
+        return launch_bwd<VEC, 2, 4, EXACT>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+    return launch_bwd<VEC, 1, 4, EXACT>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
 }
 
 static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *level,
                          int which_level, int N, int C, int ph, int pw, float *grad_image, int B, int H,
-                         int W, bool exact, void *ws, size_t ws_bytes, cudaStream_t st)
+                         int W, bool exact, void *wsp, size_t ws_bytes, cudaStream_t st)
 {
     if (B == 0 || C == 0 || H == 0 || W == 0) return SLN_OK;
-    SLN_REQUIRE((size_t)cdiv(W, BWD_TILE) * cdiv(H, BWD_TILE) * B < (1ull << 31), SLN_ERR_ARG, "too many tiles");
     SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B), SLN_ERR_WORKSPACE, "crop bwd workspace: need %zu bytes, got %zu",
                 bwd_ws_bytes(N, B), ws_bytes);
-    SLN_REQUIRE(ws != nullptr, SLN_ERR_WORKSPACE, "null workspace");
-    unsigned char *p = static_cast<unsigned char *>(ws);
-    RoiWin *win = reinterpret_cast<RoiWin *>(p);
-    p += align_up(sizeof(RoiWin) * (size_t)N, 256);
-    int *lists = reinterpret_cast<int *>(p);
-    p += align_up(sizeof(int) * (size_t)N, 256);
-    int *counts = reinterpret_cast<int *>(p);
+    SLN_REQUIRE(wsp != nullptr, SLN_ERR_WORKSPACE, "null workspace");
+    unsigned char *p = static_cast<unsigned char *>(wsp);
+    BwdWs ws;
+    ws.win = reinterpret_cast<RoiWin *>(p);        p += align_up(sizeof(RoiWin) * (size_t)N, 256);
+    ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * ((size_t)B * 64 + 1), 256);
+    ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * ((size_t)B * 64 + 1), 256);
+    ws.entries = reinterpret_cast<ListEntry *>(p);
+    const SuperGrid sg = super_grid(H, W);
+    const int n_st = B * sg.nx * sg.ny;
 
-    SLN_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)(B + 1), st));
+    SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
     if (N > 0) {
-        crop_bwd_windows_kernel<<<cdiv(N, 256), 256, 0, st>>>(boxes, box_ind, level, which_level, N, B, H, W,
-                                                             ph, pw, win, counts);
+        crop_bwd_windows_kernel<<<cdiv(N, 256), 256, 0, st>>>(boxes, box_ind, level, which_level, N, B, H, W, ph, pw,
+                                                             sg, ws.win, ws.st_count);
         SLN_LAUNCH_OK("crop_bwd_windows_kernel");
-        crop_bwd_lists_kernel<<<B, 256, 0, st>>>(box_ind, win, N, counts, lists);
-        SLN_LAUNCH_OK("crop_bwd_lists_kernel");
+    }
+    crop_bwd_scan_kernel<<<1, 1024, 0, st>>>(ws.st_count, n_st, ws.st_off);
+    SLN_LAUNCH_OK("crop_bwd_scan_kernel");
+    if (N > 0) {
+        crop_bwd_fill_kernel<<<n_st, 256, 0, st>>>(box_ind, ws.win, N, sg, ws.st_off, ws.entries);
+        SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
     const bool vec4 = (C % 4 == 0) && aligned16(grads) && aligned16(grad_image);
     if (vec4) {
-        if (exact) return launch_bwd<4, true>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
-        return launch_bwd<4, false>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
+        if (exact) return dispatch_bwd<4, true>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+        return dispatch_bwd<4, false>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
     }
-    if (exact) return launch_bwd<1, true>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
-    return launch_bwd<1, false>(grads, boxes, win, lists, counts, C, ph, pw, grad_image, B, H, W, st);
+    if (exact) return dispatch_bwd<1, true>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+    return dispatch_bwd<1, false>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
 }
 
 }  // namespace sln

@@ -154,7 +154,7 @@ def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_ou
                                                   Cc, ph, pw, ptr(out), B, H, W, flags, ptr(ws), ws.numel(), stream_ptr())
         check(rc, "sln_crop_and_resize_bwd")
     if out.numel():
-        _lib.count_launches(3 if N else 1)
+        _lib.count_launches(4 if N else 2)
     if not channels_last_out:
         out = to_contiguous_nchw(out)
     return out
