@@ -95,12 +95,15 @@ SLN_API int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_hos
                          const float *boxes, const int *box_ind, const int *level, int N,
                          int ph, int pw, float extrapolation_value,
                          float *crops, void *stream);
-/* Backward of the above for ONE level: only ROIs with level[i] == which_level
- * contribute (level may be NULL: all ROIs).  Same contract as sln_crop_and_resize_bwd. */
-SLN_API int sln_pyramid_crop_bwd_level(const float *grads, const float *boxes, const int *box_ind,
-                               const int *level, int which_level, int N, int C, int ph, int pw,
-                               float *grad_image, int B, int H, int W, int flags,
-                               void *workspace, size_t workspace_bytes, void *stream);
+/* Backward of the above for ALL levels in one call: grads f32 [N,ph,pw,C] (NHWC) are
+ * routed by level[i] into grad_maps_host[level[i]] (NHWC [B,H_l,W_l,C], fully written).
+ * One prep pass + one gather kernel cover every level.  Same determinism / flags contract
+ * as sln_crop_and_resize_bwd.                                                          */
+SLN_API size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels);
+SLN_API int sln_pyramid_crop_bwd(const float *grads, const float *boxes, const int *box_ind, const int *level,
+                         int N, int C, int ph, int pw,
+                         float *const *grad_maps_host, const int *H_host, const int *W_host, int n_levels,
+                         int B, int flags, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Layout converters (f32).  src and dst must not alias.                            */
 SLN_API int sln_nchw_to_nhwc(const float *src, float *dst, int B, int C, int H, int W, void *stream);

@@ -224,10 +224,9 @@ __device__ __forceinline__ void axis_window(float a1, float a2, int extent, int 
     w1 = (int)ceilf(fminf(hi, em1));
 }
 
-// Supertiles: the destination map is cut into at most 8x8 supertiles per image (side a
-// multiple of the 8-pixel tile); the prep kernels build, per supertile, the ordered list
-// of ROIs whose window meets it, so a tile CTA scans tens of entries instead of the
-// whole image's ROI list.
+// Supertiles: every destination map is cut into at most 8x8 supertiles per image (side a
+// multiple of 32 pixels); the prep kernels build, per supertile, the ordered list of ROIs
+// whose window meets it, so a warp scans tens of entries instead of the whole ROI list.
 struct SuperGrid {
     int side;      // pixels per supertile side
     int nx, ny;    // supertiles per image
@@ -244,92 +243,118 @@ static SuperGrid super_grid(int H, int W)
     return g;
 }
 
-// prep 1: per-ROI windows + per-supertile counts (integer atomics: order-independent)
+constexpr int BWD_MAX_LEVELS = 8;
+
+struct BwdLevel {
+    float *out;        // grad map of this level, NHWC [B,H,W,C]
+    int H, W;
+    int tiles_x, tiles_y;
+    SuperGrid sg;
+    int st_base;       // first supertile id of this level
+    int tile_base;     // first tile (CTA) id of this level
+};
+
+struct BwdParams {
+    BwdLevel lv[BWD_MAX_LEVELS];
+    int n_levels;
+};
+
+struct ListEntry {
+    RoiWin win;
+    int roi;
+};
+
+// static-index copy of P.lv[l] (dynamic indexing would spill the parameter struct)
+__device__ __forceinline__ BwdLevel pick_level(const BwdParams &P, int l)
+{
+    BwdLevel r = P.lv[0];
+#pragma unroll
+    for (int k = 1; k < BWD_MAX_LEVELS; ++k)
+        if (k == l) r = P.lv[k];
+    return r;
+}
+
+// prep 1: per-ROI pixel window on its level + per-supertile counts (integer atomics:
+// order-independent result)
 __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind,
-                                        const int *__restrict__ level, int which_level, int N, int B,
-                                        int H, int W, int ph, int pw, SuperGrid sg, RoiWin *__restrict__ win,
-                                        int *__restrict__ st_count)
+                                        const int *__restrict__ level, int N, int B, int ph, int pw,
+                                        BwdParams P, RoiWin *__restrict__ win, int *__restrict__ st_count)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= N) return;
     RoiWin w;
     w.y0 = 1; w.y1 = 0; w.x0 = 1; w.x1 = 0;
     const int b = box_ind[r];
-    const bool use = (b >= 0 && b < B) && (level == nullptr || level[r] == which_level);
-    if (use) {
+    const int l = level ? level[r] : 0;
+    if (b >= 0 && b < B && l >= 0 && l < P.n_levels) {
+        const BwdLevel L = pick_level(P, l);
         int a0, a1, c0, c1;
-        axis_window(boxes[4 * r + 0], boxes[4 * r + 2], H, ph, a0, a1);
-        axis_window(boxes[4 * r + 1], boxes[4 * r + 3], W, pw, c0, c1);
+        axis_window(boxes[4 * r + 0], boxes[4 * r + 2], L.H, ph, a0, a1);
+        axis_window(boxes[4 * r + 1], boxes[4 * r + 3], L.W, pw, c0, c1);
         if (a0 <= a1 && c0 <= c1) {
             w.y0 = (short)a0; w.y1 = (short)a1; w.x0 = (short)c0; w.x1 = (short)c1;
-            for (int sy = a0 / sg.side; sy <= a1 / sg.side; ++sy)
-                for (int sx = c0 / sg.side; sx <= c1 / sg.side; ++sx)
-                    atomicAdd(st_count + ((size_t)b * sg.ny + sy) * sg.nx + sx, 1);
+            for (int sy = a0 / L.sg.side; sy <= a1 / L.sg.side; ++sy)
+                for (int sx = c0 / L.sg.side; sx <= c1 / L.sg.side; ++sx)
+                    atomicAdd(st_count + L.st_base + (b * L.sg.ny + sy) * L.sg.nx + sx, 1);
         }
     }
     win[r] = w;
 }
 
-// prep 2: exclusive scan of the supertile counts (single CTA; n_st = B*ny*nx)
-__global__ void __launch_bounds__(1024) crop_bwd_scan_kernel(const int *__restrict__ st_count, int n_st,
-                                                             int *__restrict__ st_off)
-{
-    __shared__ int s[1024];
-    __shared__ int s_carry;
-    const int t = threadIdx.x;
-    if (t == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n_st; base += 1024) {
-        const int v = base + t < n_st ? st_count[base + t] : 0;
-        s[t] = v;
-        __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {
-            const int add = t >= off ? s[t - off] : 0;
-            __syncthreads();
-            s[t] += add;
-            __syncthreads();
-        }
-        const int carry = s_carry;
-        if (base + t < n_st) st_off[base + t] = carry + s[t] - v;
-        __syncthreads();
-        if (t == 1023) s_carry = carry + s[1023];
-        __syncthreads();
-    }
-    if (t == 0) st_off[n_st] = s_carry;
-}
+// prep 2: ordered fill.  One CTA per supertile: its list offset is the sum of the counts of
+// the supertiles before it; it then scans all ROIs in index order (ballot compaction keeps
+// the original box order) and stores each hit with its window.  st_off[st] is published
+// for the main kernel.
+constexpr int FILL_THREADS = 1024;
 
-// prep 3: ordered fill.  One CTA per supertile scans all ROIs in index order (ballot
-// compaction keeps the original box order) and stores each hit's window.
-struct ListEntry {
-    RoiWin win;
-    int roi;
-};
-
-__global__ void __launch_bounds__(256)
-crop_bwd_fill_kernel(const int *__restrict__ box_ind, const RoiWin *__restrict__ win, int N, SuperGrid sg,
-                     const int *__restrict__ st_off, ListEntry *__restrict__ entries)
+__global__ void __launch_bounds__(FILL_THREADS)
+crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ level,
+                     const RoiWin *__restrict__ win, int N, BwdParams P, const int *__restrict__ st_count,
+                     int *__restrict__ st_off, ListEntry *__restrict__ entries)
 {
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[FILL_THREADS / 32];
+    __shared__ int s_base;
     const int st = blockIdx.x;
-    const int sx = st % sg.nx, sy = (st / sg.nx) % sg.ny, b = st / (sg.nx * sg.ny);
-    const int y0 = sy * sg.side, y1 = y0 + sg.side - 1, x0 = sx * sg.side, x1 = x0 + sg.side - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int base = st_off[st];
-    if (st_off[st + 1] == base) return;
-    for (int start = 0; start < N; start += 256) {
+    // offset = sum of counts before st
+    int part = 0;
+    for (int i = tid; i < st; i += FILL_THREADS) part += st_count[i];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int k = 0; k < FILL_THREADS / 32; ++k) t += s_warp[k];
+        s_base = t;
+        st_off[st] = t;
+    }
+    __syncthreads();
+    int base = s_base;
+    const int mine = st_count[st];
+    if (mine == 0) return;
+    // which level / image / supertile is this?
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < BWD_MAX_LEVELS; ++k)
+        if (k < P.n_levels && st >= P.lv[k].st_base) l = k;
+    const BwdLevel L = pick_level(P, l);
+    const int local = st - L.st_base;
+    const int sx = local % L.sg.nx, sy = (local / L.sg.nx) % L.sg.ny, b = local / (L.sg.nx * L.sg.ny);
+    const int y0 = sy * L.sg.side, y1 = y0 + L.sg.side - 1, x0 = sx * L.sg.side, x1 = x0 + L.sg.side - 1;
+    for (int start = 0; start < N; start += FILL_THREADS) {
         const int r = start + tid;
         bool take = false;
         RoiWin w;
-        if (r < N && box_ind[r] == b) {
+        if (r < N && box_ind[r] == b && (level == nullptr || level[r] == l)) {
             w = win[r];
             take = (w.y0 <= w.y1) && !(w.y1 < y0 || w.y0 > y1 || w.x1 < x0 || w.x0 > x1);
         }
         const unsigned m = __ballot_sync(0xffffffffu, take);
+        __syncthreads();                 // s_warp reuse
         if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
         int off = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < FILL_THREADS / 32; ++k) {
             const int c = s_warp[k];
             if (k < warp) off += c;
             total += c;
@@ -341,7 +366,6 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const RoiWin *__restrict__
             entries[base + off + __popc(m & ((1u << lane) - 1u))] = e;
         }
         base += total;
-        __syncthreads();
     }
 }
 
@@ -360,212 +384,150 @@ __device__ __forceinline__ float4 accum(float4 s, float4 g, float wy, float wx, 
                        accum1<EXACT>(s.z, g.z, wy, wx, w), accum1<EXACT>(s.w, g.w, wy, wx, w));
 }
 
-constexpr int BWD_ROWS = 8;            // tile rows = warps per CTA
+constexpr int BWD_ROWS = 8;            // warps per CTA; warp w owns row w of the tile
 constexpr int BWD_THREADS = 32 * BWD_ROWS;
-constexpr int BWD_MAX_CH = 64;         // accepted ROIs staged in shared memory per round
 
-// Shared memory per round of at most CH accepted ROIs (dynamic):
-//   Tap ytab[CH][ph], xtab[CH][pw]     tap tables
-//   int roi[CH]                        accepted ROI ids, original order
-//   u16 yr[CH][8], xr[CH][8]           per tile row / column: sample range lo | hi<<8
-static size_t bwd_smem_bytes(int CH, int ph, int pw)
-{
-    return (size_t)CH * ((size_t)(ph + pw) * sizeof(Tap) + sizeof(int) + 2 * 8 * sizeof(unsigned short));
-}
-
-// Backward kernel: gather form, no atomics, every destination pixel written exactly once.
-//   CTA  = tile of 8 rows x TW columns of one image (x a channel chunk of 32*NV vectors)
-//   A    scan the supertile's ordered ROI list, keep (in order) up to CH ROIs whose window meets the tile
-//   B    tap tables of the kept ROIs; per tile row/column the contiguous range of samples touching it
-//   C    warp = tile row, lanes = channel vectors: for each kept ROI (original order), each of its
-//        samples touching the row, each pixel of the row: acc += w * g, in the reference's serial
-//        order (ROI, y, x, tap TL/TR/BL/BR; crop_and_resize.c:190-250), accumulators in registers.
-// EXACT: each term is wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247 (bit-
-// identical to the reference CPU backward); otherwise fma(wy*wx, g, acc) (<= 1 ulp per term).
+// Backward kernel: gather form, no atomics, no shared memory, no block barriers; every
+// destination pixel is written exactly once (zeros included, so no memset).
+//   warp  = one strip of TW horizontally adjacent destination pixels of one image and level
+//   lanes = channel vectors (NV per lane), accumulators in registers
+// The warp walks its supertile's ROI list in original box order.  For every ROI whose window
+// meets the strip, lane k evaluates tap k of the y axis and of the x axis (same arithmetic
+// as the forward); ballots give the samples that touch the strip's row and columns; the
+// warp then visits those samples in (y, x) order and adds each tap's term to the pixel it
+// lands on.  Per destination pixel the summation order is (ROI, y, x, tap TL/TR/BL/BR) --
+// the reference's serial order (crop_and_resize.c:190-250).
+// EXACT: each term is wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247
+// (bit-identical to the reference CPU backward); otherwise fma(wy*wx, g, acc).
 template <int VEC, int NV, int TW, bool EXACT>
 __global__ void __launch_bounds__(BWD_THREADS)
 crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
-                     const ListEntry *__restrict__ entries, const int *__restrict__ st_off, SuperGrid sg,
-                     int C, int ph, int pw, float *__restrict__ grad_image, int B, int H, int W,
-                     int tiles_x, int tiles_y, int CH)
+                     const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
+                     const int *__restrict__ st_count, BwdParams P, int C, int ph, int pw)
 {
     using V = typename VecT<VEC>::type;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    Tap *ytab = reinterpret_cast<Tap *>(s_raw);                          // [CH][ph]
-    Tap *xtab = ytab + (size_t)CH * ph;                                  // [CH][pw]
-    int *s_roi = reinterpret_cast<int *>(xtab + (size_t)CH * pw);        // [CH]
-    unsigned short *s_yr = reinterpret_cast<unsigned short *>(s_roi + CH);   // [CH][8]
-    unsigned short *s_xr = s_yr + (size_t)CH * 8;                        // [CH][8]
-    __shared__ int s_warp[BWD_ROWS];
-    __shared__ int s_last;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int t = blockIdx.x;
-    const int tx_i = t % tiles_x; t /= tiles_x;
-    const int ty_i = t % tiles_y; t /= tiles_y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < BWD_MAX_LEVELS; ++k)
+        if (k < P.n_levels && (int)blockIdx.x >= P.lv[k].tile_base) l = k;
+    const BwdLevel L = pick_level(P, l);
+    int t = blockIdx.x - L.tile_base;
+    const int tx_i = t % L.tiles_x; t /= L.tiles_x;
+    const int ty_i = t % L.tiles_y; t /= L.tiles_y;
     const int b = t;
-    const int ty0 = ty_i * BWD_ROWS, tx0 = tx_i * TW;
-    const int ty1 = min(ty0 + BWD_ROWS, H) - 1, tx1 = min(tx0 + TW, W) - 1;
+    const int H = L.H, W = L.W;
+    const int py = ty_i * BWD_ROWS + warp;
+    if (py >= H) return;
+    const int tx0 = tx_i * TW, tx1 = min(tx0 + TW, W) - 1;
     const int CV = C / VEC;
     const int cvbase = blockIdx.y * (32 * NV) + lane;
 
-    V acc[TW][NV];
-#pragma unroll
-    for (int p = 0; p < TW; ++p)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[p][v] = make_splat(0.f, (V *)nullptr);
+    // accumulators of the strip's 4 pixels x NV channel vectors: named scalars, so they
+    // stay in registers (an indexed array ends up in local memory here)
+    static_assert(TW == 4 && (NV == 1 || NV == 2), "strip shape is fixed at 4 pixels, 1-2 vectors per lane");
+    const V zero = make_splat(0.f, (V *)nullptr);
+    V p0a = zero, p1a = zero, p2a = zero, p3a = zero;
+    V p0b = zero, p1b = zero, p2b = zero, p3b = zero;
+    const bool va_ok = cvbase < CV, vb_ok = NV == 2 && cvbase + 32 < CV;
 
-    const int st = (b * sg.ny + ty0 / sg.side) * sg.nx + tx0 / sg.side;
-    const int l0 = st_off[st], n_list = st_off[st + 1] - l0;
-    const ListEntry *__restrict__ list = entries + l0;
+    const int st = L.st_base + (b * L.sg.ny + py / L.sg.side) * L.sg.nx + tx0 / L.sg.side;
+    const int n_list = st_count[st];
+    const ListEntry *__restrict__ list = entries + (n_list ? st_off[st] : 0);
     const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cvbase;
     const int S = ph * pw;
-    const int py = ty0 + warp;
 
-    int scan = 0;
-    while (scan < n_list) {
-        // ---- A: accumulate accepted ROIs (in order) until the round is full or the list ends
-        int n_acc = 0;
-        while (scan < n_list && n_acc < CH) {
-            const int li = scan + tid;
-            bool take = false;
-            int r = -1;
-            if (li < n_list) {
-                const ListEntry e = list[li];
-                r = e.roi;
-                take = !(e.win.y1 < ty0 || e.win.y0 > ty1 || e.win.x1 < tx0 || e.win.x0 > tx1);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (lane == 0) s_warp[warp] = __popc(m);
-            if (tid == 0) s_last = -1;
-            __syncthreads();
-            int off = 0, total = 0;
-#pragma unroll
-            for (int k = 0; k < BWD_ROWS; ++k) {
-                const int c = s_warp[k];
-                if (k < warp) off += c;
-                total += c;
-            }
-            const int slot = n_acc + off + __popc(m & ((1u << lane) - 1u));
-            if (take && slot < CH) s_roi[slot] = r;
-            const bool overflow = n_acc + total > CH;
-            if (overflow && take && slot == CH - 1) s_last = li;     // last entry that still fits
-            __syncthreads();
-            if (overflow) {
-                scan = s_last + 1;
-                n_acc = CH;
-            } else {
-                scan += BWD_THREADS;
-                n_acc += total;
-            }
-            // s_warp / s_last are rewritten next iteration only after the barrier above
+    for (int base = 0; base < n_list; base += 32) {
+        const int li = base + lane;
+        int my_roi = -1;
+        bool take = false;
+        if (li < n_list) {
+            const ListEntry e = list[li];
+            my_roi = e.roi;
+            take = !(e.win.y1 < py || e.win.y0 > py || e.win.x1 < tx0 || e.win.x0 > tx1);
         }
-        if (n_acc == 0) break;
-        const int n_chunk = n_acc;
-
-        // ---- B: tap tables, then per-row / per-column sample ranges of the kept ROIs
-        for (int i = tid; i < n_chunk * (ph + pw); i += BWD_THREADS) {
-            const int q = i / (ph + pw), k = i - q * (ph + pw);
-            const int rr = s_roi[q];
-            if (k < ph) {
-                const float a1 = boxes[4 * rr + 0], a2 = boxes[4 * rr + 2];
-                ytab[q * ph + k] = axis_tap(a1, a2, axis_scale(a1, a2, H, ph), H, ph, k);
-            } else {
-                const float a1 = boxes[4 * rr + 1], a2 = boxes[4 * rr + 3];
-                xtab[q * pw + (k - ph)] = axis_tap(a1, a2, axis_scale(a1, a2, W, pw), W, pw, k - ph);
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < n_chunk * (BWD_ROWS + TW); i += BWD_THREADS) {
-            const int q = i / (BWD_ROWS + TW), j = i - q * (BWD_ROWS + TW);
-            const bool isx = j >= BWD_ROWS;
-            const int jj = isx ? j - BWD_ROWS : j;
-            const int pix = (isx ? tx0 : ty0) + jj;
-            const Tap *tab = isx ? (xtab + q * pw) : (ytab + q * ph);
-            const int cnt = isx ? pw : ph;
-            int lo = 255, hi = 0;
-            bool any = false;
-            for (int k = 0; k < cnt; ++k) {
-                const Tap tp = tab[k];
-                if (tp.lo == INVALID_TAP) continue;
-                const int h = tp.lo + (tp.lerp != 0.f);
-                if (tp.lo == pix || h == pix) {
-                    if (!any) lo = k;
-                    hi = k;
-                    any = true;
-                }
-            }
-            const unsigned short packed = any ? (unsigned short)(lo | (hi << 8)) : (unsigned short)0x00ff;
-            (isx ? s_xr : s_yr)[q * 8 + jj] = packed;
-        }
-        __syncthreads();
-
-        // ---- C: accumulate
-        if (py <= ty1) {
-            for (int q = 0; q < n_chunk; ++q) {
-                const unsigned yrng = s_yr[q * 8 + warp];
-                const int ylo = yrng & 0xff, yhi = yrng >> 8;
-                if (ylo > yhi) continue;
-                const Tap *yt = ytab + q * ph;
-                const Tap *xt = xtab + q * pw;
-                const V *gr = g + (size_t)s_roi[q] * S * CV;
-#pragma unroll
-                for (int p = 0; p < TW; ++p) {
-                    const int px = tx0 + p;
-                    const unsigned xrng = s_xr[q * 8 + p];
-                    const int xlo = xrng & 0xff, xhi = xrng >> 8;
-                    if (xlo > xhi) continue;
-                    for (int y = ylo; y <= yhi; ++y) {
-                        const Tap tyy = yt[y];
-                        const bool top = (tyy.lo == py);
-                        const bool bot = (tyy.lo + (tyy.lerp != 0.f) == py);
-                        const float wy_t = __fsub_rn(1.f, tyy.lerp), wy_b = tyy.lerp;
-                        for (int x = xlo; x <= xhi; ++x) {
-                            const Tap txx = xt[x];
-                            const bool lft = (txx.lo == px);
-                            const bool rgt = (txx.lo + (txx.lerp != 0.f) == px);
-                            const float wx_l = __fsub_rn(1.f, txx.lerp), wx_r = txx.lerp;
-                            V gv[NV];
-#pragma unroll
-                            for (int v = 0; v < NV; ++v)
-                                if (cvbase + 32 * v < CV) gv[v] = ldg_vec(gr + (size_t)(y * pw + x) * CV + 32 * v);
-                            if (top != bot && lft != rgt) {          // the generic case: exactly one tap lands here
-                                const float wy = top ? wy_t : wy_b, wx = lft ? wx_l : wx_r;
-                                const float w = __fmul_rn(wy, wx);
-#pragma unroll
-                                for (int v = 0; v < NV; ++v) acc[p][v] = accum<EXACT>(acc[p][v], gv[v], wy, wx, w);
-                            } else {                                  // integral sample position: several taps coincide
-#pragma unroll
-                                for (int tap = 0; tap < 4; ++tap) {  // reference order TL, TR, BL, BR
-                                    const bool hit = ((tap >> 1) ? bot : top) && ((tap & 1) ? rgt : lft);
-                                    if (hit) {
-                                        const float wy = (tap >> 1) ? wy_b : wy_t, wx = (tap & 1) ? wx_r : wx_l;
-                                        const float w = __fmul_rn(wy, wx);
-#pragma unroll
-                                        for (int v = 0; v < NV; ++v) acc[p][v] = accum<EXACT>(acc[p][v], gv[v], wy, wx, w);
-                                    }
-                                }
+        unsigned todo = __ballot_sync(0xffffffffu, take);
+        while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int r = __shfl_sync(0xffffffffu, my_roi, bit);
+            const float by1 = __ldg(boxes + 4 * r + 0), bx1 = __ldg(boxes + 4 * r + 1);
+            const float by2 = __ldg(boxes + 4 * r + 2), bx2 = __ldg(boxes + 4 * r + 3);
+            const float sc_y = axis_scale(by1, by2, H, ph), sc_x = axis_scale(bx1, bx2, W, pw);
+            const V *gr = g + (size_t)r * S * CV;
+            for (int ky0 = 0; ky0 < ph; ky0 += 32) {
+                Tap ty;
+                ty.lo = INVALID_TAP; ty.lerp = 0.f;
+                if (ky0 + lane < ph) ty = axis_tap(by1, by2, sc_y, H, ph, ky0 + lane);
+                unsigned ym = __ballot_sync(0xffffffffu, ty.lo != INVALID_TAP &&
+                                                             (ty.lo == py || ty.lo + (ty.lerp != 0.f) == py));
+                while (ym) {
+                    const int yb = __ffs(ym) - 1;
+                    ym &= ym - 1;
+                    const int ylo = __shfl_sync(0xffffffffu, ty.lo, yb);
+                    const float yl = __shfl_sync(0xffffffffu, ty.lerp, yb);
+                    // row weights that land on py, in tap order (top before bottom)
+                    const bool y_int = (yl == 0.f);                 // floor == ceil: both taps hit this row
+                    const float wy0 = (ylo == py) ? __fsub_rn(1.f, yl) : yl;
+                    const int yoff = (ky0 + yb) * pw;
+                    for (int kx0 = 0; kx0 < pw; kx0 += 32) {
+                        Tap tx;
+                        tx.lo = INVALID_TAP; tx.lerp = 0.f;
+                        if (kx0 + lane < pw) tx = axis_tap(bx1, bx2, sc_x, W, pw, kx0 + lane);
+                        unsigned xm = __ballot_sync(0xffffffffu, tx.lo != INVALID_TAP && tx.lo <= tx1 &&
+                                                                     tx.lo + (tx.lerp != 0.f) >= tx0);
+                        while (xm) {
+                            const int xb = __ffs(xm) - 1;
+                            xm &= xm - 1;
+                            const int xlo = __shfl_sync(0xffffffffu, tx.lo, xb);
+                            const float xl = __shfl_sync(0xffffffffu, tx.lerp, xb);
+                            const bool x_int = (xl == 0.f);
+                            const float wl = __fsub_rn(1.f, xl), wr = xl;
+                            const int pl = xlo - tx0;               // strip pixel of the left tap (-1 .. TW-1)
+                            V ga = zero, gb = zero;
+                            if (va_ok) ga = ldg_vec(gr + (size_t)(yoff + kx0 + xb) * CV);
+                            if (vb_ok) gb = ldg_vec(gr + (size_t)(yoff + kx0 + xb) * CV + 32);
+                            const int pr = x_int ? pl : pl + 1;     // strip pixel of the right tap
+#define SLN_BWD_ADD(PA, PB, WX, WW)                                   \
+    {                                                                 \
+        PA = accum<EXACT>(PA, ga, wy, WX, WW);                        \
+        if (NV == 2) PB = accum<EXACT>(PB, gb, wy, WX, WW);           \
+    }
+                            // one pass per row weight (two only when the sample row is integral)
+                            for (int pass = 0; pass < (y_int ? 2 : 1); ++pass) {
+                                const float wy = pass == 0 ? wy0 : yl;
+                                const float w_l = __fmul_rn(wy, wl), w_r = __fmul_rn(wy, wr);
+                                // left tap (TL / BL) first, then right tap (TR / BR): reference order
+                                if (pl == 0) SLN_BWD_ADD(p0a, p0b, wl, w_l)
+                                else if (pl == 1) SLN_BWD_ADD(p1a, p1b, wl, w_l)
+                                else if (pl == 2) SLN_BWD_ADD(p2a, p2b, wl, w_l)
+                                else if (pl == 3) SLN_BWD_ADD(p3a, p3b, wl, w_l)
+                                if (pr == 0) SLN_BWD_ADD(p0a, p0b, wr, w_r)
+                                else if (pr == 1) SLN_BWD_ADD(p1a, p1b, wr, w_r)
+                                else if (pr == 2) SLN_BWD_ADD(p2a, p2b, wr, w_r)
+                                else if (pr == 3) SLN_BWD_ADD(p3a, p3b, wr, w_r)
                             }
+#undef SLN_BWD_ADD
                         }
                     }
                 }
             }
         }
-        __syncthreads();            // tables are rewritten by the next round
     }
 
-    // ---- write every pixel of the tile exactly once (zeros included)
-    if (py <= ty1) {
-        V *__restrict__ o = reinterpret_cast<V *>(grad_image);
-#pragma unroll
-        for (int p = 0; p < TW; ++p) {
-            const int px = tx0 + p;
-            if (px <= tx1) {
-#pragma unroll
-                for (int v = 0; v < NV; ++v)
-                    if (cvbase + 32 * v < CV) __stcs(o + (((size_t)b * H + py) * W + px) * CV + cvbase + 32 * v, acc[p][v]);
-            }
-        }
+    // ---- write every pixel of the strip exactly once (zeros included)
+    V *__restrict__ o = reinterpret_cast<V *>(L.out) + (((size_t)b * H + py) * W + tx0) * CV + cvbase;
+    if (va_ok) {
+        __stcs(o, p0a);
+        if (tx0 + 1 <= tx1) __stcs(o + (size_t)CV, p1a);
+        if (tx0 + 2 <= tx1) __stcs(o + 2 * (size_t)CV, p2a);
+        if (tx0 + 3 <= tx1) __stcs(o + 3 * (size_t)CV, p3a);
+    }
+    if (vb_ok) {
+        __stcs(o + 32, p0b);
+        if (tx0 + 1 <= tx1) __stcs(o + (size_t)CV + 32, p1b);
+        if (tx0 + 2 <= tx1) __stcs(o + 2 * (size_t)CV + 32, p2b);
+        if (tx0 + 3 <= tx1) __stcs(o + 3 * (size_t)CV + 32, p3b);
     }
 }
 
@@ -660,84 +622,101 @@ struct BwdWs {
     ListEntry *entries;
 };
 
-static size_t bwd_ws_bytes(int N, int B)
+constexpr int BWD_MAX_ST = 64;        // supertiles per image and level (8 x 8)
+
+static size_t bwd_ws_bytes(int N, int B, int n_levels)
 {
-    // every ROI can meet at most 64 supertiles of its image
-    return align_up(sizeof(RoiWin) * (size_t)N, 256) + 2 * align_up(sizeof(int) * ((size_t)B * 64 + 1), 256) +
-           align_up(sizeof(ListEntry) * (size_t)N * 64, 256);
+    // every ROI lives on one level and meets at most 64 supertiles of its image
+    const size_t n_st = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
+    return align_up(sizeof(RoiWin) * (size_t)N, 256) + 2 * align_up(sizeof(int) * n_st, 256) +
+           align_up(sizeof(ListEntry) * (size_t)N * BWD_MAX_ST, 256);
 }
 
 template <int VEC, int NV, int TW, bool EXACT>
-static int launch_bwd(const float *grads, const float *boxes, const BwdWs &ws, SuperGrid sg, int C, int ph, int pw,
-                      float *grad_image, int B, int H, int W, cudaStream_t st)
+static int launch_bwd(const float *grads, const float *boxes, const BwdWs &ws, BwdParams &P, int total_tiles_unused,
+                      int C, int ph, int pw, int B, cudaStream_t st)
 {
-    const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, BWD_ROWS);
+    (void)total_tiles_unused;
+    long long tiles = 0;
+    for (int l = 0; l < P.n_levels; ++l) {
+        BwdLevel &L = P.lv[l];
+        L.tiles_x = cdiv(L.W, TW);
+        L.tiles_y = cdiv(L.H, BWD_ROWS);
+        L.tile_base = (int)tiles;
+        tiles += (long long)L.tiles_x * L.tiles_y * B;
+    }
+    SLN_REQUIRE(tiles < (1ll << 31), SLN_ERR_ARG, "too many tiles");
     const int chunks = cdiv(C / VEC, 32 * NV);
-    int CH = BWD_MAX_CH;
-    while (CH > 1 && bwd_smem_bytes(CH, ph, pw) > 40 * 1024) CH /= 2;
-    const size_t smem = bwd_smem_bytes(CH, ph, pw);
-    SLN_REQUIRE(smem <= 200 * 1024, SLN_ERR_ARG, "crop %dx%d too large for the backward kernel", ph, pw);
-    auto kern = crop_bwd_nhwc_kernel<VEC, NV, TW, EXACT>;
-    if (smem > 48 * 1024)
-        SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
-    SLN_REQUIRE((size_t)tiles_x * tiles_y * B < (1ull << 31), SLN_ERR_ARG, "too many tiles");
-    dim3 grid((unsigned)((size_t)tiles_x * tiles_y * B), chunks);
-    kern<<<grid, BWD_THREADS, smem, st>>>(grads, boxes, ws.entries, ws.st_off, sg, C, ph, pw, grad_image, B, H, W,
-                                           tiles_x, tiles_y, CH);
+    if (tiles == 0) return SLN_OK;
+    dim3 grid((unsigned)tiles, chunks);
+    crop_bwd_nhwc_kernel<VEC, NV, TW, EXACT><<<grid, BWD_THREADS, 0, st>>>(grads, boxes, ws.entries, ws.st_off,
+                                                                          ws.st_count, P, C, ph, pw);
     SLN_LAUNCH_OK("crop_bwd_nhwc_kernel");
     return SLN_OK;
 }
 
 template <int VEC, bool EXACT>
-static int dispatch_bwd(const float *grads, const float *boxes, const BwdWs &ws, SuperGrid sg, int C, int ph, int pw,
-                        float *grad_image, int B, int H, int W, cudaStream_t st)
+static int dispatch_bwd(const float *grads, const float *boxes, const BwdWs &ws, BwdParams &P, int C, int ph, int pw,
+                        int B, cudaStream_t st)
 {
     const int CV = C / VEC;
     // two channel vectors per lane halve the control work per byte, but also the CTA count:
-    // only use them when the map alone provides enough tiles to fill the machine
-    const long long tiles4 = (long long)cdiv(W, 4) * cdiv(H, BWD_ROWS) * B;
+    // only use them when the maps provide enough strips to fill the machine
+    long long tiles4 = 0;
+    for (int l = 0; l < P.n_levels; ++l) tiles4 += (long long)cdiv(P.lv[l].W, 4) * cdiv(P.lv[l].H, BWD_ROWS) * B;
     if (CV > 32 && tiles4 >= 6LL * sm_count())
-        return launch_bwd<VEC, 2, 4, EXACT>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
-    return launch_bwd<VEC, 1, 4, EXACT>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+        return launch_bwd<VEC, 2, 4, EXACT>(grads, boxes, ws, P, 0, C, ph, pw, B, st);
+    return launch_bwd<VEC, 1, 4, EXACT>(grads, boxes, ws, P, 0, C, ph, pw, B, st);
 }
 
-static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *level,
-                         int which_level, int N, int C, int ph, int pw, float *grad_image, int B, int H,
-                         int W, bool exact, void *wsp, size_t ws_bytes, cudaStream_t st)
+// grads [N,ph,pw,C]; one grad map per level (NHWC); level[i] selects the map of ROI i (null: level 0)
+static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *level, int N, int C,
+                         int ph, int pw, float *const *maps, const int *Hs, const int *Ws, int n_levels, int B,
+                         bool exact, void *wsp, size_t ws_bytes, cudaStream_t st)
 {
-    if (B == 0 || C == 0 || H == 0 || W == 0) return SLN_OK;
-    SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B), SLN_ERR_WORKSPACE, "crop bwd workspace: need %zu bytes, got %zu",
-                bwd_ws_bytes(N, B), ws_bytes);
+    if (B == 0 || C == 0) return SLN_OK;
+    SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B, n_levels), SLN_ERR_WORKSPACE,
+                "crop bwd workspace: need %zu bytes, got %zu", bwd_ws_bytes(N, B, n_levels), ws_bytes);
     SLN_REQUIRE(wsp != nullptr, SLN_ERR_WORKSPACE, "null workspace");
+    BwdParams P{};
+    P.n_levels = n_levels;
+    int n_st = 0;
+    bool vec4 = (C % 4 == 0) && aligned16(grads);
+    for (int l = 0; l < n_levels; ++l) {
+        BwdLevel &L = P.lv[l];
+        L.out = maps[l];
+        L.H = Hs[l];
+        L.W = Ws[l];
+        L.sg = super_grid(L.H, L.W);
+        L.st_base = n_st;
+        n_st += B * L.sg.nx * L.sg.ny;
+        vec4 = vec4 && aligned16(maps[l]);
+        SLN_REQUIRE((size_t)L.H * L.W == 0 || maps[l] != nullptr, SLN_ERR_ARG, "null grad map");
+    }
     unsigned char *p = static_cast<unsigned char *>(wsp);
+    const size_t n_st_cap = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
     BwdWs ws;
     ws.win = reinterpret_cast<RoiWin *>(p);        p += align_up(sizeof(RoiWin) * (size_t)N, 256);
-    ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * ((size_t)B * 64 + 1), 256);
-    ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * ((size_t)B * 64 + 1), 256);
+    ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * n_st_cap, 256);
+    ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
     ws.entries = reinterpret_cast<ListEntry *>(p);
-    const SuperGrid sg = super_grid(H, W);
-    const int n_st = B * sg.nx * sg.ny;
 
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
-    if (N > 0) {
-        crop_bwd_windows_kernel<<<cdiv(N, 256), 256, 0, st>>>(boxes, box_ind, level, which_level, N, B, H, W, ph, pw,
-                                                             sg, ws.win, ws.st_count);
+    if (N > 0 && n_st > 0) {
+        crop_bwd_windows_kernel<<<cdiv(N, 256), 256, 0, st>>>(boxes, box_ind, level, N, B, ph, pw, P, ws.win,
+                                                             ws.st_count);
         SLN_LAUNCH_OK("crop_bwd_windows_kernel");
-    }
-    crop_bwd_scan_kernel<<<1, 1024, 0, st>>>(ws.st_count, n_st, ws.st_off);
-    SLN_LAUNCH_OK("crop_bwd_scan_kernel");
-    if (N > 0) {
-        crop_bwd_fill_kernel<<<n_st, 256, 0, st>>>(box_ind, ws.win, N, sg, ws.st_off, ws.entries);
+        crop_bwd_fill_kernel<<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, N, P, ws.st_count, ws.st_off,
+                                                            ws.entries);
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
-    const bool vec4 = (C % 4 == 0) && aligned16(grads) && aligned16(grad_image);
     if (vec4) {
-        if (exact) return dispatch_bwd<4, true>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
-        return dispatch_bwd<4, false>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+        if (exact) return dispatch_bwd<4, true>(grads, boxes, ws, P, C, ph, pw, B, st);
+        return dispatch_bwd<4, false>(grads, boxes, ws, P, C, ph, pw, B, st);
     }
-    if (exact) return dispatch_bwd<1, true>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
-    return dispatch_bwd<1, false>(grads, boxes, ws, sg, C, ph, pw, grad_image, B, H, W, st);
+    if (exact) return dispatch_bwd<1, true>(grads, boxes, ws, P, C, ph, pw, B, st);
+    return dispatch_bwd<1, false>(grads, boxes, ws, P, C, ph, pw, B, st);
 }
 
 }  // namespace sln
@@ -780,7 +759,7 @@ extern "C" int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, 
 extern "C" size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B)
 {
     if (N < 0 || B < 0) return 0;
-    return bwd_ws_bytes(N, B);
+    return bwd_ws_bytes(N, B, 1);
 }
 
 extern "C" int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
@@ -792,7 +771,9 @@ extern "C" int sln_crop_and_resize_bwd(const float *grads, const float *boxes, c
     int rc = check_crop_args(grad_image, boxes, box_ind, grad_image, B, C, H, W, N, ph, pw);
     if (rc != SLN_OK) return rc;
     SLN_REQUIRE(N == 0 || C == 0 || grads, SLN_ERR_ARG, "null grads");
-    return crop_bwd_nhwc(grads, boxes, box_ind, nullptr, 0, N, C, ph, pw, grad_image, B, H, W,
+    if (H == 0 || W == 0) return SLN_OK;
+    float *maps[1] = {grad_image};
+    return crop_bwd_nhwc(grads, boxes, box_ind, nullptr, N, C, ph, pw, maps, &H, &W, 1, B,
                          (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -814,15 +795,26 @@ extern "C" int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_
                          static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int sln_pyramid_crop_bwd_level(const float *grads, const float *boxes, const int *box_ind,
-                                          const int *level, int which_level, int N, int C, int ph, int pw,
-                                          float *grad_image, int B, int H, int W, int flags, void *workspace,
-                                          size_t workspace_bytes, void *stream)
+extern "C" size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels)
 {
-    int rc = check_crop_args(grad_image, boxes, box_ind, grad_image, B, C, H, W, N, ph, pw);
-    if (rc != SLN_OK) return rc;
+    if (N < 0 || B < 0 || n_levels < 1 || n_levels > BWD_MAX_LEVELS) return 0;
+    return bwd_ws_bytes(N, B, n_levels);
+}
+
+extern "C" int sln_pyramid_crop_bwd(const float *grads, const float *boxes, const int *box_ind, const int *level,
+                                    int N, int C, int ph, int pw, float *const *grad_maps_host, const int *H_host,
+                                    const int *W_host, int n_levels, int B, int flags, void *workspace,
+                                    size_t workspace_bytes, void *stream)
+{
+    SLN_REQUIRE(n_levels >= 1 && n_levels <= BWD_MAX_LEVELS, SLN_ERR_ARG, "n_levels %d outside [1,8]", n_levels);
+    SLN_REQUIRE(grad_maps_host && H_host && W_host, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE(n_levels == 1 || level || N == 0, SLN_ERR_ARG, "level array required for n_levels > 1");
+    for (int l = 0; l < n_levels; ++l) {
+        int rc = check_crop_args(grad_maps_host[l], boxes, box_ind, grad_maps_host[l], B, C, H_host[l], W_host[l], N, ph, pw);
+        if (rc != SLN_OK) return rc;
+    }
     SLN_REQUIRE(N == 0 || C == 0 || grads, SLN_ERR_ARG, "null grads");
-    return crop_bwd_nhwc(grads, boxes, box_ind, level, which_level, N, C, ph, pw, grad_image, B, H, W,
+    return crop_bwd_nhwc(grads, boxes, box_ind, level, N, C, ph, pw, grad_maps_host, H_host, W_host, n_levels, B,
                          (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

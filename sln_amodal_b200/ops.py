@@ -116,48 +116,75 @@ def crop_and_resize_forward(image, boxes, box_ind, crop_height, crop_width, extr
     return out
 
 
-def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_out=None, level=None, which_level=0,
-                             exact=None):
+def _prep_grads(grads):
+    g = grads.detach()
+    if g.dtype != torch.float32:
+        g = g.float()
+    cl = is_channels_last(g)
+    if not cl:
+        g = to_channels_last(g)
+    return g, cl
+
+
+def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_out=None, exact=None):
     """grad_image[B,C,H,W] of crop_and_resize w.r.t. the image (deterministic gather kernel).
 
     channels_last_out: memory format of the returned gradient (default: follow `grads`).
     exact: True -> round every term like crop_and_resize.c (bit-identical to the reference CPU
     backward); False -> fused multiply-add per term (default; see EXACT_BACKWARD)."""
+    _require_cuda(grads, "grads")
     if exact is None:
         exact = EXACT_BACKWARD
     flags = _lib.BWD_EXACT if exact else 0
-    _require_cuda(grads, "grads")
     boxes = _f32c(boxes).view(-1, 4)
     box_ind = _i32c(box_ind).view(-1)
     B, Cc, H, W = [int(v) for v in image_size]
     N, Cg, ph, pw = grads.shape
     if Cg != Cc or boxes.shape[0] != N:
         raise _lib.SlnError("grads / boxes / image_size disagree")
-    g = grads.detach()
-    if g.dtype != torch.float32:
-        g = g.float()
-    g_cl = is_channels_last(g)
+    g, g_cl = _prep_grads(grads)
     if channels_last_out is None:
         channels_last_out = g_cl
-    if not g_cl:
-        g = to_channels_last(g)
     out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grads.device, memory_format=torch.channels_last)
     with torch.cuda.device(grads.device):
-        ws_bytes = lib().sln_crop_and_resize_bwd_workspace_bytes(N, B)
-        ws = _workspace(ws_bytes, grads.device)
-        if level is None:
-            rc = lib().sln_crop_and_resize_bwd(ptr(g), ptr(boxes), ptr(box_ind), N, Cc, ph, pw, ptr(out), B, H, W,
-                                               LAYOUT_NHWC, flags, ptr(ws), ws.numel(), stream_ptr())
-        else:
-            level = _i32c(level).view(-1)
-            rc = lib().sln_pyramid_crop_bwd_level(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), int(which_level), N,
-                                                  Cc, ph, pw, ptr(out), B, H, W, flags, ptr(ws), ws.numel(), stream_ptr())
-        check(rc, "sln_crop_and_resize_bwd")
+        ws = _workspace(lib().sln_crop_and_resize_bwd_workspace_bytes(N, B), grads.device)
+        check(lib().sln_crop_and_resize_bwd(ptr(g), ptr(boxes), ptr(box_ind), N, Cc, ph, pw, ptr(out), B, H, W,
+                                            LAYOUT_NHWC, flags, ptr(ws), ws.numel(), stream_ptr()),
+              "sln_crop_and_resize_bwd")
     if out.numel():
-        _lib.count_launches(4 if N else 2)
+        _lib.count_launches(3 if N else 1)
     if not channels_last_out:
         out = to_contiguous_nchw(out)
     return out
+
+
+def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last_out=None, exact=None):
+    """Backward of pyramid_crop_forward for all levels in one call.  map_sizes: list of (B,C,H_l,W_l).
+    Returns the list of grad maps (channels_last unless channels_last_out[l] is False)."""
+    _require_cuda(grads, "grads")
+    if exact is None:
+        exact = EXACT_BACKWARD
+    flags = _lib.BWD_EXACT if exact else 0
+    boxes = _f32c(boxes).view(-1, 4)
+    box_ind = _i32c(box_ind).view(-1)
+    level = _i32c(level).view(-1)
+    N, Cc, ph, pw = grads.shape
+    nl = len(map_sizes)
+    B = int(map_sizes[0][0])
+    g, _ = _prep_grads(grads)
+    outs = [torch.empty(tuple(int(v) for v in sz), dtype=torch.float32, device=grads.device,
+                        memory_format=torch.channels_last) for sz in map_sizes]
+    mp = (C.c_void_p * nl)(*[o.data_ptr() for o in outs])
+    hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
+    ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
+    with torch.cuda.device(grads.device):
+        ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl), grads.device)
+        check(lib().sln_pyramid_crop_bwd(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), N, Cc, ph, pw, mp, hs, ws_, nl, B,
+                                         flags, ptr(ws), ws.numel(), stream_ptr()), "sln_pyramid_crop_bwd")
+    _lib.count_launches(3 if N else 1)
+    if channels_last_out is not None:
+        outs = [o if cl else to_contiguous_nchw(o) for o, cl in zip(outs, channels_last_out)]
+    return outs
 
 
 def pyramid_crop_forward(feature_maps, boxes, box_ind, level, crop_height, crop_width, extrapolation_value=0.0):

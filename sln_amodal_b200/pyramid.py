@@ -42,14 +42,8 @@ class _PyramidCrop(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         boxes, box_ind, level = ctx.saved_tensors
-        grads = []
-        g = grad if ops.is_channels_last(grad) else ops.to_channels_last(grad)
-        for l, size in enumerate(ctx.sizes):
-            if not ctx.needs[l]:
-                grads.append(None)
-                continue
-            grads.append(ops.crop_and_resize_backward(g, boxes, box_ind, size, channels_last_out=ctx.cl[l],
-                                                      level=level, which_level=l))
+        outs = ops.pyramid_crop_backward(grad, boxes, box_ind, level, ctx.sizes, channels_last_out=ctx.cl)
+        grads = [o if need else None for o, need in zip(outs, ctx.needs)]
         return (None, None, None, None) + tuple(grads)
 
 

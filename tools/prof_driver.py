@@ -26,8 +26,7 @@ if what == "crop":
         for p in bench.POOLS:
             g = torch.randn((boxes.shape[0], bench.CHANNELS, p, p), device=dev).contiguous(memory_format=torch.channels_last)
             ops.pyramid_crop_forward(maps, boxes, box_ind, level, p, p, 0.0)
-            for l in range(4):
-                ops.crop_and_resize_backward(g, boxes, box_ind, tuple(maps[l].shape), channels_last_out=True, level=level, which_level=l)
+            ops.pyramid_crop_backward(g, boxes, box_ind, level, [tuple(m.shape) for m in maps])
             del g
 elif what == "nms":
     for _ in range(reps):
