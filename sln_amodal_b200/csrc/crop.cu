@@ -249,7 +249,9 @@ struct BwdLevel {
     float *out;        // grad map of this level, NHWC [B,H,W,C]
     int H, W;
     int tiles_x, tiles_y;
+    float rcp_tiles_x, rcp_tiles_y;
     SuperGrid sg;
+    int sg_shift;      // log2(sg.side)
     int st_base;       // first supertile id of this level
     int tile_base;     // first tile (CTA) id of this level
 };
@@ -259,10 +261,47 @@ struct BwdParams {
     int n_levels;
 };
 
+struct BwdTileBases {  // passed by value to the main kernel: static-index compares only
+    int base[BWD_MAX_LEVELS];
+    int n_levels;
+};
+
 struct ListEntry {
     RoiWin win;
     int roi;
 };
+
+// Per-ROI sampling grid, evaluated once: pos(k) = base + k*scale on each axis, the same
+// expression (and rounding) as axis_tap / crop_and_resize.c:44-56.
+struct RoiAxes {
+    float by, sy, bx, sx;
+};
+
+__device__ __forceinline__ void axis_base_scale(float a1, float a2, int extent, int crop, float &base, float &scale)
+{
+    if (crop > 1) {
+        base = __fmul_rn(a1, (float)(extent - 1));
+        scale = axis_scale(a1, a2, extent, crop);
+    } else {
+        base = (float)(0.5 * (double)__fadd_rn(a1, a2) * (double)(extent - 1));
+        scale = 0.f;
+    }
+}
+
+__device__ __forceinline__ Tap tap_at(float base, float scale, float em1, int k)
+{
+    const float pos = __fadd_rn(base, __fmul_rn((float)k, scale));
+    Tap t;
+    if (!(pos >= 0.f && pos <= em1)) {
+        t.lo = INVALID_TAP;
+        t.lerp = 0.f;
+    } else {
+        const float fl = floorf(pos);
+        t.lo = (int)fl;
+        t.lerp = __fsub_rn(pos, fl);
+    }
+    return t;
+}
 
 // static-index copy of P.lv[l] (dynamic indexing would spill the parameter struct)
 __device__ __forceinline__ BwdLevel pick_level(const BwdParams &P, int l)
@@ -274,45 +313,54 @@ __device__ __forceinline__ BwdLevel pick_level(const BwdParams &P, int l)
     return r;
 }
 
-// prep 1: per-ROI pixel window on its level + per-supertile counts (integer atomics:
-// order-independent result)
+// prep 1: per-ROI axes and pixel window on its level + per-supertile counts (integer atomics:
+// order-independent result); thread 0 also publishes the level table for the main kernel.
 __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind,
                                         const int *__restrict__ level, int N, int B, int ph, int pw,
-                                        BwdParams P, RoiWin *__restrict__ win, int *__restrict__ st_count)
+                                        BwdParams P, RoiWin *__restrict__ win, RoiAxes *__restrict__ axes,
+                                        int *__restrict__ st_count, BwdLevel *__restrict__ lv_table)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
     if (r >= N) return;
     RoiWin w;
     w.y0 = 1; w.y1 = 0; w.x0 = 1; w.x1 = 0;
+    RoiAxes ax;
+    ax.by = ax.sy = ax.bx = ax.sx = 0.f;
     const int b = box_ind[r];
     const int l = level ? level[r] : 0;
     if (b >= 0 && b < B && l >= 0 && l < P.n_levels) {
         const BwdLevel L = pick_level(P, l);
+        const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
+        axis_base_scale(y1, y2, L.H, ph, ax.by, ax.sy);
+        axis_base_scale(x1, x2, L.W, pw, ax.bx, ax.sx);
         int a0, a1, c0, c1;
-        axis_window(boxes[4 * r + 0], boxes[4 * r + 2], L.H, ph, a0, a1);
-        axis_window(boxes[4 * r + 1], boxes[4 * r + 3], L.W, pw, c0, c1);
+        axis_window(y1, y2, L.H, ph, a0, a1);
+        axis_window(x1, x2, L.W, pw, c0, c1);
         if (a0 <= a1 && c0 <= c1) {
             w.y0 = (short)a0; w.y1 = (short)a1; w.x0 = (short)c0; w.x1 = (short)c1;
-            for (int sy = a0 / L.sg.side; sy <= a1 / L.sg.side; ++sy)
-                for (int sx = c0 / L.sg.side; sx <= c1 / L.sg.side; ++sx)
+            for (int sy = a0 >> L.sg_shift; sy <= (a1 >> L.sg_shift); ++sy)
+                for (int sx = c0 >> L.sg_shift; sx <= (c1 >> L.sg_shift); ++sx)
                     atomicAdd(st_count + L.st_base + (b * L.sg.ny + sy) * L.sg.nx + sx, 1);
         }
     }
     win[r] = w;
+    axes[r] = ax;
 }
 
 // prep 2: ordered fill.  One CTA per supertile: its list offset is the sum of the counts of
-// the supertiles before it; it then scans all ROIs in index order (ballot compaction keeps
-// the original box order) and stores each hit with its window.  st_off[st] is published
-// for the main kernel.
+// the supertiles before it; it then takes the ROIs in index order, FILL_PER_THREAD x 1024 at
+// a time (all loads issued up front), and compacts the hits with one block-wide scan so the
+// list keeps the original box order.  st_off[st] is published for the main kernel.
 constexpr int FILL_THREADS = 1024;
+constexpr int FILL_PER_THREAD = 8;
 
 __global__ void __launch_bounds__(FILL_THREADS)
 crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ level,
                      const RoiWin *__restrict__ win, int N, BwdParams P, const int *__restrict__ st_count,
                      int *__restrict__ st_off, ListEntry *__restrict__ entries)
 {
-    __shared__ int s_warp[FILL_THREADS / 32];
+    __shared__ int s_cnt[FILL_PER_THREAD][FILL_THREADS / 32];
     __shared__ int s_base;
     const int st = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -320,19 +368,17 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ le
     int part = 0;
     for (int i = tid; i < st; i += FILL_THREADS) part += st_count[i];
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_warp[warp] = part;
+    if (lane == 0) s_cnt[0][warp] = part;
     __syncthreads();
     if (tid == 0) {
         int t = 0;
-        for (int k = 0; k < FILL_THREADS / 32; ++k) t += s_warp[k];
+        for (int k = 0; k < FILL_THREADS / 32; ++k) t += s_cnt[0][k];
         s_base = t;
         st_off[st] = t;
     }
     __syncthreads();
     int base = s_base;
-    const int mine = st_count[st];
-    if (mine == 0) return;
-    // which level / image / supertile is this?
+    if (st_count[st] == 0) return;
     int l = 0;
 #pragma unroll
     for (int k = 1; k < BWD_MAX_LEVELS; ++k)
@@ -340,32 +386,58 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ le
     const BwdLevel L = pick_level(P, l);
     const int local = st - L.st_base;
     const int sx = local % L.sg.nx, sy = (local / L.sg.nx) % L.sg.ny, b = local / (L.sg.nx * L.sg.ny);
-    const int y0 = sy * L.sg.side, y1 = y0 + L.sg.side - 1, x0 = sx * L.sg.side, x1 = x0 + L.sg.side - 1;
-    for (int start = 0; start < N; start += FILL_THREADS) {
-        const int r = start + tid;
-        bool take = false;
-        RoiWin w;
-        if (r < N && box_ind[r] == b && (level == nullptr || level[r] == l)) {
-            w = win[r];
-            take = (w.y0 <= w.y1) && !(w.y1 < y0 || w.y0 > y1 || w.x1 < x0 || w.x0 > x1);
+    const int y0 = sy << L.sg_shift, y1 = y0 + L.sg.side - 1, x0 = sx << L.sg_shift, x1 = x0 + L.sg.side - 1;
+    for (int start = 0; start < N; start += FILL_THREADS * FILL_PER_THREAD) {
+        RoiWin w[FILL_PER_THREAD];
+        int bi[FILL_PER_THREAD], lv[FILL_PER_THREAD];
+#pragma unroll
+        for (int it = 0; it < FILL_PER_THREAD; ++it) {          // all loads first
+            const int r = start + it * FILL_THREADS + tid;
+            bi[it] = -1;
+            lv[it] = l;
+            if (r < N) {
+                bi[it] = box_ind[r];
+                if (level) lv[it] = level[r];
+                w[it] = win[r];
+            }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        __syncthreads();                 // s_warp reuse
-        if (lane == 0) s_warp[warp] = __popc(m);
+        unsigned masks[FILL_PER_THREAD];
+        __syncthreads();                                          // s_cnt reuse
+#pragma unroll
+        for (int it = 0; it < FILL_PER_THREAD; ++it) {
+            const bool take = bi[it] == b && lv[it] == l && (w[it].y0 <= w[it].y1) &&
+                              !(w[it].y1 < y0 || w[it].y0 > y1 || w[it].x1 < x0 || w[it].x0 > x1);
+            masks[it] = __ballot_sync(0xffffffffu, take);
+            if (lane == 0) s_cnt[it][warp] = __popc(masks[it]);
+        }
         __syncthreads();
-        int off = 0, total = 0;
-        for (int k = 0; k < FILL_THREADS / 32; ++k) {
-            const int c = s_warp[k];
-            if (k < warp) off += c;
-            total += c;
+        // exclusive scan over the (it, warp) grid in ROI order: warp 0 does it serially per lane group
+        if (warp == 0) {
+            int run = 0;
+#pragma unroll
+            for (int it = 0; it < FILL_PER_THREAD; ++it) {
+                const int c = s_cnt[it][lane];
+                int incl = c;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                s_cnt[it][lane] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_base = run;
         }
-        if (take) {
-            ListEntry e;
-            e.win = w;
-            e.roi = r;
-            entries[base + off + __popc(m & ((1u << lane) - 1u))] = e;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < FILL_PER_THREAD; ++it) {
+            if ((masks[it] >> lane) & 1u) {
+                ListEntry e;
+                e.win = w[it];
+                e.roi = start + it * FILL_THREADS + tid;
+                entries[base + s_cnt[it][warp] + __popc(masks[it] & ((1u << lane) - 1u))] = e;
+            }
         }
-        base += total;
+        base += s_base;
     }
 }
 
@@ -386,10 +458,20 @@ __device__ __forceinline__ float4 accum(float4 s, float4 g, float wy, float wx, 
 
 constexpr int BWD_ROWS = 8;            // warps per CTA; warp w owns row w of the tile
 constexpr int BWD_THREADS = 32 * BWD_ROWS;
+constexpr int BWD_TW = 4;              // destination pixels per warp (one strip)
+
+// t / d for 0 <= t < 2^24 with a precomputed float reciprocal (exact after one correction)
+__device__ __forceinline__ int fast_div(int t, int d, float rcp)
+{
+    int q = __float2int_rz(__fmul_rn(__int2float_rn(t), rcp));
+    const int r = t - q * d;
+    q += (r >= d) - (r < 0);
+    return q;
+}
 
 // Backward kernel: gather form, no atomics, no shared memory, no block barriers; every
 // destination pixel is written exactly once (zeros included, so no memset).
-//   warp  = one strip of TW horizontally adjacent destination pixels of one image and level
+//   warp  = one strip of 4 horizontally adjacent destination pixels of one image and level
 //   lanes = channel vectors (NV per lane), accumulators in registers
 // The warp walks its supertile's ROI list in original box order.  For every ROI whose window
 // meets the strip, lane k evaluates tap k of the y axis and of the x axis (same arithmetic
@@ -399,43 +481,53 @@ constexpr int BWD_THREADS = 32 * BWD_ROWS;
 // the reference's serial order (crop_and_resize.c:190-250).
 // EXACT: each term is wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247
 // (bit-identical to the reference CPU backward); otherwise fma(wy*wx, g, acc).
-template <int VEC, int NV, int TW, bool EXACT>
+template <int VEC, int NV, bool EXACT>
 __global__ void __launch_bounds__(BWD_THREADS)
-crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
+crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict__ axes,
                      const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
-                     const int *__restrict__ st_count, BwdParams P, int C, int ph, int pw)
+                     const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
+                     BwdTileBases TB, int C, int ph, int pw)
 {
     using V = typename VecT<VEC>::type;
+    constexpr int TW = BWD_TW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l = 0;
 #pragma unroll
     for (int k = 1; k < BWD_MAX_LEVELS; ++k)
-        if (k < P.n_levels && (int)blockIdx.x >= P.lv[k].tile_base) l = k;
-    const BwdLevel L = pick_level(P, l);
+        if (k < TB.n_levels && (int)blockIdx.x >= TB.base[k]) l = k;
+    const BwdLevel L = lv_table[l];
     int t = blockIdx.x - L.tile_base;
-    const int tx_i = t % L.tiles_x; t /= L.tiles_x;
-    const int ty_i = t % L.tiles_y; t /= L.tiles_y;
-    const int b = t;
+    const int q1 = fast_div(t, L.tiles_x, L.rcp_tiles_x);
+    const int tx_i = t - q1 * L.tiles_x;
+    const int b = fast_div(q1, L.tiles_y, L.rcp_tiles_y);
+    const int ty_i = q1 - b * L.tiles_y;
     const int H = L.H, W = L.W;
     const int py = ty_i * BWD_ROWS + warp;
     if (py >= H) return;
     const int tx0 = tx_i * TW, tx1 = min(tx0 + TW, W) - 1;
     const int CV = C / VEC;
     const int cvbase = blockIdx.y * (32 * NV) + lane;
+    const float em1y = (float)(H - 1), em1x = (float)(W - 1);
 
     // accumulators of the strip's 4 pixels x NV channel vectors: named scalars, so they
     // stay in registers (an indexed array ends up in local memory here)
-    static_assert(TW == 4 && (NV == 1 || NV == 2), "strip shape is fixed at 4 pixels, 1-2 vectors per lane");
+    static_assert(NV == 1 || NV == 2, "1-2 vectors per lane");
     const V zero = make_splat(0.f, (V *)nullptr);
     V p0a = zero, p1a = zero, p2a = zero, p3a = zero;
     V p0b = zero, p1b = zero, p2b = zero, p3b = zero;
     const bool va_ok = cvbase < CV, vb_ok = NV == 2 && cvbase + 32 < CV;
 
-    const int st = L.st_base + (b * L.sg.ny + py / L.sg.side) * L.sg.nx + tx0 / L.sg.side;
+    const int st = L.st_base + (b * L.sg.ny + (py >> L.sg_shift)) * L.sg.nx + (tx0 >> L.sg_shift);
     const int n_list = st_count[st];
     const ListEntry *__restrict__ list = entries + (n_list ? st_off[st] : 0);
     const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cvbase;
     const int S = ph * pw;
+
+#define SLN_BWD_ADD(PA, PB, WX, WW)                                   \
+    {                                                                 \
+        PA = accum<EXACT>(PA, ga, wy, WX, WW);                        \
+        if (NV == 2) PB = accum<EXACT>(PB, gb, wy, WX, WW);           \
+    }
 
     for (int base = 0; base < n_list; base += 32) {
         const int li = base + lane;
@@ -451,29 +543,27 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
             const int bit = __ffs(todo) - 1;
             todo &= todo - 1;
             const int r = __shfl_sync(0xffffffffu, my_roi, bit);
-            const float by1 = __ldg(boxes + 4 * r + 0), bx1 = __ldg(boxes + 4 * r + 1);
-            const float by2 = __ldg(boxes + 4 * r + 2), bx2 = __ldg(boxes + 4 * r + 3);
-            const float sc_y = axis_scale(by1, by2, H, ph), sc_x = axis_scale(bx1, bx2, W, pw);
+            const float4 axv = __ldg(reinterpret_cast<const float4 *>(axes) + r);   // by, sy, bx, sx
             const V *gr = g + (size_t)r * S * CV;
             for (int ky0 = 0; ky0 < ph; ky0 += 32) {
                 Tap ty;
                 ty.lo = INVALID_TAP; ty.lerp = 0.f;
-                if (ky0 + lane < ph) ty = axis_tap(by1, by2, sc_y, H, ph, ky0 + lane);
-                unsigned ym = __ballot_sync(0xffffffffu, ty.lo != INVALID_TAP &&
-                                                             (ty.lo == py || ty.lo + (ty.lerp != 0.f) == py));
+                if (ky0 + lane < ph) ty = tap_at(axv.x, axv.y, em1y, ky0 + lane);
+                unsigned ym = __ballot_sync(0xffffffffu, ty.lo == py || (ty.lo + 1 == py && ty.lerp != 0.f));
                 while (ym) {
                     const int yb = __ffs(ym) - 1;
                     ym &= ym - 1;
                     const int ylo = __shfl_sync(0xffffffffu, ty.lo, yb);
                     const float yl = __shfl_sync(0xffffffffu, ty.lerp, yb);
-                    // row weights that land on py, in tap order (top before bottom)
-                    const bool y_int = (yl == 0.f);                 // floor == ceil: both taps hit this row
+                    // row weight that lands on py; when the sample row is integral (floor == ceil)
+                    // both the top and the bottom tap hit this row, weights 1 and 0, in that order
+                    const bool y_int = (yl == 0.f);
                     const float wy0 = (ylo == py) ? __fsub_rn(1.f, yl) : yl;
                     const int yoff = (ky0 + yb) * pw;
                     for (int kx0 = 0; kx0 < pw; kx0 += 32) {
                         Tap tx;
                         tx.lo = INVALID_TAP; tx.lerp = 0.f;
-                        if (kx0 + lane < pw) tx = axis_tap(bx1, bx2, sc_x, W, pw, kx0 + lane);
+                        if (kx0 + lane < pw) tx = tap_at(axv.z, axv.w, em1x, kx0 + lane);
                         unsigned xm = __ballot_sync(0xffffffffu, tx.lo != INVALID_TAP && tx.lo <= tx1 &&
                                                                      tx.lo + (tx.lerp != 0.f) >= tx0);
                         while (xm) {
@@ -481,39 +571,46 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const float *__restrict__ 
                             xm &= xm - 1;
                             const int xlo = __shfl_sync(0xffffffffu, tx.lo, xb);
                             const float xl = __shfl_sync(0xffffffffu, tx.lerp, xb);
-                            const bool x_int = (xl == 0.f);
                             const float wl = __fsub_rn(1.f, xl), wr = xl;
-                            const int pl = xlo - tx0;               // strip pixel of the left tap (-1 .. TW-1)
+                            const int pl = xlo - tx0;               // strip pixel of the left tap (-1 .. 3)
                             V ga = zero, gb = zero;
                             if (va_ok) ga = ldg_vec(gr + (size_t)(yoff + kx0 + xb) * CV);
                             if (vb_ok) gb = ldg_vec(gr + (size_t)(yoff + kx0 + xb) * CV + 32);
-                            const int pr = x_int ? pl : pl + 1;     // strip pixel of the right tap
-#define SLN_BWD_ADD(PA, PB, WX, WW)                                   \
-    {                                                                 \
-        PA = accum<EXACT>(PA, ga, wy, WX, WW);                        \
-        if (NV == 2) PB = accum<EXACT>(PB, gb, wy, WX, WW);           \
-    }
-                            // one pass per row weight (two only when the sample row is integral)
-                            for (int pass = 0; pass < (y_int ? 2 : 1); ++pass) {
-                                const float wy = pass == 0 ? wy0 : yl;
+                            if (!y_int && xl != 0.f) {
+                                // generic sample: one row weight; left tap on pl, right tap on pl+1
+                                const float wy = wy0;
                                 const float w_l = __fmul_rn(wy, wl), w_r = __fmul_rn(wy, wr);
-                                // left tap (TL / BL) first, then right tap (TR / BR): reference order
-                                if (pl == 0) SLN_BWD_ADD(p0a, p0b, wl, w_l)
-                                else if (pl == 1) SLN_BWD_ADD(p1a, p1b, wl, w_l)
-                                else if (pl == 2) SLN_BWD_ADD(p2a, p2b, wl, w_l)
-                                else if (pl == 3) SLN_BWD_ADD(p3a, p3b, wl, w_l)
-                                if (pr == 0) SLN_BWD_ADD(p0a, p0b, wr, w_r)
-                                else if (pr == 1) SLN_BWD_ADD(p1a, p1b, wr, w_r)
-                                else if (pr == 2) SLN_BWD_ADD(p2a, p2b, wr, w_r)
-                                else if (pr == 3) SLN_BWD_ADD(p3a, p3b, wr, w_r)
+                                switch (pl) {
+                                case -1: SLN_BWD_ADD(p0a, p0b, wr, w_r) break;
+                                case 0: SLN_BWD_ADD(p0a, p0b, wl, w_l) SLN_BWD_ADD(p1a, p1b, wr, w_r) break;
+                                case 1: SLN_BWD_ADD(p1a, p1b, wl, w_l) SLN_BWD_ADD(p2a, p2b, wr, w_r) break;
+                                case 2: SLN_BWD_ADD(p2a, p2b, wl, w_l) SLN_BWD_ADD(p3a, p3b, wr, w_r) break;
+                                default: SLN_BWD_ADD(p3a, p3b, wl, w_l) break;
+                                }
+                            } else {
+                                // integral sample position on an axis: taps coincide; keep the reference's
+                                // TL, TR, BL, BR order per pixel
+                                const int pr = (xl == 0.f) ? pl : pl + 1;
+                                for (int pass = 0; pass < (y_int ? 2 : 1); ++pass) {
+                                    const float wy = pass == 0 ? wy0 : yl;
+                                    const float w_l = __fmul_rn(wy, wl), w_r = __fmul_rn(wy, wr);
+                                    if (pl == 0) SLN_BWD_ADD(p0a, p0b, wl, w_l)
+                                    else if (pl == 1) SLN_BWD_ADD(p1a, p1b, wl, w_l)
+                                    else if (pl == 2) SLN_BWD_ADD(p2a, p2b, wl, w_l)
+                                    else if (pl == 3) SLN_BWD_ADD(p3a, p3b, wl, w_l)
+                                    if (pr == 0) SLN_BWD_ADD(p0a, p0b, wr, w_r)
+                                    else if (pr == 1) SLN_BWD_ADD(p1a, p1b, wr, w_r)
+                                    else if (pr == 2) SLN_BWD_ADD(p2a, p2b, wr, w_r)
+                                    else if (pr == 3) SLN_BWD_ADD(p3a, p3b, wr, w_r)
+                                }
                             }
-#undef SLN_BWD_ADD
                         }
                     }
                 }
             }
         }
     }
+#undef SLN_BWD_ADD
 
     // ---- write every pixel of the strip exactly once (zeros included)
     V *__restrict__ o = reinterpret_cast<V *>(L.out) + (((size_t)b * H + py) * W + tx0) * CV + cvbase;
@@ -617,8 +714,10 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
 
 struct BwdWs {
     RoiWin *win;
+    RoiAxes *axes;
     int *st_count;
     int *st_off;
+    BwdLevel *lv_table;
     ListEntry *entries;
 };
 
@@ -628,46 +727,37 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels)
 {
     // every ROI lives on one level and meets at most 64 supertiles of its image
     const size_t n_st = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
-    return align_up(sizeof(RoiWin) * (size_t)N, 256) + 2 * align_up(sizeof(int) * n_st, 256) +
+    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(RoiAxes) * (size_t)N, 256) +
+           2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) +
            align_up(sizeof(ListEntry) * (size_t)N * BWD_MAX_ST, 256);
 }
 
-template <int VEC, int NV, int TW, bool EXACT>
-static int launch_bwd(const float *grads, const float *boxes, const BwdWs &ws, BwdParams &P, int total_tiles_unused,
-                      int C, int ph, int pw, int B, cudaStream_t st)
+template <int VEC, int NV, bool EXACT>
+static int launch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
+                      cudaStream_t st)
 {
-    (void)total_tiles_unused;
-    long long tiles = 0;
-    for (int l = 0; l < P.n_levels; ++l) {
-        BwdLevel &L = P.lv[l];
-        L.tiles_x = cdiv(L.W, TW);
-        L.tiles_y = cdiv(L.H, BWD_ROWS);
-        L.tile_base = (int)tiles;
-        tiles += (long long)L.tiles_x * L.tiles_y * B;
-    }
-    SLN_REQUIRE(tiles < (1ll << 31), SLN_ERR_ARG, "too many tiles");
     const int chunks = cdiv(C / VEC, 32 * NV);
     SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
     if (tiles == 0) return SLN_OK;
+    BwdTileBases TB{};
+    TB.n_levels = P.n_levels;
+    for (int l = 0; l < P.n_levels; ++l) TB.base[l] = P.lv[l].tile_base;
     dim3 grid((unsigned)tiles, chunks);
-    crop_bwd_nhwc_kernel<VEC, NV, TW, EXACT><<<grid, BWD_THREADS, 0, st>>>(grads, boxes, ws.entries, ws.st_off,
-                                                                          ws.st_count, P, C, ph, pw);
+    crop_bwd_nhwc_kernel<VEC, NV, EXACT><<<grid, BWD_THREADS, 0, st>>>(grads, ws.axes, ws.entries, ws.st_off,
+                                                                      ws.st_count, ws.lv_table, TB, C, ph, pw);
     SLN_LAUNCH_OK("crop_bwd_nhwc_kernel");
     return SLN_OK;
 }
 
 template <int VEC, bool EXACT>
-static int dispatch_bwd(const float *grads, const float *boxes, const BwdWs &ws, BwdParams &P, int C, int ph, int pw,
-                        int B, cudaStream_t st)
+static int dispatch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
+                        cudaStream_t st)
 {
     const int CV = C / VEC;
     // two channel vectors per lane halve the control work per byte, but also the CTA count:
     // only use them when the maps provide enough strips to fill the machine
-    long long tiles4 = 0;
-    for (int l = 0; l < P.n_levels; ++l) tiles4 += (long long)cdiv(P.lv[l].W, 4) * cdiv(P.lv[l].H, BWD_ROWS) * B;
-    if (CV > 32 && tiles4 >= 6LL * sm_count())
-        return launch_bwd<VEC, 2, 4, EXACT>(grads, boxes, ws, P, 0, C, ph, pw, B, st);
-    return launch_bwd<VEC, 1, 4, EXACT>(grads, boxes, ws, P, 0, C, ph, pw, B, st);
+    if (CV > 32 && tiles >= 6LL * sm_count()) return launch_bwd<VEC, 2, EXACT>(grads, ws, P, tiles, C, ph, pw, st);
+    return launch_bwd<VEC, 1, EXACT>(grads, ws, P, tiles, C, ph, pw, st);
 }
 
 // grads [N,ph,pw,C]; one grad map per level (NHWC); level[i] selects the map of ROI i (null: level 0)
@@ -682,6 +772,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     BwdParams P{};
     P.n_levels = n_levels;
     int n_st = 0;
+    long long tiles = 0;
     bool vec4 = (C % 4 == 0) && aligned16(grads);
     for (int l = 0; l < n_levels; ++l) {
         BwdLevel &L = P.lv[l];
@@ -689,34 +780,46 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         L.H = Hs[l];
         L.W = Ws[l];
         L.sg = super_grid(L.H, L.W);
+        L.sg_shift = 0;
+        while ((1 << L.sg_shift) < L.sg.side) ++L.sg_shift;
         L.st_base = n_st;
         n_st += B * L.sg.nx * L.sg.ny;
+        L.tiles_x = cdiv(L.W, BWD_TW);
+        L.tiles_y = cdiv(L.H, BWD_ROWS);
+        L.rcp_tiles_x = L.tiles_x ? 1.0f / (float)L.tiles_x : 0.f;
+        L.rcp_tiles_y = L.tiles_y ? 1.0f / (float)L.tiles_y : 0.f;
+        L.tile_base = (int)tiles;
+        tiles += (long long)L.tiles_x * L.tiles_y * B;
         vec4 = vec4 && aligned16(maps[l]);
         SLN_REQUIRE((size_t)L.H * L.W == 0 || maps[l] != nullptr, SLN_ERR_ARG, "null grad map");
     }
+    SLN_REQUIRE(tiles < (1ll << 24), SLN_ERR_ARG, "too many tiles (%lld)", tiles);
     unsigned char *p = static_cast<unsigned char *>(wsp);
     const size_t n_st_cap = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
     BwdWs ws;
     ws.win = reinterpret_cast<RoiWin *>(p);        p += align_up(sizeof(RoiWin) * (size_t)N, 256);
+    ws.axes = reinterpret_cast<RoiAxes *>(p);      p += align_up(sizeof(RoiAxes) * (size_t)N, 256);
     ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * n_st_cap, 256);
     ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
+    ws.lv_table = reinterpret_cast<BwdLevel *>(p); p += align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256);
     ws.entries = reinterpret_cast<ListEntry *>(p);
 
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
+    // the windows kernel also publishes the level table, so it always runs (>= 1 CTA)
+    crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
+        boxes, box_ind, level, N, B, ph, pw, P, ws.win, ws.axes, ws.st_count, ws.lv_table);
+    SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
-        crop_bwd_windows_kernel<<<cdiv(N, 256), 256, 0, st>>>(boxes, box_ind, level, N, B, ph, pw, P, ws.win,
-                                                             ws.st_count);
-        SLN_LAUNCH_OK("crop_bwd_windows_kernel");
         crop_bwd_fill_kernel<<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, N, P, ws.st_count, ws.st_off,
                                                             ws.entries);
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
     if (vec4) {
-        if (exact) return dispatch_bwd<4, true>(grads, boxes, ws, P, C, ph, pw, B, st);
-        return dispatch_bwd<4, false>(grads, boxes, ws, P, C, ph, pw, B, st);
+        if (exact) return dispatch_bwd<4, true>(grads, ws, P, tiles, C, ph, pw, st);
+        return dispatch_bwd<4, false>(grads, ws, P, tiles, C, ph, pw, st);
     }
-    if (exact) return dispatch_bwd<1, true>(grads, boxes, ws, P, C, ph, pw, B, st);
-    return dispatch_bwd<1, false>(grads, boxes, ws, P, C, ph, pw, B, st);
+    if (exact) return dispatch_bwd<1, true>(grads, ws, P, tiles, C, ph, pw, st);
+    return dispatch_bwd<1, false>(grads, ws, P, tiles, C, ph, pw, st);
 }
 
 }  // namespace sln
