@@ -481,8 +481,9 @@ __device__ __forceinline__ int fast_div(int t, int d, float rcp)
 // the reference's serial order (crop_and_resize.c:190-250).
 // EXACT: each term is wx*(wy*g) with every operation rounded like crop_and_resize.c:241-247
 // (bit-identical to the reference CPU backward); otherwise fma(wy*wx, g, acc).
+// 4 resident CTAs per SM (<= 64 registers): measured best on B200 (A/B runs, profiles/README.md)
 template <int VEC, int NV, bool EXACT>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, 4)
 crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict__ axes,
                      const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
                      const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
