@@ -147,7 +147,7 @@ SLN_API int sln_proposal_layer(const float *probs, const float *deltas, const fl
  * codec helpers it drives (modal/Functions.py:1012-1095).  label u64 [B,H,W] (bit i =
  * object i visible, bit 32+i = object i occluded) -> out u8 [B,n_max,L,H,W]
  * (planes of objects >= n_obj are zero), n_obj i32 [B] (not clamped to n_max).
- * scratch: B u32 words of device memory (overwritten).                              */
+ * scratch: 2*B u32 words of device memory (overwritten).                            */
 SLN_API int sln_layer_decode(const uint64_t *label, int B, int H, int W, int L, int n_max,
                      uint8_t *out, int *n_obj, uint32_t *scratch, void *stream);
 

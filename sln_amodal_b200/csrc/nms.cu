@@ -23,30 +23,68 @@ namespace sln {
 // 1. rank sort
 // ---------------------------------------------------------------------------
 constexpr int RANK_ROWS = 256;     // elements ranked per CTA (one per thread)
-constexpr int RANK_COLS = 2048;    // elements compared against per CTA (staged in smem)
+constexpr int RANK_COLS = 1024;    // elements compared against per CTA (staged in smem)
+
+// MODE 0: every column index is below every row index of this CTA  -> count key_j >= key_i
+// MODE 1: every column index is above every row index              -> count key_j >  key_i
+// MODE 2: index ranges overlap, or explicit tie ids                 -> full (key, tie) compare
+template <int MODE>
+__device__ __forceinline__ int rank_count(const uint4 *__restrict__ k4, const int4 *__restrict__ t4, int n4,
+                                          unsigned ki, int ti)
+{
+    int cnt = 0;
+#pragma unroll 4
+    for (int q = 0; q < n4; ++q) {
+        const uint4 k = k4[q];      // broadcast 16-byte shared load: four keys per instruction
+        if (MODE == 0) {
+            cnt += (k.x >= ki) + (k.y >= ki) + (k.z >= ki) + (k.w >= ki);
+        } else if (MODE == 1) {
+            cnt += (k.x > ki) + (k.y > ki) + (k.z > ki) + (k.w > ki);
+        } else {
+            const int4 t = t4[q];
+            cnt += (k.x > ki || (k.x == ki && t.x < ti)) + (k.y > ki || (k.y == ki && t.y < ti)) +
+                   (k.z > ki || (k.z == ki && t.z < ti)) + (k.w > ki || (k.w == ki && t.w < ti));
+        }
+    }
+    return cnt;
+}
 
 __global__ void __launch_bounds__(RANK_ROWS)
 rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict__ tie_ids, int n,
             int *__restrict__ rank)
 {
-    __shared__ unsigned s_key[RANK_COLS];
-    __shared__ int s_tie[RANK_COLS];
-    const int i = blockIdx.x * RANK_ROWS + threadIdx.x;
+    __shared__ __align__(16) unsigned s_key[RANK_COLS];
+    __shared__ __align__(16) int s_tie[RANK_COLS];
+    const int i0 = blockIdx.x * RANK_ROWS, i = i0 + threadIdx.x;
     const int j0 = blockIdx.y * RANK_COLS;
     const int jn = min(RANK_COLS, n - j0);
-    for (int t = threadIdx.x; t < jn; t += RANK_ROWS) {
-        s_key[t] = score_key(__ldg(scores + (size_t)(j0 + t) * stride));
-        s_tie[t] = tie_ids ? __ldg(tie_ids + j0 + t) : (j0 + t);
+    // pad the tile to a multiple of 4 with entries that never count (key 0 with the largest tie id
+    // loses every compare except against key 0 rows in MODE 0, handled by clamping below)
+    for (int t = threadIdx.x; t < RANK_COLS; t += RANK_ROWS) {
+        unsigned k = 0u;
+        int tie = 0x7fffffff;
+        if (t < jn) {
+            k = score_key(__ldg(scores + (size_t)(j0 + t) * stride));
+            tie = tie_ids ? __ldg(tie_ids + j0 + t) : (j0 + t);
+        }
+        s_key[t] = k;
+        s_tie[t] = tie;
     }
     __syncthreads();
     if (i >= n) return;
     const unsigned ki = score_key(__ldg(scores + (size_t)i * stride));
     const int ti = tie_ids ? __ldg(tie_ids + i) : i;
-    int cnt = 0;
-#pragma unroll 8
-    for (int t = 0; t < jn; ++t) {
-        const unsigned kj = s_key[t];
-        cnt += (kj > ki) || (kj == ki && s_tie[t] < ti);
+    const int n4 = (jn + 3) >> 2, pad = n4 * 4 - jn;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key);
+    const int4 *t4 = reinterpret_cast<const int4 *>(s_tie);
+    int cnt;
+    if (tie_ids == nullptr && j0 + jn <= i0) {
+        cnt = rank_count<0>(k4, t4, n4, ki, ti);
+        if (ki == 0u) cnt -= pad;                      // padded keys (0) satisfy 0 >= 0
+    } else if (tie_ids == nullptr && j0 >= i0 + RANK_ROWS) {
+        cnt = rank_count<1>(k4, t4, n4, ki, ti);
+    } else {
+        cnt = rank_count<2>(k4, t4, n4, ki, ti);
     }
     if (cnt) atomicAdd(rank + i, cnt);
 }
@@ -177,12 +215,21 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restri
     __syncthreads();
 
     int total = 0;
+    // diagonal tile rows of the current chunk, prefetched one chunk ahead by warp 0
+    unsigned long long d0 = 0ull, d1 = 0ull;
+    if (warp == 0) {
+        if (lane < n) d0 = mask[(size_t)lane * W];
+        if (lane + 32 < n) d1 = mask[(size_t)(lane + 32) * W];
+    }
     for (int c = 0; c < W; ++c) {
         if (warp == 0) {
-            const int r0 = c * 64 + lane, r1 = r0 + 32;
-            // diagonal tile rows (successor bits are all the loop needs)
-            const unsigned long long d0 = r0 < n ? mask[(size_t)r0 * W + c] : 0ull;
-            const unsigned long long d1 = r1 < n ? mask[(size_t)r1 * W + c] : 0ull;
+            // issue the next chunk's diagonal loads now; they complete during this step
+            unsigned long long n0 = 0ull, n1 = 0ull;
+            if (c + 1 < W) {
+                const int r0 = (c + 1) * 64 + lane, r1 = r0 + 32;
+                if (r0 < n) n0 = __ldg(mask + (size_t)r0 * W + c + 1);
+                if (r1 < n) n1 = __ldg(mask + (size_t)r1 * W + c + 1);
+            }
             const int nb = min(64, n - c * 64);
             const unsigned long long valid = nb == 64 ? ~0ull : ((1ull << nb) - 1ull);
             unsigned long long cand = ~s_removed[c] & valid;
@@ -220,6 +267,8 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restri
                 }
             }
             if (lane == 0) { s_kept = kept; s_total = total + cnt; }
+            d0 = n0;
+            d1 = n1;
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
@@ -228,10 +277,20 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restri
         if (kept) {
             for (int w = c + 1 + tid; w < W; w += SCAN_THREADS) {
                 unsigned long long acc = 0ull, k = kept;
-                while (k) {
-                    const int b = __ffsll((long long)k) - 1;
-                    k &= k - 1ull;
-                    acc |= __ldg(mask + (size_t)(c * 64 + b) * W + w);
+                const unsigned long long *col = mask + (size_t)c * 64 * W + w;
+                while (k) {                    // eight independent loads in flight per batch
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = 0ull;
+                        if (k) {
+                            const int b = __ffsll((long long)k) - 1;
+                            k &= k - 1ull;
+                            v[u] = __ldg(col + (size_t)b * W);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc |= v[u];
                 }
                 s_removed[w] |= acc;
             }

@@ -285,7 +285,7 @@ def layer_decode_device(label, L, n_max):
     B, H, W = label.shape
     out = torch.empty((B, n_max, L, H, W), dtype=torch.uint8, device=label.device)
     n_obj = torch.empty(B, dtype=torch.int32, device=label.device)
-    scratch = torch.empty(max(B, 1), dtype=torch.int32, device=label.device)
+    scratch = torch.empty(2 * max(B, 1), dtype=torch.int32, device=label.device)
     with torch.cuda.device(label.device):
         check(lib().sln_layer_decode(ptr(label), B, H, W, int(L), int(n_max), ptr(out), ptr(n_obj), ptr(scratch),
                                      stream_ptr()), "sln_layer_decode")
@@ -311,6 +311,6 @@ def edt_sq_device(maps):
         check(lib().sln_edt_sq(ptr(maps), M, H, W, ptr(out), ptr(ws), ws.numel(), stream_ptr()), "sln_edt_sq")
     if M and H * W:
         per = 2 * H * W
-        chunk = max(1, min(M, (48 << 20) // per))
+        chunk = max(1, min(M, (2048 << 20) // per))
         _lib.count_launches(2 * ((M + chunk - 1) // chunk))
     return out
