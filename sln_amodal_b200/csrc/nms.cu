@@ -197,112 +197,235 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
 }
 
 // ---------------------------------------------------------------------------
-// 4. greedy scan (single CTA)
+// 4. greedy scan (single CTA, software-pipelined over super-steps of 8 chunks = 512 boxes)
 // ---------------------------------------------------------------------------
+// The scan is inherently sequential in 64-box chunks: chunk c can only be resolved once the
+// kept boxes of chunks < c have been ORed into its `removed` word.  To keep global-memory
+// latency off that chain, the mask is consumed in two ways:
+//   band(k)  rows of super-step k x the 16 words [8k, 8k+16): fetched UNCONDITIONALLY into
+//            shared memory with cp.async one super-step ahead (double buffered).  Warp 0
+//            resolves the 8 chunks of a super-step from shared memory alone: the diagonal word
+//            gives the in-chunk relation (resolved by a ballot fixpoint, typically 2-3 rounds),
+//            the other band words carry the kept rows into the next <= 15 words.
+//   far(k)   kept rows of super-step k x words >= 8k+16: read from global memory by the other
+//            31 warps while warp 0 already resolves super-step k+1 (they have a whole
+//            super-step of slack); results land in the shared `removed` words via atomicOr.
+// One block barrier per super-step; nothing else synchronises.
 constexpr int SCAN_THREADS = 1024;
+constexpr int SS_CHUNKS = 8;                       // chunks per super-step
+constexpr int SS_ROWS = 64 * SS_CHUNKS;            // boxes per super-step
+constexpr int BAND_WORDS = 2 * SS_CHUNKS;          // words of a band row
+constexpr int BAND_STRIDE = BAND_WORDS + 1;        // padded row stride (u64) against bank conflicts
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ order, int n, int W,
-                int max_keep, int64_t *__restrict__ keep64, int *__restrict__ keep32,
-                int *__restrict__ num_keep)
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 {
-    extern __shared__ unsigned long long s_removed[];      // [W]
-    __shared__ unsigned long long s_kept;
-    __shared__ int s_total;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__device__ __forceinline__ unsigned long long ballot64(bool a, bool b)
+{
+    const unsigned lo = __ballot_sync(0xffffffffu, a), hi = __ballot_sync(0xffffffffu, b);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// n may live in device memory (n_dev != nullptr): the two-stage pipeline compacts on the device
+__global__ void __launch_bounds__(SCAN_THREADS)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ order, int n_host,
+                const int *__restrict__ n_dev, int W_stride, int max_keep_host, const int *__restrict__ keep_base_dev,
+                int64_t *__restrict__ keep64, int *__restrict__ keep32, int *__restrict__ num_keep)
+{
+    extern __shared__ __align__(16) unsigned long long s_mem[];
+    const int n = n_dev ? *n_dev : n_host;
+    const int W = (n + 63) >> 6;
+    // keep_base: survivors already emitted by an earlier stage (they count against max_keep)
+    const int keep_base = keep_base_dev ? *keep_base_dev : 0;
+    const int max_keep = max_keep_host;
+    unsigned long long *s_removed = s_mem;                                      // [W_stride]
+    unsigned long long *s_band = s_mem + W_stride;                              // [2][SS_ROWS][BAND_STRIDE]
+    int *s_klist = reinterpret_cast<int *>(s_band + 2 * SS_ROWS * BAND_STRIDE); // [2][SS_ROWS]
+    __shared__ unsigned long long s_K[2][SS_CHUNKS];   // kept bits of the chunks of a super-step
+    __shared__ int s_base[2];                          // survivors emitted before the super-step
+    __shared__ int s_nk[2];
+    __shared__ int s_total, s_stop;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int w = tid; w < W; w += SCAN_THREADS) s_removed[w] = 0ull;
-    if (tid == 0) { s_total = 0; s_kept = 0ull; }
+    if (tid == 0) { s_total = keep_base; s_stop = (keep_base >= max_keep || n == 0) ? 1 : 0; s_nk[0] = s_nk[1] = 0; }
+
+    auto prefetch_band = [&](int k, int first_thread, int nthreads) {
+        unsigned long long *dst = s_band + (size_t)(k & 1) * SS_ROWS * BAND_STRIDE;
+        const int row0 = k * SS_ROWS, w0 = k * SS_CHUNKS;
+        for (int i = tid - first_thread; i < SS_ROWS * BAND_WORDS; i += nthreads) {
+            const int rl = i / BAND_WORDS, wl = i - rl * BAND_WORDS;
+            const int row = row0 + rl, w = w0 + wl;
+            if (row < n && w < W) cp_async_8(dst + rl * BAND_STRIDE + wl, mask + (size_t)row * W_stride + w);
+            else dst[rl * BAND_STRIDE + wl] = 0ull;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // emit the survivors of chunk j of super-step kk (kept bits in s_K, count before the super-step in
+    // s_base): one warp per chunk, so the eight chunks' dependent order[] loads overlap
+    auto emit = [&](int kk, int j) {
+        const int c = kk * SS_CHUNKS + j;
+        int before = 0, all = 0;
+#pragma unroll
+        for (int jj = 0; jj < SS_CHUNKS; ++jj) {
+            const int cnt = __popcll(s_K[kk & 1][jj]);
+            if (jj < j) before += cnt;
+            all += cnt;
+        }
+        if (j == 0 && lane == 0) s_nk[kk & 1] = all;
+        if (c >= W) return;
+        const unsigned long long K = s_K[kk & 1][j];
+        const int total = s_base[kk & 1] + before;
+        int *klist = s_klist + (kk & 1) * SS_ROWS;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int b = lane + 32 * half;
+            if ((K >> b) & 1ull) {
+                const int off = __popcll(K & ((1ull << b) - 1ull));
+                const int pos = c * 64 + b;
+                const int idx = order ? order[pos] : pos;
+                if (keep64) keep64[total + off] = idx;
+                if (keep32) keep32[total + off] = idx;
+                klist[before + off] = pos;
+            }
+        }
+    };
+
+    const int n_super = (W + SS_CHUNKS - 1) / SS_CHUNKS;
+    prefetch_band(0, 0, SCAN_THREADS);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    int total = 0;
-    // diagonal tile rows of the current chunk, prefetched one chunk ahead by warp 0
-    unsigned long long d0 = 0ull, d1 = 0ull;
-    if (warp == 0) {
-        if (lane < n) d0 = mask[(size_t)lane * W];
-        if (lane + 32 < n) d1 = mask[(size_t)(lane + 32) * W];
-    }
-    for (int c = 0; c < W; ++c) {
+    int k = 0;
+    for (; k < n_super; ++k) {
+        if (s_stop) break;
+        const unsigned long long *band = s_band + (size_t)(k & 1) * SS_ROWS * BAND_STRIDE;
         if (warp == 0) {
-            // issue the next chunk's diagonal loads now; they complete during this step
-            unsigned long long n0 = 0ull, n1 = 0ull;
-            if (c + 1 < W) {
-                const int r0 = (c + 1) * 64 + lane, r1 = r0 + 32;
-                if (r0 < n) n0 = __ldg(mask + (size_t)r0 * W + c + 1);
-                if (r1 < n) n1 = __ldg(mask + (size_t)r1 * W + c + 1);
-            }
-            const int nb = min(64, n - c * 64);
-            const unsigned long long valid = nb == 64 ? ~0ull : ((1ull << nb) - 1ull);
-            unsigned long long cand = ~s_removed[c] & valid;
-            unsigned long long kept = 0ull;
-            while (cand) {
-                const int b = __ffsll((long long)cand) - 1;
-                kept |= 1ull << b;
-                const unsigned long long ra = __shfl_sync(0xffffffffu, d0, b & 31);
-                const unsigned long long rb_ = __shfl_sync(0xffffffffu, d1, b & 31);
-                const unsigned long long row = b < 32 ? ra : rb_;
-                cand &= ~row;
-                cand &= ~(1ull << b);
-            }
-            int cnt = __popcll(kept);
-            if (total + cnt > max_keep) {      // keep only the first (max_keep-total) survivors
-                int need = max_keep - total;
-                unsigned long long k2 = 0ull, rest = kept;
-                while (need-- > 0) {
-                    const int b = __ffsll((long long)rest) - 1;
-                    k2 |= 1ull << b;
-                    rest &= ~(1ull << b);
+            // ------------------------------------------------ resolve the 8 chunks of super-step k (the serial chain)
+            int total = s_total;
+            if (lane == 0) s_base[k & 1] = total;
+            if (lane < SS_CHUNKS) s_K[k & 1][lane] = 0ull;
+            __syncwarp();
+            for (int j = 0; j < SS_CHUNKS; ++j) {
+                const int c = k * SS_CHUNKS + j;
+                if (c >= W) break;
+                const int nb = min(64, n - c * 64);
+                const unsigned long long valid = nb == 64 ? ~0ull : ((1ull << nb) - 1ull);
+                // predecessor sets of my two boxes inside the chunk (diagonal tiles are symmetric)
+                const unsigned long long p0 = band[(64 * j + lane) * BAND_STRIDE + j] & ((1ull << lane) - 1ull);
+                const unsigned long long p1 = band[(64 * j + lane + 32) * BAND_STRIDE + j] & ((1ull << (lane + 32)) - 1ull);
+                const unsigned long long U = ~s_removed[c] & valid;
+                const bool u0 = (U >> lane) & 1ull, u1 = (U >> (lane + 32)) & 1ull;
+                // K is the unique fixed point of  K = { b in U : no a in K, a < b, overlaps b }  (the
+                // relation is acyclic); iterate from K = U until stable: 2 ANDs + 2 ballots per round
+                unsigned long long K = U;
+                for (;;) {
+                    const unsigned long long Kn = ballot64(u0 && !(p0 & K), u1 && !(p1 & K));
+                    if (Kn == K) break;
+                    K = Kn;
                 }
-                kept = k2;
-                cnt = __popcll(kept);
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int b = lane + 32 * half;
-                if ((kept >> b) & 1ull) {
-                    const int slot = total + __popcll(kept & ((1ull << b) - 1ull));
-                    const int pos = c * 64 + b;
-                    const int idx = order ? order[pos] : pos;
-                    if (keep64) keep64[slot] = idx;
-                    if (keep32) keep32[slot] = idx;
+                int cnt = __popcll(K);
+                if (total + cnt > max_keep) {          // keep only the first (max_keep-total) survivors
+                    int need = max_keep - total;
+                    unsigned long long k2 = 0ull, rest = K;
+                    while (need-- > 0) {
+                        const int b = __ffsll((long long)rest) - 1;
+                        k2 |= 1ull << b;
+                        rest &= ~(1ull << b);
+                    }
+                    K = k2;
+                    cnt = __popcll(K);
                 }
+                if (lane == 0) s_K[k & 1][j] = K;
+                total += cnt;
+                if (total >= max_keep) { if (lane == 0) s_stop = 1; break; }
+                // carry the kept rows into the band words after the diagonal: lane = (word wl, half of K);
+                // only set bits of K are visited
+                if (K) {
+                    const int wl = lane & 15, half = lane >> 4;
+                    unsigned long long acc = 0ull;
+                    unsigned kb = (unsigned)(K >> (32 * half));
+                    const unsigned long long *rows = band + (size_t)(64 * j + 32 * half) * BAND_STRIDE + wl;
+                    while (kb) {
+                        const int i = __ffs(kb) - 1;
+                        kb &= kb - 1u;
+                        acc |= rows[i * BAND_STRIDE];
+                    }
+                    acc |= shfl_xor_u64(acc, 16);
+                    const int w = k * SS_CHUNKS + wl;
+                    // atomic: the background warps OR into words >= 8k+8 at the same time
+                    if (half == 0 && wl > j && w < W && acc) atomicOr(s_removed + w, acc);
+                }
+                __syncwarp();
             }
-            if (lane == 0) { s_kept = kept; s_total = total + cnt; }
-            d0 = n0;
-            d1 = n1;
-        }
-        __syncthreads();
-        const unsigned long long kept = s_kept;
-        total = s_total;
-        if (total >= max_keep) break;
-        if (kept) {
-            for (int w = c + 1 + tid; w < W; w += SCAN_THREADS) {
-                unsigned long long acc = 0ull, k = kept;
-                const unsigned long long *col = mask + (size_t)c * 64 * W + w;
-                while (k) {                    // eight independent loads in flight per batch
-                    unsigned long long v[8];
+            if (lane == 0) s_total = total;
+        } else {
+            // ------------------------------------------------ background warps
+            // (0) next band: asynchronous copies, waited for at the end of the iteration
+            if (k + 1 < n_super) prefetch_band(k + 1, 32, SCAN_THREADS - 32);
+            // (1) warps 1..8 write out the survivors of super-step k-1 and build its row list
+            if (k >= 1 && warp <= SS_CHUNKS) emit(k - 1, warp - 1);
+            asm volatile("bar.sync 1, %0;" ::"r"(SCAN_THREADS - 32) : "memory");
+            // (2) far update: kept rows of super-step k-1 x words >= 8(k+1), straight from global memory
+            if (k >= 1) {
+                const int kp = k - 1;
+                const int nk = s_nk[kp & 1];
+                const int *klist = s_klist + (kp & 1) * SS_ROWS;
+                const int wbeg = (kp + 2) * SS_CHUNKS;
+                const int nw = W - wbeg;
+                if (nw > 0 && nk > 0) {
+                    // thread = (word, row group): a fixed word per thread, rows strided by the group
+                    // count, eight independent loads in flight, one atomicOr per thread at the end
+                    const int T = SCAN_THREADS - 32, t = tid - 32;
+                    const int cols = min(nw, T);
+                    const int groups = max(1, T / cols);
+                    const int g = t / cols, wi = t - g * cols;
+                    if (g < groups) {
+                        for (int w = wbeg + wi; w < W; w += cols) {
+                            const unsigned long long *col = mask + w;
+                            unsigned long long acc = 0ull;
+                            for (int r0 = g; r0 < nk; r0 += 8 * groups) {
+                                unsigned long long v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = 0ull;
-                        if (k) {
-                            const int b = __ffsll((long long)k) - 1;
-                            k &= k - 1ull;
-                            v[u] = __ldg(col + (size_t)b * W);
+                                for (int u = 0; u < 8; ++u) {
+                                    const int r = r0 + u * groups;
+                                    v[u] = r < nk ? __ldg(col + (size_t)klist[r] * W_stride) : 0ull;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) acc |= v[u];
+                            }
+                            if (acc) atomicOr(s_removed + w, acc);
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) acc |= v[u];
                 }
-                s_removed[w] |= acc;
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
     }
-    if (tid == 0) *num_keep = total;
+    // survivors of the last resolved super-step
+    if (warp >= 1 && warp <= SS_CHUNKS && k >= 1) emit(k - 1, warp - 1);
+    if (tid == 0) *num_keep = min(s_total, max_keep);
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+static size_t scan_smem_bytes(int W)
+{
+    return sizeof(unsigned long long) * ((size_t)W + 2 * (size_t)SS_ROWS * BAND_STRIDE) + sizeof(int) * 2 * SS_ROWS;
+}
+
 size_t nms_buffers_bytes(int n)
 {
     const size_t W = (size_t)cdiv(n, 64);
@@ -343,11 +466,10 @@ int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, c
     else
         nms_mask_kernel<false><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n, W, n_tiles, thresh, mask);
     SLN_LAUNCH_OK("nms_mask_kernel");
-    const size_t smem = sizeof(unsigned long long) * (size_t)W;
-    SLN_REQUIRE(smem <= 200 * 1024, SLN_ERR_ARG, "nms: n=%d too large for the scan kernel", n);
-    if (smem > 48 * 1024)
-        SLN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(mask, order, n, W, max_keep, keep64, keep32, num_keep);
+    const size_t smem = scan_smem_bytes(W);
+    SLN_REQUIRE(smem <= 220 * 1024, SLN_ERR_ARG, "nms: n=%d too large for the scan kernel", n);
+    SLN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(mask, order, n, nullptr, W, max_keep, nullptr, keep64, keep32, num_keep);
     SLN_LAUNCH_OK("nms_scan_kernel");
     return SLN_OK;
 }
