@@ -315,6 +315,42 @@ def per_class_nms(boxes, class_ids, scores, thresh):
     return np.unique(np.concatenate(kept)).astype(np.int64)
 
 
+def refine_detections(rois, probs, deltas, window, image_hw=(1024, 1024), std_dev=(0.1, 0.1, 0.2, 0.2),
+                      use_nms=True, min_confidence=0.3, nms_threshold=0.3):
+    """refine_detections (Functions.py:453-557) for one image in numpy fp32 (exp from torch CPU).
+    Returns (detections [M,6] = (y1,x1,y2,x2,class_id,score), keep indices [M]); empty arrays when
+    nothing survives."""
+    rois, probs, deltas = _f32(rois), _f32(probs), _f32(deltas)
+    n = rois.shape[0]
+    class_ids = probs.argmax(1)                                           # :468
+    idx = np.arange(n)
+    class_scores = probs[idx, class_ids]
+    d = deltas[idx, class_ids] * np.asarray(std_dev, np.float32).reshape(1, 4)   # coordinate_convert :436-450
+    refined = apply_box_deltas(rois, d)
+    H, W = image_hw
+    refined = refined * np.asarray([H, W, H, W], np.float32)
+    refined = clip_boxes(refined, window)                                 # clip_to_window :423-433
+    refined = np.rint(refined).astype(np.float32)                         # torch.round: half to even, :485
+    keep_bool = class_ids > 0
+    if use_nms:
+        if min_confidence:
+            keep_bool = keep_bool & (class_scores >= np.float32(min_confidence))
+        keep = np.nonzero(keep_bool)[0]
+        if keep.size == 0:
+            return np.zeros((0, 6), np.float32), np.zeros(0, np.int64)
+        nms_keep = per_class_nms(refined[keep], class_ids[keep], class_scores[keep], nms_threshold)   # :506-525
+        keep = keep[nms_keep]
+    else:
+        keep = np.nonzero(keep_bool)[0]
+        if keep.size > 100:                                               # :528-532
+            keep = keep[stable_order(class_scores[keep])[:100]]
+    if keep.size == 0:
+        return np.zeros((0, 6), np.float32), np.zeros(0, np.int64)
+    keep = keep[stable_order(class_scores[keep])]                         # :538-546
+    det = np.concatenate([refined[keep], class_ids[keep, None].astype(np.float32), class_scores[keep, None]], 1)
+    return det.astype(np.float32), keep.astype(np.int64)
+
+
 # ---------------------------------------------------------------------------
 # the reference's own C, unmodified (oracle/_ref)
 # ---------------------------------------------------------------------------

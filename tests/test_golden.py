@@ -1,0 +1,132 @@
+"""Golden fixtures produced by the reference's own Python (tests/golden/make_golden.py, run in the
+build container where /root/reference exists).  CPU tests pin the oracle restatement to them;
+GPU tests hold the CUDA path to the same vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def smooth_map(C, H, W, phase):
+    c = np.arange(C, dtype=np.float32)[:, None, None]
+    y = np.arange(H, dtype=np.float32)[None, :, None]
+    x = np.arange(W, dtype=np.float32)[None, None, :]
+    v = np.sin(np.float32(0.37) * y + np.float32(0.11) * c + np.float32(phase)) * np.cos(np.float32(0.23) * x - np.float32(0.05) * c)
+    return (v + np.float32(0.01) * (y * x % np.float32(7.0))).astype(np.float32)[None]
+
+
+def pyramid_maps(g):
+    C = int(g["channels"])
+    return [smooth_map(C, int(s), int(s), 0.3 * i) for i, s in enumerate(g["sides"])]
+
+
+def layer_cases():
+    g = load("load_layer2")
+    for i in range(int(g["n_cases"])):
+        shape = tuple(int(v) for v in g["shape%d" % i])
+        ref = np.unpackbits(g["mask_layers%d" % i])[: int(np.prod(shape))].reshape(shape).astype(bool)
+        yield g["label%d" % i], int(g["num_classes%d" % i]), ref, g["class_ids%d" % i]
+
+
+class Cfg:
+    RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    IMAGE_SHAPE = np.array([1024, 1024, 3])
+    GPU_COUNT = 1
+    USE_NMS = True
+    DETECTION_MIN_CONFIDENCE = 0.3
+    DETECTION_NMS_THRESHOLD = 0.3
+    DETECTION_MAX_INSTANCES = 100
+    NUM_CLASSES = 3
+
+
+# ------------------------------------------------------------------ CPU: oracle vs reference Python
+def test_oracle_proposal_layer_matches_reference_python():
+    g = load("proposal_layer")
+    got = oracle.proposal_layer(g["probs"], g["deltas"], g["anchors"], int(g["proposal_count"]), float(g["nms_threshold"]))
+    assert got.shape == g["out"][0].shape
+    assert got.tobytes() == g["out"][0].tobytes()
+
+
+def test_oracle_pyramid_roi_align_matches_reference_python():
+    g = load("pyramid_roi_align")
+    maps = pyramid_maps(g)
+    for pool, key in ((7, "pooled7"), (16, "pooled16")):
+        got = oracle.pyramid_roi_align(g["boxes"], maps, pool, (256, 256))
+        assert got.tobytes() == g[key].tobytes()
+    img = oracle.crop_and_resize_fwd(maps[1], g["boxes"], np.zeros(g["boxes"].shape[0], np.int32), 8, 8, 0.0)
+    assert img.tobytes() == g["image_crop8"].tobytes()
+
+
+def test_oracle_refine_detections_matches_reference_python():
+    g = load("refine_detections")
+    det, keep = oracle.refine_detections(g["rois"], g["probs"], g["deltas"], g["window"])
+    assert np.array_equal(keep, g["keep"])
+    assert det.tobytes() == g["detections"].tobytes()
+
+
+def test_oracle_layer_codec_matches_reference_python():
+    for label, nc, ref, class_ids in layer_cases():
+        loops = oracle.layer_decode_loops(label, nc)
+        assert np.array_equal(loops, ref)
+        planes, n_obj = oracle.layer_decode(label, nc - 1, n_max=16)
+        assert n_obj == ref.shape[3] == class_ids.size and np.all(class_ids == 1)
+        assert np.array_equal(planes[:n_obj].transpose(2, 3, 1, 0).astype(bool), ref)
+
+
+# ------------------------------------------------------------------ GPU: CUDA path vs reference Python
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.gpu
+def test_gpu_proposal_layer_matches_reference_python():
+    from sln_amodal_b200 import proposal_layer
+    g = load("proposal_layer")
+    got = proposal_layer([cuda(g["probs"]).unsqueeze(0), cuda(g["deltas"]).unsqueeze(0)], int(g["proposal_count"]),
+                         float(g["nms_threshold"]), cuda(g["anchors"]), Cfg())
+    assert tuple(got.shape) == g["out"].shape
+    np.testing.assert_allclose(got.cpu().numpy(), g["out"], rtol=3e-7, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_pyramid_roi_align_matches_reference_python():
+    from sln_amodal_b200 import pyramid_roi_align, pyramid_roi_align_image
+    g = load("pyramid_roi_align")
+    maps = pyramid_maps(g)
+    for cl in (False, True):
+        tm = [cuda(m).contiguous(memory_format=torch.channels_last) if cl else cuda(m) for m in maps]
+        for pool, key in ((7, "pooled7"), (16, "pooled16")):
+            got = pyramid_roi_align([cuda(g["boxes"]).unsqueeze(0)] + tm, pool, (256, 256, 3))
+            assert got.contiguous().cpu().numpy().tobytes() == g[key].tobytes()
+        img = pyramid_roi_align_image([cuda(g["boxes"]).unsqueeze(0), tm[1]], 8, (256, 256, 3))
+        assert img.contiguous().cpu().numpy().tobytes() == g["image_crop8"].tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_refine_detections_matches_reference_python():
+    from sln_amodal_b200 import refine_detections
+    g = load("refine_detections")
+    det, keep = refine_detections(cuda(g["rois"]), cuda(g["probs"]), cuda(g["deltas"]), g["window"], Cfg())
+    assert np.array_equal(keep.cpu().numpy(), g["keep"])
+    np.testing.assert_allclose(det.cpu().numpy(), g["detections"], rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_layer_decode_matches_reference_python():
+    from sln_amodal_b200 import decode_layers
+    for label, nc, ref, _ in layer_cases():
+        planes, n_obj = decode_layers(label, nc, n_max=16)
+        n = int(n_obj[0])
+        assert n == ref.shape[3]
+        got = planes[0, :n].permute(2, 3, 1, 0).cpu().numpy().astype(bool)
+        assert np.array_equal(got, ref)
+        assert not planes[0, n:].any()
