@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import nms as _nms
+from .nms import batched_nms
 
 
 def apply_box_deltas(boxes, deltas):
@@ -52,7 +52,7 @@ def refine_detections(rois, probs, deltas, window, config):
         keep = torch.nonzero(keep_bool)[:, 0]
         if keep.numel() == 0:
             return [], []
-        nms_keep = _nms.batched_nms(refined[keep], class_scores[keep], class_ids[keep],
+        nms_keep = batched_nms(refined[keep], class_scores[keep], class_ids[keep],
                                     config.DETECTION_NMS_THRESHOLD)               # :506-525 in one call
         keep = keep[nms_keep]
     else:
