@@ -33,18 +33,24 @@ struct PyramidMaps {
     int W[8];
 };
 
+// Per-sample record built once per CTA: offsets of the four taps inside the ROI's image (units of
+// VEC floats, channel vector 0) and the two lerp weights; o00 < 0 marks an extrapolated sample.
+struct SampleRec {
+    int o00, o01, o10, o11;
+    float xl, yl;
+};
+
 // img/out addressed in units of VEC floats.  LEVELS: take the source map from
 // `pm` by level[r]; otherwise use pm.map[0].
 template <int VEC, bool LEVELS>
 __global__ void __launch_bounds__(256)
 crop_fwd_nhwc_kernel(PyramidMaps pm, int B, int C, const float *__restrict__ boxes,
                      const int *__restrict__ box_ind, const int *__restrict__ level, int n_levels,
-                     int ph, int pw, float ext, float *__restrict__ out)
+                     int ph, int pw, int band, float ext, float *__restrict__ out)
 {
     using V = typename VecT<VEC>::type;
-    extern __shared__ Tap s_tab[];          // [ph] y taps, then [pw] x taps
-    Tap *ytab = s_tab;
-    Tap *xtab = s_tab + ph;
+    extern __shared__ __align__(16) unsigned char s_fwd_raw[];
+    SampleRec *rec = reinterpret_cast<SampleRec *>(s_fwd_raw);      // [band]: samples [s_lo, s_hi) of the crop
 
     const int r = blockIdx.x;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -62,11 +68,10 @@ crop_fwd_nhwc_kernel(PyramidMaps pm, int B, int C, const float *__restrict__ box
         for (int l = 1; l < 8; ++l)
             if (l == lv) { H = pm.H[l]; W = pm.W[l]; mp = pm.map[l]; }
     }
-    const V *__restrict__ img = reinterpret_cast<const V *>(mp);
     V *__restrict__ o = reinterpret_cast<V *>(out);
     const int CV = C / VEC;
-    const int S = ph * pw;
-    const size_t out_base = (size_t)r * S * CV;
+    const int s_lo = blockIdx.y * band, S = min(ph * pw - s_lo, band);     // this CTA's slice of the crop
+    const size_t out_base = ((size_t)r * ph * pw + s_lo) * CV;
 
     if (!ok) {   // reference GPU kernel skips such boxes (kernel.cu:34-38): rows stay zero
         V z = make_splat(0.f, (V *)nullptr);
@@ -76,72 +81,53 @@ crop_fwd_nhwc_kernel(PyramidMaps pm, int B, int C, const float *__restrict__ box
 
     const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1];
     const float y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
-    if (tid < ph) {
-        ytab[tid] = axis_tap(y1, y2, axis_scale(y1, y2, H, ph), H, ph, tid);
-    } else if (tid < ph + pw) {
-        const int k = tid - ph;
-        xtab[k] = axis_tap(x1, x2, axis_scale(x1, x2, W, pw), W, pw, k);
-    }
-    for (int k = tid + nthr; k < ph + pw; k += nthr) {   // crops larger than the block
-        if (k < ph) ytab[k] = axis_tap(y1, y2, axis_scale(y1, y2, H, ph), H, ph, k);
-        else xtab[k - ph] = axis_tap(x1, x2, axis_scale(x1, x2, W, pw), W, pw, k - ph);
+    const float sc_y = axis_scale(y1, y2, H, ph), sc_x = axis_scale(x1, x2, W, pw);
+    for (int s = tid; s < S; s += nthr) {
+        const int y = (s_lo + s) / pw, x = (s_lo + s) - y * pw;
+        const Tap ty = axis_tap(y1, y2, sc_y, H, ph, y), tx = axis_tap(x1, x2, sc_x, W, pw, x);
+        SampleRec q;
+        q.o00 = -1; q.o01 = q.o10 = q.o11 = 0;
+        q.xl = tx.lerp; q.yl = ty.lerp;
+        if (ty.lo != INVALID_TAP && tx.lo != INVALID_TAP) {
+            const int yh = ty.lo + (ty.lerp != 0.f), xh = tx.lo + (tx.lerp != 0.f);
+            q.o00 = (ty.lo * W + tx.lo) * CV; q.o01 = (ty.lo * W + xh) * CV;
+            q.o10 = (yh * W + tx.lo) * CV;    q.o11 = (yh * W + xh) * CV;
+        }
+        rec[s] = q;
     }
     __syncthreads();
 
     const V vext = make_splat(ext, (V *)nullptr);
-    const size_t img_base = (size_t)b * H * W * CV;
+    const V *__restrict__ img = reinterpret_cast<const V *>(mp) + (size_t)b * H * W * CV;
     const int sstep = blockDim.y;
 
     for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
+        const V *__restrict__ imc = img + cv;
+        V *__restrict__ oc = o + out_base + cv;
         int s = threadIdx.y;
         // two sample points per iteration: 8 independent 16-byte loads in flight
         for (; s + sstep < S; s += 2 * sstep) {
-            const int sA = s, sB = s + sstep;
-            const int yA = sA / pw, xA = sA - yA * pw;
-            const int yB = sB / pw, xB = sB - yB * pw;
-            const Tap tyA = ytab[yA], txA = xtab[xA];
-            const Tap tyB = ytab[yB], txB = xtab[xB];
-            const bool vA = (tyA.lo != INVALID_TAP) && (txA.lo != INVALID_TAP);
-            const bool vB = (tyB.lo != INVALID_TAP) && (txB.lo != INVALID_TAP);
+            const SampleRec qa = rec[s], qb = rec[s + sstep];
             V a0, a1, a2, a3, b0, b1, b2, b3;
-            if (vA) {
-                const int yh = tyA.lo + (tyA.lerp != 0.f), xh = txA.lo + (txA.lerp != 0.f);
-                const V *p0 = img + img_base + ((size_t)tyA.lo * W) * CV + cv;
-                const V *p1 = img + img_base + ((size_t)yh * W) * CV + cv;
-                a0 = ldg_vec(p0 + (size_t)txA.lo * CV);
-                a1 = ldg_vec(p0 + (size_t)xh * CV);
-                a2 = ldg_vec(p1 + (size_t)txA.lo * CV);
-                a3 = ldg_vec(p1 + (size_t)xh * CV);
+            if (qa.o00 >= 0) {
+                a0 = ldg_vec(imc + qa.o00); a1 = ldg_vec(imc + qa.o01);
+                a2 = ldg_vec(imc + qa.o10); a3 = ldg_vec(imc + qa.o11);
             }
-            if (vB) {
-                const int yh = tyB.lo + (tyB.lerp != 0.f), xh = txB.lo + (txB.lerp != 0.f);
-                const V *p0 = img + img_base + ((size_t)tyB.lo * W) * CV + cv;
-                const V *p1 = img + img_base + ((size_t)yh * W) * CV + cv;
-                b0 = ldg_vec(p0 + (size_t)txB.lo * CV);
-                b1 = ldg_vec(p0 + (size_t)xh * CV);
-                b2 = ldg_vec(p1 + (size_t)txB.lo * CV);
-                b3 = ldg_vec(p1 + (size_t)xh * CV);
+            if (qb.o00 >= 0) {
+                b0 = ldg_vec(imc + qb.o00); b1 = ldg_vec(imc + qb.o01);
+                b2 = ldg_vec(imc + qb.o10); b3 = ldg_vec(imc + qb.o11);
             }
-            const V ra = vA ? lerp2v(a0, a1, a2, a3, txA.lerp, tyA.lerp) : vext;
-            const V rb = vB ? lerp2v(b0, b1, b2, b3, txB.lerp, tyB.lerp) : vext;
-            __stcs(o + out_base + (size_t)sA * CV + cv, ra);
-            __stcs(o + out_base + (size_t)sB * CV + cv, rb);
+            const V ra = qa.o00 >= 0 ? lerp2v(a0, a1, a2, a3, qa.xl, qa.yl) : vext;
+            const V rb = qb.o00 >= 0 ? lerp2v(b0, b1, b2, b3, qb.xl, qb.yl) : vext;
+            __stcs(oc + (size_t)s * CV, ra);
+            __stcs(oc + (size_t)(s + sstep) * CV, rb);
         }
         if (s < S) {
-            const int y = s / pw, x = s - y * pw;
-            const Tap ty = ytab[y], tx = xtab[x];
+            const SampleRec q = rec[s];
             V res = vext;
-            if (ty.lo != INVALID_TAP && tx.lo != INVALID_TAP) {
-                const int yh = ty.lo + (ty.lerp != 0.f), xh = tx.lo + (tx.lerp != 0.f);
-                const V *p0 = img + img_base + ((size_t)ty.lo * W) * CV + cv;
-                const V *p1 = img + img_base + ((size_t)yh * W) * CV + cv;
-                const V a0 = ldg_vec(p0 + (size_t)tx.lo * CV);
-                const V a1 = ldg_vec(p0 + (size_t)xh * CV);
-                const V a2 = ldg_vec(p1 + (size_t)tx.lo * CV);
-                const V a3 = ldg_vec(p1 + (size_t)xh * CV);
-                res = lerp2v(a0, a1, a2, a3, tx.lerp, ty.lerp);
-            }
-            __stcs(o + out_base + (size_t)s * CV + cv, res);
+            if (q.o00 >= 0)
+                res = lerp2v(ldg_vec(imc + q.o00), ldg_vec(imc + q.o01), ldg_vec(imc + q.o10), ldg_vec(imc + q.o11), q.xl, q.yl);
+            __stcs(oc + (size_t)s * CV, res);
         }
     }
 }
@@ -700,14 +686,19 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
     const int CV = vec4 ? C / 4 : C;
     dim3 block;
     fwd_block_shape(CV, block);
-    const size_t smem = sizeof(Tap) * (size_t)(ph + pw);
-    dim3 grid(N);
+    const int band = ph * pw < 2048 ? ph * pw : 2048;        // samples per CTA (48 KB of records at most)
+    const size_t smem = sizeof(SampleRec) * (size_t)band;
+    size_t plane_max = 0;
+    for (int l = 0; l < n_levels; ++l) plane_max = plane_max > (size_t)pm.H[l] * pm.W[l] ? plane_max : (size_t)pm.H[l] * pm.W[l];
+    SLN_REQUIRE(plane_max * (size_t)CV < (1ull << 31), SLN_ERR_ARG, "feature map too large for 32-bit tap offsets");
+    dim3 grid(N, cdiv(ph * pw, band));
+    SLN_REQUIRE(grid.y <= 65535, SLN_ERR_ARG, "crop too large");
     if (vec4) {
-        if (levels) crop_fwd_nhwc_kernel<4, true><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, ext, out);
-        else crop_fwd_nhwc_kernel<4, false><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, ext, out);
+        if (levels) crop_fwd_nhwc_kernel<4, true><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, band, ext, out);
+        else crop_fwd_nhwc_kernel<4, false><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, band, ext, out);
     } else {
-        if (levels) crop_fwd_nhwc_kernel<1, true><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, ext, out);
-        else crop_fwd_nhwc_kernel<1, false><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, ext, out);
+        if (levels) crop_fwd_nhwc_kernel<1, true><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, band, ext, out);
+        else crop_fwd_nhwc_kernel<1, false><<<grid, block, smem, st>>>(pm, B, C, boxes, box_ind, level, n_levels, ph, pw, band, ext, out);
     }
     SLN_LAUNCH_OK("crop_fwd_nhwc_kernel");
     return SLN_OK;
