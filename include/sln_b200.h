@@ -79,7 +79,7 @@ SLN_API int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, int
  * result bit-identical to the reference CPU backward (about 3x the arithmetic).
  * grad_image is fully written (zeros included); no memset needed.                 */
 #define SLN_BWD_EXACT 1          /* flags bit: round every product/sum like crop_and_resize.c:241-247 */
-SLN_API size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B);
+SLN_API size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B, int ph, int pw);
 SLN_API int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
                             int C, int ph, int pw,
                             float *grad_image, int B, int H, int W, int layout, int flags,
@@ -99,7 +99,7 @@ SLN_API int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_hos
  * routed by level[i] into grad_maps_host[level[i]] (NHWC [B,H_l,W_l,C], fully written).
  * One prep pass + one gather kernel cover every level.  Same determinism / flags contract
  * as sln_crop_and_resize_bwd.                                                          */
-SLN_API size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels);
+SLN_API size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels, int ph, int pw);
 SLN_API int sln_pyramid_crop_bwd(const float *grads, const float *boxes, const int *box_ind, const int *level,
                          int N, int C, int ph, int pw,
                          float *const *grad_maps_host, const int *H_host, const int *W_host, int n_levels,

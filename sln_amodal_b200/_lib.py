@@ -24,11 +24,11 @@ PROTOTYPES = {
     "sln_last_error_string": (C.c_char_p, []),
     "sln_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "sln_crop_and_resize_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
-    "sln_crop_and_resize_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "sln_crop_and_resize_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sln_crop_and_resize_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "sln_pyramid_crop_fwd": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, _vp, _vp, _vp, _i,
                                   _i, _i, _f, _vp, _vp]),
-    "sln_pyramid_crop_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "sln_pyramid_crop_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sln_pyramid_crop_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i,
                                   _i, _vp, _sz, _vp]),
     "sln_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -245,10 +245,13 @@ struct BwdLevel {
 struct BwdParams {
     BwdLevel lv[BWD_MAX_LEVELS];
     int n_levels;
+    int sched_base[BWD_MAX_LEVELS];   // CTA numbering: smallest maps first (their strips see the longest
+    int sched_lvl[BWD_MAX_LEVELS];    // ROI lists, so they must not form the tail of the launch)
 };
 
 struct BwdTileBases {  // passed by value to the main kernel: static-index compares only
-    int base[BWD_MAX_LEVELS];
+    int base[BWD_MAX_LEVELS];   // first CTA of the j-th scheduled level (ascending)
+    int lvl[BWD_MAX_LEVELS];    // which level that is
     int n_levels;
 };
 
@@ -272,6 +275,15 @@ __device__ __forceinline__ void axis_base_scale(float a1, float a2, int extent, 
         base = (float)(0.5 * (double)__fadd_rn(a1, a2) * (double)(extent - 1));
         scale = 0.f;
     }
+}
+
+__device__ __forceinline__ Tap ld_tap(const Tap *p)
+{
+    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+    Tap t;
+    t.lo = v.x;
+    t.lerp = __int_as_float(v.y);
+    return t;
 }
 
 __device__ __forceinline__ Tap tap_at(float base, float scale, float em1, int k)
@@ -303,7 +315,7 @@ __device__ __forceinline__ BwdLevel pick_level(const BwdParams &P, int l)
 // order-independent result); thread 0 also publishes the level table for the main kernel.
 __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind,
                                         const int *__restrict__ level, int N, int B, int ph, int pw,
-                                        BwdParams P, RoiWin *__restrict__ win, RoiAxes *__restrict__ axes,
+                                        BwdParams P, RoiWin *__restrict__ win, Tap *__restrict__ taps,
                                         int *__restrict__ st_count, BwdLevel *__restrict__ lv_table)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,15 +323,15 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
     if (r >= N) return;
     RoiWin w;
     w.y0 = 1; w.y1 = 0; w.x0 = 1; w.x1 = 0;
-    RoiAxes ax;
-    ax.by = ax.sy = ax.bx = ax.sx = 0.f;
     const int b = box_ind[r];
     const int l = level ? level[r] : 0;
+    Tap *tp = taps + (size_t)r * (ph + pw);          // [ph] y taps then [pw] x taps of this ROI
     if (b >= 0 && b < B && l >= 0 && l < P.n_levels) {
         const BwdLevel L = pick_level(P, l);
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
-        axis_base_scale(y1, y2, L.H, ph, ax.by, ax.sy);
-        axis_base_scale(x1, x2, L.W, pw, ax.bx, ax.sx);
+        const float sc_y = axis_scale(y1, y2, L.H, ph), sc_x = axis_scale(x1, x2, L.W, pw);
+        for (int k = 0; k < ph; ++k) tp[k] = axis_tap(y1, y2, sc_y, L.H, ph, k);
+        for (int k = 0; k < pw; ++k) tp[ph + k] = axis_tap(x1, x2, sc_x, L.W, pw, k);
         int a0, a1, c0, c1;
         axis_window(y1, y2, L.H, ph, a0, a1);
         axis_window(x1, x2, L.W, pw, c0, c1);
@@ -331,7 +343,6 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
         }
     }
     win[r] = w;
-    axes[r] = ax;
 }
 
 // prep 2: ordered fill.  One CTA per supertile: its list offset is the sum of the counts of
@@ -470,7 +481,7 @@ __device__ __forceinline__ int fast_div(int t, int d, float rcp)
 // 4 resident CTAs per SM (<= 64 registers): measured best on B200 (A/B runs, profiles/README.md)
 template <int VEC, int NV, bool EXACT>
 __global__ void __launch_bounds__(BWD_THREADS, 4)
-crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict__ axes,
+crop_bwd_nhwc_kernel(const float *__restrict__ grads, const Tap *__restrict__ taps,
                      const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
                      const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
                      BwdTileBases TB, int C, int ph, int pw)
@@ -478,10 +489,10 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict_
     using V = typename VecT<VEC>::type;
     constexpr int TW = BWD_TW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int l = 0;
+    int l = TB.lvl[0];
 #pragma unroll
     for (int k = 1; k < BWD_MAX_LEVELS; ++k)
-        if (k < TB.n_levels && (int)blockIdx.x >= TB.base[k]) l = k;
+        if (k < TB.n_levels && (int)blockIdx.x >= TB.base[k]) l = TB.lvl[k];
     const BwdLevel L = lv_table[l];
     int t = blockIdx.x - L.tile_base;
     const int q1 = fast_div(t, L.tiles_x, L.rcp_tiles_x);
@@ -494,7 +505,6 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict_
     const int tx0 = tx_i * TW, tx1 = min(tx0 + TW, W) - 1;
     const int CV = C / VEC;
     const int cvbase = blockIdx.y * (32 * NV) + lane;
-    const float em1y = (float)(H - 1), em1x = (float)(W - 1);
 
     // accumulators of the strip's 4 pixels x NV channel vectors: named scalars, so they
     // stay in registers (an indexed array ends up in local memory here)
@@ -530,12 +540,12 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict_
             const int bit = __ffs(todo) - 1;
             todo &= todo - 1;
             const int r = __shfl_sync(0xffffffffu, my_roi, bit);
-            const float4 axv = __ldg(reinterpret_cast<const float4 *>(axes) + r);   // by, sy, bx, sx
+            const Tap *__restrict__ tp = taps + (size_t)r * (ph + pw);   // precomputed by the prep kernel
             const V *gr = g + (size_t)r * S * CV;
             for (int ky0 = 0; ky0 < ph; ky0 += 32) {
                 Tap ty;
                 ty.lo = INVALID_TAP; ty.lerp = 0.f;
-                if (ky0 + lane < ph) ty = tap_at(axv.x, axv.y, em1y, ky0 + lane);
+                if (ky0 + lane < ph) ty = ld_tap(tp + ky0 + lane);
                 unsigned ym = __ballot_sync(0xffffffffu, ty.lo == py || (ty.lo + 1 == py && ty.lerp != 0.f));
                 while (ym) {
                     const int yb = __ffs(ym) - 1;
@@ -550,7 +560,7 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const RoiAxes *__restrict_
                     for (int kx0 = 0; kx0 < pw; kx0 += 32) {
                         Tap tx;
                         tx.lo = INVALID_TAP; tx.lerp = 0.f;
-                        if (kx0 + lane < pw) tx = tap_at(axv.z, axv.w, em1x, kx0 + lane);
+                        if (kx0 + lane < pw) tx = ld_tap(tp + ph + kx0 + lane);
                         unsigned xm = __ballot_sync(0xffffffffu, tx.lo != INVALID_TAP && tx.lo <= tx1 &&
                                                                      tx.lo + (tx.lerp != 0.f) >= tx0);
                         while (xm) {
@@ -706,7 +716,7 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
 
 struct BwdWs {
     RoiWin *win;
-    RoiAxes *axes;
+    Tap *taps;
     int *st_count;
     int *st_off;
     BwdLevel *lv_table;
@@ -715,11 +725,11 @@ struct BwdWs {
 
 constexpr int BWD_MAX_ST = 64;        // supertiles per image and level (8 x 8)
 
-static size_t bwd_ws_bytes(int N, int B, int n_levels)
+static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
 {
     // every ROI lives on one level and meets at most 64 supertiles of its image
     const size_t n_st = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
-    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(RoiAxes) * (size_t)N, 256) +
+    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256) +
            2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) +
            align_up(sizeof(ListEntry) * (size_t)N * BWD_MAX_ST, 256);
 }
@@ -733,9 +743,9 @@ static int launch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P, l
     if (tiles == 0) return SLN_OK;
     BwdTileBases TB{};
     TB.n_levels = P.n_levels;
-    for (int l = 0; l < P.n_levels; ++l) TB.base[l] = P.lv[l].tile_base;
+    for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
     dim3 grid((unsigned)tiles, chunks);
-    crop_bwd_nhwc_kernel<VEC, NV, EXACT><<<grid, BWD_THREADS, 0, st>>>(grads, ws.axes, ws.entries, ws.st_off,
+    crop_bwd_nhwc_kernel<VEC, NV, EXACT><<<grid, BWD_THREADS, 0, st>>>(grads, ws.taps, ws.entries, ws.st_off,
                                                                       ws.st_count, ws.lv_table, TB, C, ph, pw);
     SLN_LAUNCH_OK("crop_bwd_nhwc_kernel");
     return SLN_OK;
@@ -758,8 +768,8 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
                          bool exact, void *wsp, size_t ws_bytes, cudaStream_t st)
 {
     if (B == 0 || C == 0) return SLN_OK;
-    SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B, n_levels), SLN_ERR_WORKSPACE,
-                "crop bwd workspace: need %zu bytes, got %zu", bwd_ws_bytes(N, B, n_levels), ws_bytes);
+    SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B, n_levels, ph, pw), SLN_ERR_WORKSPACE,
+                "crop bwd workspace: need %zu bytes, got %zu", bwd_ws_bytes(N, B, n_levels, ph, pw), ws_bytes);
     SLN_REQUIRE(wsp != nullptr, SLN_ERR_WORKSPACE, "null workspace");
     BwdParams P{};
     P.n_levels = n_levels;
@@ -780,17 +790,31 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         L.tiles_y = cdiv(L.H, BWD_ROWS);
         L.rcp_tiles_x = L.tiles_x ? 1.0f / (float)L.tiles_x : 0.f;
         L.rcp_tiles_y = L.tiles_y ? 1.0f / (float)L.tiles_y : 0.f;
-        L.tile_base = (int)tiles;
-        tiles += (long long)L.tiles_x * L.tiles_y * B;
         vec4 = vec4 && aligned16(maps[l]);
         SLN_REQUIRE((size_t)L.H * L.W == 0 || maps[l] != nullptr, SLN_ERR_ARG, "null grad map");
+    }
+    {   // schedule levels by ascending map area
+        int ord[BWD_MAX_LEVELS];
+        for (int l = 0; l < n_levels; ++l) ord[l] = l;
+        for (int a = 0; a < n_levels; ++a)
+            for (int b2 = a + 1; b2 < n_levels; ++b2)
+                if ((long long)P.lv[ord[b2]].H * P.lv[ord[b2]].W < (long long)P.lv[ord[a]].H * P.lv[ord[a]].W) {
+                    const int t = ord[a]; ord[a] = ord[b2]; ord[b2] = t;
+                }
+        for (int j = 0; j < n_levels; ++j) {
+            BwdLevel &L = P.lv[ord[j]];
+            L.tile_base = (int)tiles;
+            P.sched_base[j] = (int)tiles;
+            P.sched_lvl[j] = ord[j];
+            tiles += (long long)L.tiles_x * L.tiles_y * B;
+        }
     }
     SLN_REQUIRE(tiles < (1ll << 24), SLN_ERR_ARG, "too many tiles (%lld)", tiles);
     unsigned char *p = static_cast<unsigned char *>(wsp);
     const size_t n_st_cap = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
     BwdWs ws;
     ws.win = reinterpret_cast<RoiWin *>(p);        p += align_up(sizeof(RoiWin) * (size_t)N, 256);
-    ws.axes = reinterpret_cast<RoiAxes *>(p);      p += align_up(sizeof(RoiAxes) * (size_t)N, 256);
+    ws.taps = reinterpret_cast<Tap *>(p);          p += align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256);
     ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * n_st_cap, 256);
     ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
     ws.lv_table = reinterpret_cast<BwdLevel *>(p); p += align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256);
@@ -799,7 +823,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
     // the windows kernel also publishes the level table, so it always runs (>= 1 CTA)
     crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
-        boxes, box_ind, level, N, B, ph, pw, P, ws.win, ws.axes, ws.st_count, ws.lv_table);
+        boxes, box_ind, level, N, B, ph, pw, P, ws.win, ws.taps, ws.st_count, ws.lv_table);
     SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
         crop_bwd_fill_kernel<<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, N, P, ws.st_count, ws.st_off,
@@ -851,10 +875,10 @@ extern "C" int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, 
     return SLN_OK;
 }
 
-extern "C" size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B)
+extern "C" size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B, int ph, int pw)
 {
-    if (N < 0 || B < 0) return 0;
-    return bwd_ws_bytes(N, B, 1);
+    if (N < 0 || B < 0 || ph < 1 || pw < 1) return 0;
+    return bwd_ws_bytes(N, B, 1, ph, pw);
 }
 
 extern "C" int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
@@ -890,10 +914,10 @@ extern "C" int sln_pyramid_crop_fwd(const float *const *maps_host, const int *H_
                          static_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels)
+extern "C" size_t sln_pyramid_crop_bwd_workspace_bytes(int N, int B, int n_levels, int ph, int pw)
 {
-    if (N < 0 || B < 0 || n_levels < 1 || n_levels > BWD_MAX_LEVELS) return 0;
-    return bwd_ws_bytes(N, B, n_levels);
+    if (N < 0 || B < 0 || n_levels < 1 || n_levels > BWD_MAX_LEVELS || ph < 1 || pw < 1) return 0;
+    return bwd_ws_bytes(N, B, n_levels, ph, pw);
 }
 
 extern "C" int sln_pyramid_crop_bwd(const float *grads, const float *boxes, const int *box_ind, const int *level,

@@ -147,7 +147,7 @@ def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_ou
         channels_last_out = g_cl
     out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=grads.device, memory_format=torch.channels_last)
     with torch.cuda.device(grads.device):
-        ws = _workspace(lib().sln_crop_and_resize_bwd_workspace_bytes(N, B), grads.device)
+        ws = _workspace(lib().sln_crop_and_resize_bwd_workspace_bytes(N, B, ph, pw), grads.device)
         check(lib().sln_crop_and_resize_bwd(ptr(g), ptr(boxes), ptr(box_ind), N, Cc, ph, pw, ptr(out), B, H, W,
                                             LAYOUT_NHWC, flags, ptr(ws), ws.numel(), stream_ptr()),
               "sln_crop_and_resize_bwd")
@@ -178,7 +178,7 @@ def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last
     hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
     ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
     with torch.cuda.device(grads.device):
-        ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl), grads.device)
+        ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), grads.device)
         check(lib().sln_pyramid_crop_bwd(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), N, Cc, ph, pw, mp, hs, ws_, nl, B,
                                          flags, ptr(ws), ws.numel(), stream_ptr()), "sln_pyramid_crop_bwd")
     _lib.count_launches(3 if N else 1)

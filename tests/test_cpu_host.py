@@ -40,7 +40,7 @@ def test_workspace_queries_and_arg_errors(built_lib):
     assert L.sln_nms_workspace_bytes(0) >= 0
     n = 12000
     assert L.sln_nms_workspace_bytes(n) >= n * ((n + 63) // 64) * 8
-    assert L.sln_crop_and_resize_bwd_workspace_bytes(8000, 8) >= 8000 * 12
+    assert L.sln_crop_and_resize_bwd_workspace_bytes(8000, 8, 7, 7) >= 8000 * 12
     assert L.sln_edt_workspace_bytes(320, 1024, 1024) <= 320 * 2 * 1024 * 1024
     assert L.sln_proposal_workspace_bytes(261888, 6000) == L.sln_proposal_workspace_bytes(10 ** 6, 6000)
     # argument validation happens before any CUDA call
