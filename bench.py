@@ -52,6 +52,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _ncu_traffic(k):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["bytes"]
+        pool = "14x14" if "14x14" in k["what"] else "7x7"
+        return t.get("%s %s" % (k["kernel"], pool))
+    except Exception:
+        return None
+
+
 def make_workload(seed_shift=0):
     n = IMAGES_PER_GPU * ROIS_PER_IMAGE
     boxes = synth.roi_boxes(n, seed=4321 + seed_shift)
@@ -102,38 +112,53 @@ def bwd_bytes(n_level, side, pool):
 # clocks sampling during the timed region
 # --------------------------------------------------------------------------------------
 class ClockSampler:
+    """One `nvidia-smi -lms 20` child process; samples are time-stamped on arrival so that the ones taken
+    inside the timed window can be selected afterwards."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.stop = threading.Event()
+        self.samples = []          # (host time, fields)
+        self.proc = None
         self.t = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in o.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.05)
+        try:
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
+        except Exception:
+            pass
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=10)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=5)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        sel = [f for (t, f) in self.samples if t0 is None or (t0 <= t <= t1)]
+        window = "timed region"
+        if len(sel) < 3:
+            sel = [f for (_, f) in self.samples]
+            window = "timed region + load extension"
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in sel:
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
@@ -143,7 +168,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------
@@ -191,12 +216,22 @@ def run_ours(args):
     l0 = _lib.launches()
     with ClockSampler(local_rank) as clocks:
         barrier()
+        t_start = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
-    launches = _lib.launches() - l0
+        t_end = time.perf_counter()
+        launches_timed = _lib.launches() - l0
+        # the timed region can be shorter than nvidia-smi's sampling period: keep the same load running
+        # (untimed) until a few clock samples exist, so throttling during this workload is visible
+        t_ext = time.perf_counter()
+        while time.perf_counter() - t_ext < 0.6:
+            step()
+        torch.cuda.synchronize()
+    clocks_summary = clocks.summary(t_start, t_end)
+    launches = launches_timed
     ms_total = sdist.max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / args.steps
     crops_per_step = n_rois * len(POOLS) * world
@@ -231,7 +266,7 @@ def run_ours(args):
     step_bytes = sum(k["algorithmic_bytes"] for k in kernels)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "what": dom["what"], "achieved": round(dom["achieved_gbs"], 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(dom["frac"], 4),
-                "traffic": None,
+                "traffic": _ncu_traffic(dom),
                 "step": {"algorithmic_bytes": step_bytes, "achieved": round(step_bytes / ms_per_step / 1e6, 1),
                          "frac": round(step_bytes / ms_per_step / 1e6 / peak, 4),
                          "frac_of_8TBs_nominal": round(step_bytes / ms_per_step / 1e6 / 8000.0, 4)}}
@@ -300,7 +335,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "layout": "channels_last (NHWC kernels)", "rois_per_step_per_gpu": n_rois,
                        "l2_policy": "working set 4.7 GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": "images (box_ind) across ranks; no data-path collective"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks_summary, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kernels],
             "extra": extra,

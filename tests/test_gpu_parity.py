@@ -244,6 +244,32 @@ def test_nms_near_threshold_pairs():
     assert np.array_equal(got, want)
 
 
+def test_nms_long_dependency_chain_takes_serial_fallback():
+    """A chain where box k only overlaps box k+1 needs ~n rounds of the parallel fixed-point resolve;
+    it must fall back to the serial scan and still be exact."""
+    from nms.nms_wrapper import nms
+    n = 10400                               # >= 160 words: takes the parallel resolve first
+    w, s = 100.0, 12.0                      # IoU(k,k+1) = 88/112 = 0.786 >= 0.7, IoU(k,k+2) = 76/124 < 0.7
+    k = np.arange(n, dtype=np.float32)
+    boxes = np.stack([np.zeros(n, np.float32), k * s, np.full(n, 49.0, np.float32), k * s + w - 1], 1)
+    scores = np.linspace(1.0, 0.0, n).astype(np.float32)
+    dets = np.concatenate([boxes, scores[:, None]], 1).astype(np.float32)
+    want = oracle.nms(dets, 0.7)
+    assert np.array_equal(want, np.arange(0, n, 2))
+    assert np.array_equal(nms(cuda(dets), 0.7).cpu().numpy(), want)
+
+
+def test_nms_two_stage_path_20k():
+    from sln_amodal_b200 import ops
+    n = 20000
+    dets = np.concatenate([synth.nms_boxes(n, seed=21), synth.nms_scores(n, seed=22)[:, None]], 1)
+    want = oracle.nms(dets, 0.7)
+    keep, num = ops.nms_device(cuda(dets), 0.7)
+    assert np.array_equal(keep[: int(num.item())].cpu().numpy(), want)
+    keep, num = ops.nms_device(cuda(dets), 0.7, max_keep=500)
+    assert np.array_equal(keep[: int(num.item())].cpu().numpy(), want[:500])
+
+
 def test_nms_empty_and_degenerate():
     from nms.nms_wrapper import nms
     assert nms(torch.zeros((0, 5), device=dev()), 0.5).numel() == 0
