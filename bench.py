@@ -179,6 +179,9 @@ def run_ours(args):
     from sln_amodal_b200 import _lib, ops, dist as sdist
     from sln_amodal_b200.crop_and_resize import CropAndResizeFunction
 
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner, ...) write to fd 1
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world = sdist.init()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
@@ -340,7 +343,8 @@ def run_ours(args):
             "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kernels],
             "extra": extra,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
