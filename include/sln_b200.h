@@ -126,6 +126,17 @@ SLN_API size_t sln_nms_workspace_bytes(int n);
 SLN_API int sln_nms(const float *dets, const int *class_ids, int n, float thresh, int max_keep,
             int64_t *keep, int *num_keep, void *workspace, size_t workspace_bytes,
             void *stream);
+/* Same call with a `flags` word and an optional report of the path taken.  Two device pipelines produce
+ * the identical result: a sparse one (boxes binned by centre, exact pair tests on neighbouring cells only,
+ * in-CTA fixed point) used when 65 <= n <= 65535, thresh >= 0.05 and the boxes are finite, ordered
+ * (c2 >= c0, c3 >= c1) and within +-32768; and the dense 64x64-tile bit-matrix pipeline, which also takes over
+ * (decided on the device, no host round trip) when the sparse one meets more than 16 n overlapping pairs.
+ * SLN_NMS_DENSE_ONLY forces the dense pipeline.  *path_out (device i32, may be NULL) receives 1 when the
+ * sparse pipeline produced the result, else 0.                                                        */
+#define SLN_NMS_DENSE_ONLY 1
+SLN_API int sln_nms_ex(const float *dets, const int *class_ids, int n, float thresh, int max_keep, int flags,
+               int64_t *keep, int *num_keep, int *path_out, void *workspace, size_t workspace_bytes,
+               void *stream);
 
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:

@@ -17,6 +17,8 @@
 //                       OR the kept rows into the `removed` words in shared memory
 #include "nms_core.cuh"
 
+#include <cooperative_groups.h>
+
 namespace sln {
 
 // ---------------------------------------------------------------------------
@@ -152,8 +154,9 @@ template <bool CLS>
 __global__ void __launch_bounds__(64 * MASK_GROUPS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls,
                 int n_host, const int *__restrict__ n_dev, int W_stride, float thresh,
-                unsigned long long *__restrict__ mask)
+                unsigned long long *__restrict__ mask, const int *__restrict__ skip)
 {
+    if (skip && *skip == 1) return;                // the sparse path already produced the result
     // n may live in device memory (second stage of the two-stage pipeline): the grid is sized for the
     // worst case and surplus CTAs leave at once
     const int n = n_dev ? *n_dev : n_host;
@@ -247,10 +250,11 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ order, int n_host,
                 const int *__restrict__ n_dev, int W_stride, int max_keep_host, const int *__restrict__ keep_base_dev,
                 int64_t *__restrict__ keep64, int *__restrict__ keep32, int *__restrict__ num_keep,
-                const int *__restrict__ done_flag)
+                const int *__restrict__ done_flag, const int *__restrict__ skip)
 {
     extern __shared__ __align__(16) unsigned long long s_mem[];
     if (done_flag && *done_flag == 1) return;      // the parallel resolve already produced the result
+    if (skip && *skip == 1) return;                // so did the sparse path
     const int n = n_dev ? *n_dev : n_host;
     const int W = (n + 63) >> 6;
     // keep_base: survivors already emitted by an earlier stage (they count against max_keep)
@@ -465,8 +469,9 @@ nms_fixpoint_kernel(const unsigned long long *__restrict__ mask, const int *__re
                     const int *__restrict__ n_dev, int W_stride, int max_keep, const int *__restrict__ keep_base_dev,
                     unsigned long long *__restrict__ removed /* [2][W_stride] */, unsigned long long *__restrict__ Kbuf /* [W_stride] */,
                     FixState *__restrict__ state, int64_t *__restrict__ keep64, int *__restrict__ keep32,
-                    int *__restrict__ num_keep)
+                    int *__restrict__ num_keep, const int *__restrict__ skip)
 {
+    if (skip && *skip == 1) return;                // uniform over the grid: nobody reaches a barrier
     const int n = n_dev ? *n_dev : n_host;
     const int W = (n + 63) >> 6;
     const int keep_base = keep_base_dev ? *keep_base_dev : 0;
@@ -569,8 +574,9 @@ template <bool CLS>
 __global__ void __launch_bounds__(256)
 nms_suppress_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls,
                     int T, int n, const int *__restrict__ keepA, const int *__restrict__ numA, float thresh,
-                    unsigned char *__restrict__ dead)
+                    unsigned char *__restrict__ dead, const int *__restrict__ skip)
 {
+    if (skip && *skip == 1) return;
     __shared__ float4 s_box[256];
     __shared__ float s_area[256];
     __shared__ int s_cls[256];
@@ -609,8 +615,9 @@ __global__ void __launch_bounds__(1024)
 nms_compact_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls,
                    const int *__restrict__ order, const unsigned char *__restrict__ dead, int T, int n,
                    float4 *__restrict__ boxes2, float *__restrict__ areas2, int *__restrict__ cls2,
-                   int *__restrict__ order2, int *__restrict__ n2_out)
+                   int *__restrict__ order2, int *__restrict__ n2_out, const int *__restrict__ skip)
 {
+    if (skip && *skip == 1) return;
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -643,6 +650,467 @@ nms_compact_kernel(const float4 *__restrict__ boxes, const float *__restrict__ a
 }
 
 // ---------------------------------------------------------------------------
+// 5. sparse path: spatial binning -> exact pair tests on neighbours only -> in-CTA fixed point
+// ---------------------------------------------------------------------------
+// The dense pipeline above tests all n(n-1)/2 pairs (72 M at 12k boxes) although only a few edges per
+// box exist.  A pair can only satisfy IoU >= t if the boxes' centres are close:
+//   with W = x2-x1+1 (the reference's +1 widths), w = overlap length along x, IoU >= t implies
+//   w >= t*max(W_a, W_b), W_b in [t*W_a, W_a/t] and w <= (W_a+W_b)/2 - |cx_a - cx_b|, hence
+//   |cx_a - cx_b| <= W_a * (1-t) * max(1, 1/(2t))            (same along y).
+// Boxes are bucketed by centre on a G x G grid (x CB class buckets for the class-aware call); a warp per
+// box walks the cell rows its window meets and runs the SAME exact iou_ge test as the mask kernel on those
+// candidates only.  Every hit (a before b in visiting order) becomes one packed edge (b << 16 | a).
+// A single CTA then iterates  K <- { b : no a in K with edge a->b }  from K = all boxes to the fixed point
+// -- the greedy survivor set, see section 4b -- with K in shared memory, and emits in visiting order.
+// The window carries 1 % + 0.5 px of slack against fp32 rounding (coordinates are bounded by 32768, so one
+// rounding is <= 0.004 px); the result does not depend on the order of cells, candidates or edges.
+// Contract: 64 < n <= 65535, t >= 0.05, finite boxes with x2 >= x1, y2 >= y1, |coordinate| <= 32768, at
+// most SP_EDGES_PER_BOX*n edges, fixed point within SP_MAX_ROUNDS rounds.  Anything else leaves status at 0
+// and the dense kernels (launched right after; they exit at once when status == 1) produce the result.
+constexpr int SP_MAX_N = 65535;
+constexpr int SP_MIN_N = 65;
+constexpr int SP_MAX_CELLS = 4096;
+constexpr int SP_EDGES_PER_BOX = 16;
+constexpr int SP_BIN_THREADS = 1024;
+constexpr int SP_PAIR_WARPS = 8;
+constexpr int SP_WARP_BUF = 128;           // edges buffered per warp before one atomic allocation
+constexpr int SP_MAX_ROUNDS = 96;
+constexpr int SP_RESOLVE_THREADS = 1024;
+constexpr int SP_SMEM_EDGES = 40960;       // edges cached in shared memory by the resolve kernel (160 KB)
+constexpr float SP_MAX_COORD = 32768.f;
+
+struct SparseHdr {
+    int status;            // 1: the sparse path produced the result
+    int bail;              // 1: outside the contract -> dense path
+    unsigned edge_count;
+    int G, CB;
+    float minx, miny, invx, invy;
+};
+
+struct SparseBufs {
+    SparseHdr *hdr;
+    int *cell_start;       // [CB*G*G + 1]
+    float4 *cbox;          // boxes / areas / positions / classes sorted by cell
+    float *carea;
+    int *cpos;
+    int *ccls;
+    unsigned *edges;       // [SP_EDGES_PER_BOX * n]
+};
+
+static size_t nms_sparse_bytes(int n)
+{
+    if (n > SP_MAX_N) return 256;
+    size_t b = 256;
+    b += align_up(sizeof(int) * (SP_MAX_CELLS + 1), 256);
+    b += align_up(sizeof(float4) * (size_t)n, 256);
+    b += 3 * align_up(sizeof(int) * (size_t)n, 256);
+    b += align_up(sizeof(unsigned) * (size_t)SP_EDGES_PER_BOX * n, 256);
+    return b;
+}
+
+static void sparse_carve(void *ws, int n, SparseBufs &b)
+{
+    unsigned char *p = static_cast<unsigned char *>(ws);
+    b.hdr = reinterpret_cast<SparseHdr *>(p);     p += 256;
+    b.cell_start = reinterpret_cast<int *>(p);    p += align_up(sizeof(int) * (SP_MAX_CELLS + 1), 256);
+    b.cbox = reinterpret_cast<float4 *>(p);       p += align_up(sizeof(float4) * (size_t)n, 256);
+    b.carea = reinterpret_cast<float *>(p);       p += align_up(sizeof(int) * (size_t)n, 256);
+    b.cpos = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
+    b.ccls = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
+    b.edges = reinterpret_cast<unsigned *>(p);
+}
+
+// monotone in v (every fp32 operation is), so lo <= v <= hi implies cell(lo) <= cell(v) <= cell(hi)
+__device__ __forceinline__ int sp_cell(float v, float minv, float inv, int G)
+{
+    const float f = floorf(__fmul_rn(__fsub_rn(v, minv), inv));
+    return (int)fminf(fmaxf(f, 0.f), (float)(G - 1));
+}
+
+__device__ __forceinline__ bool sp_sane(const float4 b)
+{
+    return fabsf(b.x) <= SP_MAX_COORD && fabsf(b.y) <= SP_MAX_COORD && fabsf(b.z) <= SP_MAX_COORD &&
+           fabsf(b.w) <= SP_MAX_COORD && b.z >= b.x && b.w >= b.y;       // false for NaN / inf
+}
+
+// single CTA: bounds of the centres, cell histogram, exclusive scan, scatter into cell order.
+// The three passes over the boxes keep SP_BIN_UNROLL independent 16-byte loads in flight per thread: with one
+// CTA the kernel is bound by load latency, not bandwidth (31 us -> see profiles/README.md).
+constexpr int SP_BIN_UNROLL = 8;
+
+template <bool CLS>
+__global__ void __launch_bounds__(SP_BIN_THREADS)
+nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls, int n,
+               int G, int CB, SparseBufs sb)
+{
+    __shared__ int s_hist[SP_MAX_CELLS];
+    __shared__ float s_red[4][SP_BIN_THREADS / 32];
+    __shared__ int s_warp[SP_BIN_THREADS / 32];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NC = CB * G * G;
+    constexpr int STEP = SP_BIN_THREADS * SP_BIN_UNROLL;
+    if (tid == 0) s_bad = 0;
+    for (int k = tid; k < NC; k += SP_BIN_THREADS) s_hist[k] = 0;
+    __syncthreads();
+    float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+    bool bad = false;
+    for (int i0 = tid; i0 < n; i0 += STEP) {
+        float4 v[SP_BIN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+            const int i = i0 + u * SP_BIN_THREADS;
+            v[u] = boxes[i < n ? i : i0];
+        }
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+            const float4 b = v[u];
+            bad = bad || !sp_sane(b);
+            const float cx = __fmul_rn(0.5f, __fadd_rn(b.x, b.z)), cy = __fmul_rn(0.5f, __fadd_rn(b.y, b.w));
+            mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx);
+            mny = fminf(mny, cy); mxy = fmaxf(mxy, cy);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) { sb.hdr->status = 0; sb.hdr->bail = 1; sb.hdr->edge_count = 0u; }
+        return;
+    }
+    mnx = s_red[0][lane]; mny = s_red[1][lane]; mxx = s_red[2][lane]; mxy = s_red[3][lane];
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    const float invx = __fdiv_rn((float)G, fmaxf(__fsub_rn(mxx, mnx), 1e-3f));
+    const float invy = __fdiv_rn((float)G, fmaxf(__fsub_rn(mxy, mny), 1e-3f));
+    if (tid == 0) {
+        sb.hdr->status = 0; sb.hdr->bail = 0; sb.hdr->edge_count = 0u;
+        sb.hdr->G = G; sb.hdr->CB = CB;
+        sb.hdr->minx = mnx; sb.hdr->miny = mny; sb.hdr->invx = invx; sb.hdr->invy = invy;
+    }
+    auto key_of = [&](const float4 b, int c) {
+        const float cx = __fmul_rn(0.5f, __fadd_rn(b.x, b.z)), cy = __fmul_rn(0.5f, __fadd_rn(b.y, b.w));
+        const int cb = CLS ? (int)((unsigned)c % (unsigned)CB) : 0;
+        return (cb * G + sp_cell(cy, mny, invy, G)) * G + sp_cell(cx, mnx, invx, G);
+    };
+    for (int i0 = tid; i0 < n; i0 += STEP) {
+        float4 v[SP_BIN_UNROLL];
+        int c[SP_BIN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+            const int i = i0 + u * SP_BIN_THREADS;
+            v[u] = boxes[i < n ? i : i0];
+            c[u] = CLS ? cls[i < n ? i : i0] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u)
+            if (i0 + u * SP_BIN_THREADS < n) atomicAdd(&s_hist[key_of(v[u], c[u])], 1);
+    }
+    __syncthreads();
+    // exclusive scan of NC <= 4096 counters: 4 per thread
+    {
+        int v[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int k = 4 * tid + q; v[q] = k < NC ? s_hist[k] : 0; sum += v[q]; }
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        int run = s_warp[warp] + incl - sum;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = 4 * tid + q;
+            if (k < NC) { s_hist[k] = run; sb.cell_start[k] = run; }
+            run += v[q];
+        }
+        if (tid == 0) sb.cell_start[NC] = n;
+    }
+    __syncthreads();
+    for (int i0 = tid; i0 < n; i0 += STEP) {
+        float4 v[SP_BIN_UNROLL];
+        float a[SP_BIN_UNROLL];
+        int c[SP_BIN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+            const int i = i0 + u * SP_BIN_THREADS, ii = i < n ? i : i0;
+            v[u] = boxes[ii];
+            a[u] = areas[ii];
+            c[u] = CLS ? cls[ii] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+            const int i = i0 + u * SP_BIN_THREADS;
+            if (i < n) {
+                const int p = atomicAdd(&s_hist[key_of(v[u], c[u])], 1);   // order inside a cell is irrelevant to the result
+                sb.cbox[p] = v[u];
+                sb.carea[p] = a[u];
+                sb.cpos[p] = i;
+                if (CLS) sb.ccls[p] = c[u];
+            }
+        }
+    }
+}
+
+// warp per box (grid-strided): exact tests against the boxes binned in the window's cells.  The window's cell
+// rows are contiguous ranges of the cell-sorted arrays; their (start, running count) table is built once per box
+// in shared memory (one row per lane, all loads in flight together) and the lanes then walk the concatenation of
+// the ranges, so every pass tests 32 candidates whatever the row lengths are.
+template <bool CLS>
+__global__ void __launch_bounds__(32 * SP_PAIR_WARPS)
+nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls, int n,
+                 float thresh, float ct, unsigned edge_cap, SparseBufs sb)
+{
+    __shared__ unsigned s_buf[SP_PAIR_WARPS][SP_WARP_BUF];
+    __shared__ int s_rs[SP_PAIR_WARPS][64];        // first item of each window row
+    __shared__ int s_ri[SP_PAIR_WARPS][64];        // inclusive running count of candidates
+    const SparseHdr h = *sb.hdr;
+    if (h.bail) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *buf = s_buf[warp];
+    int *rs = s_rs[warp], *ri = s_ri[warp];
+    int cnt = 0;                                   // warp-uniform
+    auto flush = [&]() {
+        unsigned base = 0u;
+        if (lane == 0) base = atomicAdd(&sb.hdr->edge_count, (unsigned)cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < cnt; k += 32)
+            if (base + k < edge_cap) sb.edges[base + k] = buf[k];
+        __syncwarp();
+        cnt = 0;
+    };
+    const int G = h.G;                             // <= 64
+    for (int b = blockIdx.x * SP_PAIR_WARPS + warp; b < n; b += gridDim.x * SP_PAIR_WARPS) {
+        if (b == 0) continue;                      // nothing precedes the first box
+        const float4 bb = boxes[b];
+        const float ab = areas[b];
+        const int cbk = CLS ? cls[b] : 0;
+        const float rx = __fadd_rn(__fmul_rn(__fadd_rn(__fsub_rn(bb.z, bb.x), 1.f), ct), 0.5f);
+        const float ry = __fadd_rn(__fmul_rn(__fadd_rn(__fsub_rn(bb.w, bb.y), 1.f), ct), 0.5f);
+        const float cx = __fmul_rn(0.5f, __fadd_rn(bb.x, bb.z)), cy = __fmul_rn(0.5f, __fadd_rn(bb.y, bb.w));
+        const int ix0 = sp_cell(__fsub_rn(cx, rx), h.minx, h.invx, G), ix1 = sp_cell(__fadd_rn(cx, rx), h.minx, h.invx, G);
+        const int iy0 = sp_cell(__fsub_rn(cy, ry), h.miny, h.invy, G), iy1 = sp_cell(__fadd_rn(cy, ry), h.miny, h.invy, G);
+        const int plane = CLS ? (int)((unsigned)cbk % (unsigned)h.CB) * G : 0;
+        const int nrows = iy1 - iy0 + 1;
+        int total = 0;
+        __syncwarp();                              // the previous box's table reads are done
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = lane + 32 * half;
+            int s = 0, c = 0;
+            if (r < nrows) {
+                const int row = (plane + iy0 + r) * G;
+                s = __ldg(sb.cell_start + row + ix0);
+                c = __ldg(sb.cell_start + row + ix1 + 1) - s;
+            }
+            int incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            rs[r] = s;
+            ri[r] = total + incl;
+            total += __shfl_sync(0xffffffffu, incl, 31);
+            if (nrows <= 32) break;                // warp-uniform
+        }
+        __syncwarp();
+        int r = 0;                                 // this lane's current row (monotone in t)
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            bool hit = false;
+            int a = 0;
+            if (t < total) {
+                while (t >= ri[r]) ++r;
+                const int k = rs[r] + (t - (r ? ri[r - 1] : 0));
+                a = sb.cpos[k];
+                if (a < b && (!CLS || sb.ccls[k] == cbk)) hit = iou_ge(sb.cbox[k], sb.carea[k], bb, ab, thresh);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                const int c = __popc(m);
+                if (cnt + c > SP_WARP_BUF) flush();
+                if (hit) buf[cnt + __popc(m & ((1u << lane) - 1u))] = ((unsigned)b << 16) | (unsigned)a;
+                __syncwarp();
+                cnt += c;
+            }
+        }
+    }
+    if (cnt) flush();
+}
+
+// one cluster of SP_CLUSTER CTAs: fixed point over the edge list, then ordered emission.
+// Every CTA keeps a full copy of the survivor set K (32-bit words) and a private `removed` set R in shared memory
+// and owns 1/SP_CLUSTER of the edges (cached in its shared memory) and of the words.  One round:
+//   edge pass    for each of my edges a->b with a in K: R[b] |= 1                       (local shared atomics)
+//   cluster.sync
+//   word pass    for each of my words: K' = valid & ~(OR of the SP_CLUSTER copies of R) read through DSMEM,
+//                written into every CTA's K; a per-CTA "changed" flag goes to every CTA
+//   cluster.sync
+// until no word changed.  Two hardware cluster barriers per round replace the software grid barrier of the dense
+// cooperative resolve; K never leaves the SMs.
+constexpr int SP_CLUSTER = 8;
+constexpr int SP_WORDS = 2048;             // 32-bit words of K / R (n <= 65535)
+
+__global__ void __cluster_dims__(SP_CLUSTER, 1, 1) __launch_bounds__(SP_RESOLVE_THREADS)
+nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, unsigned edge_cap, SparseBufs sb,
+                          int64_t *__restrict__ keep64, int *__restrict__ keep32, int *__restrict__ num_keep)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_wsum[SP_RESOLVE_THREADS / 32];
+    if (sb.hdr->bail) return;                      // uniform over the cluster: nobody is left at a barrier
+    const unsigned E = sb.hdr->edge_count;
+    if (E > edge_cap) return;                      // status stays 0: dense path
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cluster.block_rank();
+    unsigned *K = reinterpret_cast<unsigned *>(s_raw);          // [SP_WORDS]
+    unsigned *R = K + SP_WORDS;                                 // [SP_WORDS]
+    int *flags = reinterpret_cast<int *>(R + SP_WORDS);         // [2][SP_CLUSTER] (+ padding)
+    unsigned *ecache = reinterpret_cast<unsigned *>(flags + 32);// [SP_SMEM_EDGES]
+    const int W32 = (n + 31) >> 5;
+    const unsigned per = (E + SP_CLUSTER - 1) / SP_CLUSTER;
+    const unsigned e0 = min(E, crank * per), e1 = min(E, e0 + per);
+    const unsigned mine = e1 - e0, Ec = mine < (unsigned)SP_SMEM_EDGES ? mine : (unsigned)SP_SMEM_EDGES;
+    const unsigned *my_edges = sb.edges + e0;
+    for (unsigned e = tid; e < Ec; e += SP_RESOLVE_THREADS) ecache[e] = my_edges[e];
+    auto valid_word = [&](int w) -> unsigned {
+        const int nb = n - w * 32;
+        return nb >= 32 ? 0xffffffffu : (nb > 0 ? ((1u << nb) - 1u) : 0u);
+    };
+    for (int w = tid; w < SP_WORDS; w += SP_RESOLVE_THREADS) { K[w] = valid_word(w); R[w] = 0u; }
+    if (tid < 32) flags[tid] = 0;
+    const int wper = (W32 + SP_CLUSTER - 1) / SP_CLUSTER;       // <= 256
+    const int w0 = min(W32, (int)crank * wper), w1 = min(W32, w0 + wper);
+    cluster.sync();                                // every CTA's shared memory is initialised before remote access
+    bool converged = false;
+    for (int round = 0; round < SP_MAX_ROUNDS; ++round) {
+        for (unsigned e = tid; e < mine; e += SP_RESOLVE_THREADS) {
+            const unsigned ed = e < Ec ? ecache[e] : __ldg(my_edges + e);
+            const unsigned a = ed & 0xffffu, b = ed >> 16;
+            if ((K[a >> 5] >> (a & 31u)) & 1u) atomicOr(R + (b >> 5), 1u << (b & 31u));
+        }
+        cluster.sync();
+        int changed = 0;
+        if (tid < w1 - w0) {
+            const int w = w0 + tid;
+            unsigned r = 0u;
+#pragma unroll
+            for (int c = 0; c < SP_CLUSTER; ++c) r |= *cluster.map_shared_rank(R + w, c);
+            const unsigned kn = valid_word(w) & ~r;
+            changed = kn != K[w];
+            if (changed) {
+#pragma unroll
+                for (int c = 0; c < SP_CLUSTER; ++c) *cluster.map_shared_rank(K + w, c) = kn;
+            }
+        }
+        const int any = __syncthreads_or(changed);
+        if (tid < SP_CLUSTER) *cluster.map_shared_rank(flags + (round & 1) * SP_CLUSTER + crank, tid) = any;
+        cluster.sync();
+        int glob = 0;
+#pragma unroll
+        for (int c = 0; c < SP_CLUSTER; ++c) glob |= flags[(round & 1) * SP_CLUSTER + c];
+        for (int w = tid; w < W32; w += SP_RESOLVE_THREADS) R[w] = 0u;
+        __syncthreads();
+        if (!glob) { converged = true; break; }    // uniform over the cluster
+    }
+    if (!converged) return;
+    // emission in visiting order: every CTA scans the per-word popcounts itself (2 words per thread) and writes
+    // the survivors of the positions it owns
+    const int c0 = __popc(K[2 * tid]), c1 = __popc(K[2 * tid + 1]);
+    const int mine2 = c0 + c1;
+    int incl = mine2;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_wsum[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    int *pre = reinterpret_cast<int *>(R);         // R is free now
+    const int excl = s_wsum[warp] + incl - mine2;
+    pre[2 * tid] = excl;
+    pre[2 * tid + 1] = excl + c0;
+    __syncthreads();
+    for (int pos = (int)crank * SP_RESOLVE_THREADS + tid; pos < n; pos += SP_CLUSTER * SP_RESOLVE_THREADS) {
+        const unsigned kw = K[pos >> 5];
+        if ((kw >> (pos & 31)) & 1u) {
+            const int slot = pre[pos >> 5] + __popc(kw & ((1u << (pos & 31)) - 1u));
+            if (slot < max_keep) {
+                const int idx = order ? order[pos] : pos;
+                if (keep64) keep64[slot] = idx;
+                if (keep32) keep32[slot] = idx;
+            }
+        }
+    }
+    if (crank == 0 && tid == SP_RESOLVE_THREADS - 1) {
+        *num_keep = min(excl + mine2, max_keep);
+        sb.hdr->status = 1;
+    }
+}
+
+// returns the device address of the status word the dense kernels test (nullptr: sparse path not taken)
+static int launch_sparse(const float4 *boxes, const float *areas, const int *cls, const int *order, int n, float thresh,
+                         int max_keep, int64_t *keep64, int *keep32, int *num_keep, void *sparse, cudaStream_t st,
+                         const int **skip_out)
+{
+    *skip_out = nullptr;
+    if (sparse == nullptr || n < SP_MIN_N || n > SP_MAX_N || !(thresh >= 0.05f)) return SLN_OK;
+    SparseBufs sb;
+    sparse_carve(sparse, n, sb);
+    // grid: ~3 boxes per cell; the class-aware call spends the cells on class buckets first
+    int CB = 1, G = 64;
+    if (cls) { CB = 64; G = 8; }
+    while (G > 8 && (long long)CB * G * G > (long long)n / 2) G >>= 1;
+    const float t = thresh > 1.f ? 1.f : thresh;
+    const float ct = (1.f - t) * (t < 0.5f ? 0.5f / t : 1.f) * 1.01f;
+    const unsigned edge_cap = (unsigned)SP_EDGES_PER_BOX * (unsigned)n;
+    if (cls) nms_bin_kernel<true><<<1, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
+    else nms_bin_kernel<false><<<1, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
+    SLN_LAUNCH_OK("nms_bin_kernel");
+    int ctas = cdiv(n, SP_PAIR_WARPS);
+    if (ctas > 8 * sm_count()) ctas = 8 * sm_count();
+    if (cls) nms_pairs_kernel<true><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
+    else nms_pairs_kernel<false><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
+    SLN_LAUNCH_OK("nms_pairs_kernel");
+    const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32 + SP_SMEM_EDGES);
+    SLN_CUDA_OK(cudaFuncSetAttribute(nms_sparse_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_sparse_resolve_kernel<<<SP_CLUSTER, SP_RESOLVE_THREADS, smem, st>>>(order, n, max_keep, edge_cap, sb, keep64, keep32, num_keep);
+    SLN_LAUNCH_OK("nms_sparse_resolve_kernel");
+    *skip_out = &sb.hdr->status;
+    return SLN_OK;
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static size_t scan_smem_bytes(int W)
@@ -652,8 +1120,9 @@ static size_t scan_smem_bytes(int W)
 
 __global__ void nms_emit_stageA_kernel(const int *__restrict__ keepA, const int *__restrict__ numA,
                                        const int *__restrict__ order, int64_t *__restrict__ keep64,
-                                       int *__restrict__ keep32)
+                                       int *__restrict__ keep32, const int *__restrict__ skip)
 {
+    if (skip && *skip == 1) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *numA) return;
     const int pos = keepA[i];
@@ -680,6 +1149,7 @@ size_t nms_buffers_bytes(int n)
     b += 3 * align_up(sizeof(int) * (size_t)n, 256);
     b += align_up(sizeof(unsigned long long) * nm * W, 256);
     b += 2 * nms_fix_bytes(n);
+    b += nms_sparse_bytes(n);
     if (nms_two_stage(n)) {
         b += align_up(sizeof(unsigned long long) * (size_t)NMS_STAGE_A * (NMS_STAGE_A / 64), 256);   // stage-A mask
         b += align_up(sizeof(float4) * nm, 256) + align_up(sizeof(float) * nm, 256);                   // boxes2, areas2
@@ -703,20 +1173,21 @@ void nms_carve(void *ws, int n, NmsBuffers &b)
     b.rank = reinterpret_cast<int *>(p);     p += align_up(sizeof(int) * (size_t)n, 256);
     b.mask = reinterpret_cast<unsigned long long *>(p); p += align_up(sizeof(unsigned long long) * nm * W, 256);
     b.fix = p;                               p += 2 * nms_fix_bytes(n);
+    b.sparse = p;                            p += nms_sparse_bytes(n);
     b.stage = p;
 }
 
 static int launch_mask(const float4 *boxes, const float *areas, const int *cls, int n_max, const int *n_dev,
-                       int W_stride, float thresh, unsigned long long *mask, cudaStream_t st)
+                       int W_stride, float thresh, unsigned long long *mask, const int *skip, cudaStream_t st)
 {
     const int W = cdiv(n_max, 64);
     const long long n_tiles = (long long)W * (W + 1) / 2;
     const long long n_blocks = (n_tiles + MASK_GROUPS - 1) / MASK_GROUPS;
     SLN_REQUIRE(n_blocks < (1ll << 31), SLN_ERR_ARG, "nms: n=%d too large", n_max);
     if (cls)
-        nms_mask_kernel<true><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask);
+        nms_mask_kernel<true><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip);
     else
-        nms_mask_kernel<false><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask);
+        nms_mask_kernel<false><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip);
     SLN_LAUNCH_OK("nms_mask_kernel");
     return SLN_OK;
 }
@@ -730,7 +1201,7 @@ static size_t nms_fix_bytes(int n_max)
 
 static int launch_scan(const unsigned long long *mask, const int *order, int n_max, const int *n_dev, int W_stride,
                        int max_keep, const int *keep_base_dev, int64_t *keep64, int *keep32, int *num_keep,
-                       void *fix, cudaStream_t st)
+                       void *fix, const int *skip, cudaStream_t st)
 {
     // (1) parallel fixed-point resolve on the whole GPU
     const bool parallel = W_stride >= FIX_MIN_WORDS;     // short problems: the serial chain is cheaper than grid barriers
@@ -752,7 +1223,7 @@ static int launch_scan(const unsigned long long *mask, const int *order, int n_m
     if (parallel) {
     void *args[] = {(void *)&mask, (void *)&order, (void *)&n_host, (void *)&n_dev, (void *)&W_stride, (void *)&max_keep,
                     (void *)&keep_base_dev, (void *)&removed, (void *)&Kbuf, (void *)&state, (void *)&keep64,
-                    (void *)&keep32, (void *)&num_keep};
+                    (void *)&keep32, (void *)&num_keep, (void *)&skip};
     SLN_CUDA_OK(cudaLaunchCooperativeKernel((const void *)nms_fixpoint_kernel, dim3(G), dim3(FIX_THREADS), args, 0, st));
     }
     // (2) serial scan: only does work when the fixed point was not reached in FIX_MAX_ROUNDS
@@ -760,7 +1231,7 @@ static int launch_scan(const unsigned long long *mask, const int *order, int n_m
     SLN_REQUIRE(smem <= 220 * 1024, SLN_ERR_ARG, "nms: n=%d too large for the scan kernel", n_max);
     SLN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(mask, order, n_max, n_dev, W_stride, max_keep, keep_base_dev, keep64,
-                                                  keep32, num_keep, &state->status);
+                                                  keep32, num_keep, &state->status, skip);
     SLN_LAUNCH_OK("nms_scan_kernel");
     return SLN_OK;
 }
@@ -769,18 +1240,22 @@ static int launch_scan(const unsigned long long *mask, const int *order, int n_m
 // are visiting positions.
 int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, const int *order, int n,
                       float thresh, int max_keep, unsigned long long *mask, int64_t *keep64, int *keep32,
-                      int *num_keep, cudaStream_t st, void *stage, void *fix)
+                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse)
 {
     if (max_keep <= 0 || max_keep > n) max_keep = n;
     if (n == 0) {
         SLN_CUDA_OK(cudaMemsetAsync(num_keep, 0, sizeof(int), st));
         return SLN_OK;
     }
+    // sparse path first; the dense kernels below are launched regardless and leave at once when it succeeded
+    const int *skip = nullptr;
+    int rc = launch_sparse(boxes, areas, cls, order, n, thresh, max_keep, keep64, keep32, num_keep, sparse, st, &skip);
+    if (rc != SLN_OK) return rc;
     if (!nms_two_stage(n) || stage == nullptr) {
         const int W = cdiv(n, 64);
-        int rc = launch_mask(boxes, areas, cls, n, nullptr, W, thresh, mask, st);
+        rc = launch_mask(boxes, areas, cls, n, nullptr, W, thresh, mask, skip, st);
         if (rc != SLN_OK) return rc;
-        return launch_scan(mask, order, n, nullptr, W, max_keep, nullptr, keep64, keep32, num_keep, fix, st);
+        return launch_scan(mask, order, n, nullptr, W, max_keep, nullptr, keep64, keep32, num_keep, fix, skip, st);
     }
     // ---- two stages
     const int T = NMS_STAGE_A, nm = n - T, W2 = cdiv(nm, 64);
@@ -795,24 +1270,24 @@ int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, c
     int *numA = reinterpret_cast<int *>(p);
     int *n2 = numA + 1;
     // stage A: exact NMS of the first T boxes; survivors go straight to the output
-    int rc = launch_mask(boxes, areas, cls, T, nullptr, T / 64, thresh, maskA, st);
+    rc = launch_mask(boxes, areas, cls, T, nullptr, T / 64, thresh, maskA, skip, st);
     if (rc != SLN_OK) return rc;
-    rc = launch_scan(maskA, nullptr, T, nullptr, T / 64, max_keep, nullptr, nullptr, keepA, numA, fix, st);
+    rc = launch_scan(maskA, nullptr, T, nullptr, T / 64, max_keep, nullptr, nullptr, keepA, numA, fix, skip, st);
     if (rc != SLN_OK) return rc;
     // everything a stage-A survivor overlaps is gone; compact the rest (order preserved)
-    if (cls) nms_suppress_kernel<true><<<cdiv(nm, 256), 256, 0, st>>>(boxes, areas, cls, T, n, keepA, numA, thresh, dead);
-    else nms_suppress_kernel<false><<<cdiv(nm, 256), 256, 0, st>>>(boxes, areas, cls, T, n, keepA, numA, thresh, dead);
+    if (cls) nms_suppress_kernel<true><<<cdiv(nm, 256), 256, 0, st>>>(boxes, areas, cls, T, n, keepA, numA, thresh, dead, skip);
+    else nms_suppress_kernel<false><<<cdiv(nm, 256), 256, 0, st>>>(boxes, areas, cls, T, n, keepA, numA, thresh, dead, skip);
     SLN_LAUNCH_OK("nms_suppress_kernel");
-    nms_compact_kernel<<<1, 1024, 0, st>>>(boxes, areas, cls, order, dead, T, n, boxes2, areas2, cls2, order2, n2);
+    nms_compact_kernel<<<1, 1024, 0, st>>>(boxes, areas, cls, order, dead, T, n, boxes2, areas2, cls2, order2, n2, skip);
     SLN_LAUNCH_OK("nms_compact_kernel");
     // stage-A survivors -> output (positions -> original indices)
-    nms_emit_stageA_kernel<<<cdiv(T, 256), 256, 0, st>>>(keepA, numA, order, keep64, keep32);
+    nms_emit_stageA_kernel<<<cdiv(T, 256), 256, 0, st>>>(keepA, numA, order, keep64, keep32, skip);
     SLN_LAUNCH_OK("nms_emit_stageA_kernel");
     // stage B on the compacted remainder, appended after the stage-A survivors
-    rc = launch_mask(boxes2, areas2, cls ? cls2 : nullptr, nm, n2, W2, thresh, mask, st);
+    rc = launch_mask(boxes2, areas2, cls ? cls2 : nullptr, nm, n2, W2, thresh, mask, skip, st);
     if (rc != SLN_OK) return rc;
     return launch_scan(mask, order2, nm, n2, W2, max_keep, numA, keep64, keep32, num_keep,
-                       static_cast<unsigned char *>(fix) + nms_fix_bytes(n), st);
+                       static_cast<unsigned char *>(fix) + nms_fix_bytes(n), skip, st);
 }
 
 }  // namespace sln
@@ -825,12 +1300,14 @@ extern "C" size_t sln_nms_workspace_bytes(int n)
     return nms_buffers_bytes(n);
 }
 
-extern "C" int sln_nms(const float *dets, const int *class_ids, int n, float thresh, int max_keep,
-                       int64_t *keep, int *num_keep, void *workspace, size_t workspace_bytes, void *stream)
+extern "C" int sln_nms_ex(const float *dets, const int *class_ids, int n, float thresh, int max_keep, int flags,
+                          int64_t *keep, int *num_keep, int *path_out, void *workspace, size_t workspace_bytes,
+                          void *stream)
 {
     SLN_REQUIRE(n >= 0, SLN_ERR_ARG, "negative n");
     SLN_REQUIRE(num_keep != nullptr, SLN_ERR_ARG, "null num_keep");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (path_out) SLN_CUDA_OK(cudaMemsetAsync(path_out, 0, sizeof(int), st));
     if (n == 0) {
         SLN_CUDA_OK(cudaMemsetAsync(num_keep, 0, sizeof(int), st));
         return SLN_OK;
@@ -840,11 +1317,22 @@ extern "C" int sln_nms(const float *dets, const int *class_ids, int n, float thr
                 "nms workspace: need %zu bytes, got %zu", nms_buffers_bytes(n), workspace_bytes);
     NmsBuffers b;
     nms_carve(workspace, n, b);
+    const bool try_sparse = !(flags & SLN_NMS_DENSE_ONLY) && n >= SP_MIN_N && n <= SP_MAX_N && thresh >= 0.05f;
     SLN_CUDA_OK(cudaMemsetAsync(b.rank, 0, sizeof(int) * (size_t)n, st));
     int rc = rank_sort_launch(dets + 4, 5, nullptr, n, b.rank, st);
     if (rc != SLN_OK) return rc;
     nms_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(dets, class_ids, b.rank, n, b.boxes, b.areas, b.cls, b.order);
     SLN_LAUNCH_OK("nms_gather_kernel");
-    return nms_sorted_launch(b.boxes, b.areas, class_ids ? b.cls : nullptr, b.order, n, thresh, max_keep, b.mask,
-                             keep, nullptr, num_keep, st, b.stage, b.fix);
+    rc = nms_sorted_launch(b.boxes, b.areas, class_ids ? b.cls : nullptr, b.order, n, thresh, max_keep, b.mask,
+                           keep, nullptr, num_keep, st, b.stage, b.fix, try_sparse ? b.sparse : nullptr);
+    if (rc != SLN_OK) return rc;
+    if (path_out && try_sparse)      // SparseHdr.status: 1 when the sparse path produced the result
+        SLN_CUDA_OK(cudaMemcpyAsync(path_out, b.sparse, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SLN_OK;
+}
+
+extern "C" int sln_nms(const float *dets, const int *class_ids, int n, float thresh, int max_keep,
+                       int64_t *keep, int *num_keep, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return sln_nms_ex(dets, class_ids, n, thresh, max_keep, 0, keep, num_keep, nullptr, workspace, workspace_bytes, stream);
 }

@@ -16,6 +16,7 @@ struct NmsBuffers {
     unsigned long long *mask;      // [n][W] IoU>=thresh bitmask, W = ceil(n/64)
     void *stage;                   // scratch of the two-stage pipeline (see nms.cu)
     void *fix;                     // scratch of the parallel fixed-point resolve
+    void *sparse;                  // scratch of the sparse (binned) path
 };
 
 size_t nms_buffers_bytes(int n);
@@ -26,7 +27,7 @@ void nms_carve(void *ws, int n, NmsBuffers &b);
 //   keep64 / keep32  : either may be nullptr
 int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, const int *order, int n,
                       float thresh, int max_keep, unsigned long long *mask, int64_t *keep64, int *keep32,
-                      int *num_keep, cudaStream_t st, void *stage, void *fix);
+                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse);
 
 // Total order used everywhere a "descending score, stable" sort is needed:
 // larger key first; NaN sorts as the largest value (torch.sort's convention);

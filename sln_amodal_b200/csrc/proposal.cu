@@ -353,7 +353,7 @@ extern "C" int sln_proposal_layer(const float *probs, const float *deltas, const
                                                         nb.boxes, nb.areas);
     SLN_LAUNCH_OK("proposal_decode_kernel");
     rc = nms_sorted_launch(nb.boxes, nb.areas, nullptr, nullptr, K, nms_thresh, proposal_count, nb.mask, nullptr,
-                           b.keep, b.num_keep, st, nb.stage, nb.fix);
+                           b.keep, b.num_keep, st, nb.stage, nb.fix, nb.sparse);
     if (rc != SLN_OK) return rc;
     proposal_finalize_kernel<<<cdiv(proposal_count, 128), 128, 0, st>>>(
         nb.boxes, b.keep, b.num_keep, proposal_count, img_h, img_w, reinterpret_cast<float4 *>(out_boxes), num_out);

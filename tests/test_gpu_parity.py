@@ -279,6 +279,98 @@ def test_nms_empty_and_degenerate():
         assert np.array_equal(nms(cuda(dets), thr).cpu().numpy(), oracle.nms(dets, thr))
 
 
+def _nms_both_paths(dets, thr, cls=None, max_keep=0):
+    """(sparse-or-whatever-ran result, dense-only result, path flag) as numpy."""
+    from sln_amodal_b200 import ops
+    d = cuda(dets)
+    c = None if cls is None else cuda(cls)
+    keep, num, path = ops.nms_device(d, thr, class_ids=c, max_keep=max_keep, return_path=True)
+    keep_d, num_d = ops.nms_device(d, thr, class_ids=c, max_keep=max_keep, dense_only=True)
+    return (keep[: int(num.item())].cpu().numpy(), keep_d[: int(num_d.item())].cpu().numpy(), int(path.item()))
+
+
+@pytest.mark.parametrize("kind,n,thr,sparse", [
+    ("rpn", 65, 0.7, True), ("rpn", 1000, 0.7, True), ("rpn", 12000, 0.7, True), ("uniform", 12000, 0.7, True),
+    ("rpn", 6000, 0.5, None), ("rpn", 6000, 0.3, None), ("uniform", 6000, 0.3, True), ("rpn", 4000, 0.05, None),
+    ("uniform", 4000, 0.05, None), ("rpn", 3000, 0.95, True), ("rpn", 3000, 1.0, True), ("rpn", 40000, 0.7, True),
+    ("uniform", 65535, 0.6, True)])
+def test_nms_sparse_path_equals_dense_and_oracle(kind, n, thr, sparse):
+    """The binned pipeline must take the inputs marked True (path == 1) -- the others may exceed its edge budget and
+    hand over to the dense kernels on the device -- and always agree with the dense bit-matrix pipeline; up to 12k
+    boxes both are also checked against nms.c."""
+    dets = np.concatenate([synth.nms_boxes(n, seed=31 + n, kind=kind), synth.nms_scores(n, seed=32 + n)[:, None]], 1)
+    got, dense, path = _nms_both_paths(dets, thr)
+    assert path == 1 or not sparse
+    assert np.array_equal(got, dense)
+    if n <= 12000:
+        assert np.array_equal(got, oracle.nms(dets, thr))
+    got, dense, path = _nms_both_paths(dets, thr, max_keep=100)
+    assert (path == 1 or not sparse) and np.array_equal(got, dense) and got.size <= 100
+
+
+def test_nms_sparse_path_offsets_and_scales():
+    """Windows are relative to the box size and the grid to the centres' bounding box: translated, huge and tiny
+    boxes (still inside +-32768) must stay on the sparse path and agree with nms.c."""
+    n = 3000
+    base = synth.nms_boxes(n, seed=5)
+    sc = synth.nms_scores(n, seed=6)
+    for scale, shift in ((1.0, -20000.0), (30.0, 0.0), (1.0 / 8, 0.0), (1.0 / 512, 0.0), (1.0, 31000.0)):
+        dets = np.concatenate([(base * scale + shift).astype(np.float32), sc[:, None]], 1)
+        got, dense, path = _nms_both_paths(dets, 0.7)
+        assert path == 1 or scale < 1.0          # sub-pixel boxes all overlap under the +1 convention: may bail out
+        assert np.array_equal(got, dense) and np.array_equal(got, oracle.nms(dets, 0.7))
+
+
+def test_nms_sparse_path_bails_out_to_dense():
+    """Outside the sparse contract the dense kernels must produce the result: heavy duplication (more than
+    16 n overlapping pairs), non-finite / inverted / far-away boxes, tiny thresholds."""
+    rng = np.random.default_rng(11)
+    n = 2000
+    sc = synth.nms_scores(n, seed=13)
+    # (a) 2000 near-identical boxes: ~n^2/2 edges
+    boxes = (np.array([100, 100, 300, 300], np.float32) + rng.normal(0, 1.0, (n, 4))).astype(np.float32)
+    dets = np.concatenate([boxes, sc[:, None]], 1)
+    got, dense, path = _nms_both_paths(dets, 0.7)
+    assert path == 0 and np.array_equal(got, dense) and np.array_equal(got, oracle.nms(dets, 0.7))
+    # (b) one inverted box / one NaN / one inf / one far outside the coordinate bound
+    base = synth.nms_boxes(n, seed=14)
+    for bad in ([50, 50, 10, 10], [np.nan, 0, 10, 10], [0, 0, np.inf, 10], [0, 0, 10, 40000.0]):
+        b = base.copy()
+        b[777] = np.array(bad, np.float32)
+        dets = np.concatenate([b, sc[:, None]], 1)
+        got, dense, path = _nms_both_paths(dets, 0.7)
+        assert path == 0 and np.array_equal(got, dense)
+        if np.isfinite(b).all():
+            assert np.array_equal(got, oracle.nms(dets, 0.7))
+    # (c) thresholds below 0.05 (and NaN) are dense by construction
+    dets = np.concatenate([base, sc[:, None]], 1)
+    for thr in (0.0, 0.01, -1.0):
+        got, dense, path = _nms_both_paths(dets, thr)
+        assert path == 0 and np.array_equal(got, oracle.nms(dets, thr))
+
+
+def test_nms_sparse_chain_falls_back():
+    """A 3000-long dependency chain exceeds the sparse resolve's round budget: dense takes over, still exact."""
+    n = 3000
+    k = np.arange(n, dtype=np.float32)
+    boxes = np.stack([np.zeros(n, np.float32), k * 12.0, np.full(n, 49.0, np.float32), k * 12.0 + 99.0], 1)
+    dets = np.concatenate([boxes, np.linspace(1.0, 0.0, n, dtype=np.float32)[:, None]], 1).astype(np.float32)
+    got, dense, path = _nms_both_paths(dets, 0.7)
+    assert path == 0 and np.array_equal(got, np.arange(0, n, 2)) and np.array_equal(dense, got)
+
+
+@pytest.mark.parametrize("K,n,thr", [(81, 12000, 0.3), (61, 12000, 0.3), (5, 5000, 0.5), (1000, 8000, 0.3)])
+def test_nms_sparse_class_aware_equals_dense(K, n, thr):
+    rng = np.random.default_rng(K + n)
+    boxes = synth.nms_boxes(n, seed=40 + K, rounded=True)
+    dets = np.concatenate([boxes, synth.nms_scores(n, seed=41 + K)[:, None]], 1)
+    cls = (rng.integers(0, K, n) - K // 2).astype(np.int32)          # negative ids too
+    got, dense, path = _nms_both_paths(dets, thr, cls=cls)
+    assert path == 1 and np.array_equal(got, dense)
+    want = oracle.per_class_nms(boxes, cls, dets[:, 4].copy(), thr)
+    assert np.array_equal(np.sort(got), want)
+
+
 @pytest.mark.parametrize("K,n", [(81, 3000), (61, 12000)])
 def test_per_class_nms_matches_reference_loop(K, n):
     from sln_amodal_b200 import batched_nms
