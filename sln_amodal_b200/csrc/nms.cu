@@ -30,25 +30,52 @@ constexpr int RANK_COLS = 1024;    // elements compared against per CTA (staged 
 // MODE 0: every column index is below every row index of this CTA  -> count key_j >= key_i
 // MODE 1: every column index is above every row index              -> count key_j >  key_i
 // MODE 2: index ranges overlap, or explicit tie ids                 -> full (key, tie) compare
-template <int MODE>
-__device__ __forceinline__ int rank_count(const uint4 *__restrict__ k4, const int4 *__restrict__ t4, int n4,
-                                          unsigned ki, int ti)
+// Carry-flag counting: `sub.cc` leaves the carry of a - b in CC.CF and `addc` adds it to the counter -- two
+// instructions per compare, no predicate (ptxas even folds two carries into one IADD3.X).  Whether CF means
+// "borrow" (a < b, the PTX manual's wording) or "no borrow" (a >= b, what the sm_100a SASS does) is NOT assumed:
+// carry_counts_ge() probes it once per thread and the callers fold the answer in.
+__device__ __forceinline__ void count_cf(int &cnt, unsigned a, unsigned b)
 {
-    int cnt = 0;
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(cnt) : "r"(a), "r"(b));
+}
+// same for (ahi, alo) - (bhi, blo) as 64-bit unsigned, three instructions
+__device__ __forceinline__ void count_cf64(int &cnt, unsigned ahi, unsigned alo, unsigned bhi, unsigned blo)
+{
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.cc.u32 t, %3, %4;\n\taddc.u32 %0, %0, 0;\n\t}"
+        : "+r"(cnt) : "r"(alo), "r"(blo), "r"(ahi), "r"(bhi));
+}
+__device__ __forceinline__ bool carry_counts_ge(unsigned one)    // `one` must be a run-time 1
+{
+    int probe = 0;
+    count_cf(probe, one, 0u);                       // 1 - 0: no borrow
+    return probe != 0;                              // true: count_cf counts a >= b; false: it counts a < b
+}
+
+// s_tie holds ~tie: "j precedes i" <=> (key_j, ~tie_j) > (key_i, ~tie_i) as one 64-bit unsigned compare.
+// Returns, over the 4*n4 staged columns (padding: key 0, ~tie 0x80000000 -- never precedes anything and is never
+// below anything):  MODE 0: #(key_j >= key_i)   MODE 1: #(key_j > key_i)   MODE 2: #(j precedes i)
+template <int MODE>
+__device__ __forceinline__ int rank_count(const uint4 *__restrict__ k4, const uint4 *__restrict__ t4, int n4,
+                                          unsigned ki, unsigned nti, bool cf_is_ge)
+{
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;            // four independent carry chains
 #pragma unroll 4
     for (int q = 0; q < n4; ++q) {
         const uint4 k = k4[q];      // broadcast 16-byte shared load: four keys per instruction
-        if (MODE == 0) {
-            cnt += (k.x >= ki) + (k.y >= ki) + (k.z >= ki) + (k.w >= ki);
-        } else if (MODE == 1) {
-            cnt += (k.x > ki) + (k.y > ki) + (k.z > ki) + (k.w > ki);
-        } else {
-            const int4 t = t4[q];
-            cnt += (k.x > ki || (k.x == ki && t.x < ti)) + (k.y > ki || (k.y == ki && t.y < ti)) +
-                   (k.z > ki || (k.z == ki && t.z < ti)) + (k.w > ki || (k.w == ki && t.w < ti));
+        if (MODE == 0) {            // carry of key_j - key_i
+            count_cf(c0, k.x, ki); count_cf(c1, k.y, ki); count_cf(c2, k.z, ki); count_cf(c3, k.w, ki);
+        } else if (MODE == 1) {     // carry of key_i - key_j
+            count_cf(c0, ki, k.x); count_cf(c1, ki, k.y); count_cf(c2, ki, k.z); count_cf(c3, ki, k.w);
+        } else {                    // carry of K_i - K_j
+            const uint4 t = t4[q];
+            count_cf64(c0, ki, nti, k.x, t.x); count_cf64(c1, ki, nti, k.y, t.y);
+            count_cf64(c2, ki, nti, k.z, t.z); count_cf64(c3, ki, nti, k.w, t.w);
         }
     }
-    return cnt;
+    const int c = (c0 + c1) + (c2 + c3), all = 4 * n4;
+    // MODE 0 wants #(key_j >= key_i); MODES 1/2 want #(K_i < K_j)
+    if (MODE == 0) return cf_is_ge ? c : all - c;
+    return cf_is_ge ? all - c : c;
 }
 
 __global__ void __launch_bounds__(RANK_ROWS)
@@ -56,37 +83,53 @@ rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict_
             int *__restrict__ rank)
 {
     __shared__ __align__(16) unsigned s_key[RANK_COLS];
-    __shared__ __align__(16) int s_tie[RANK_COLS];
+    __shared__ __align__(16) unsigned s_tie[RANK_COLS];     // ~tie id
     const int i0 = blockIdx.x * RANK_ROWS, i = i0 + threadIdx.x;
     const int j0 = blockIdx.y * RANK_COLS;
     const int jn = min(RANK_COLS, n - j0);
     // pad the tile to a multiple of 4 with entries that never count (key 0 with the largest tie id
     // loses every compare except against key 0 rows in MODE 0, handled by clamping below)
-    for (int t = threadIdx.x; t < RANK_COLS; t += RANK_ROWS) {
-        unsigned k = 0u;
-        int tie = 0x7fffffff;
+    // all loads of the thread (4 column keys, its own row key) are issued before the first use
+    float sc[RANK_COLS / RANK_ROWS];
+    int tie[RANK_COLS / RANK_ROWS];
+#pragma unroll
+    for (int q = 0; q < RANK_COLS / RANK_ROWS; ++q) {
+        const int t = threadIdx.x + q * RANK_ROWS;
+        sc[q] = 0.f;
+        tie[q] = 0x7fffffff;
         if (t < jn) {
-            k = score_key(__ldg(scores + (size_t)(j0 + t) * stride));
-            tie = tie_ids ? __ldg(tie_ids + j0 + t) : (j0 + t);
+            sc[q] = __ldg(scores + (size_t)(j0 + t) * stride);
+            tie[q] = tie_ids ? __ldg(tie_ids + j0 + t) : (j0 + t);
         }
-        s_key[t] = k;
-        s_tie[t] = tie;
+    }
+    float si = 0.f;
+    int ti = i;
+    if (i < n) {
+        si = __ldg(scores + (size_t)i * stride);
+        if (tie_ids) ti = __ldg(tie_ids + i);
+    }
+#pragma unroll
+    for (int q = 0; q < RANK_COLS / RANK_ROWS; ++q) {
+        const int t = threadIdx.x + q * RANK_ROWS;
+        s_key[t] = t < jn ? score_key(sc[q]) : 0u;
+        s_tie[t] = ~(unsigned)tie[q];
     }
     __syncthreads();
     if (i >= n) return;
-    const unsigned ki = score_key(__ldg(scores + (size_t)i * stride));
-    const int ti = tie_ids ? __ldg(tie_ids + i) : i;
+    const unsigned ki = score_key(si);
     const int n4 = (jn + 3) >> 2, pad = n4 * 4 - jn;
     const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key);
-    const int4 *t4 = reinterpret_cast<const int4 *>(s_tie);
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(s_tie);
+    const unsigned nti = ~(unsigned)ti;
+    const bool cf_ge = carry_counts_ge((unsigned)(stride > 0));
     int cnt;
     if (tie_ids == nullptr && j0 + jn <= i0) {
-        cnt = rank_count<0>(k4, t4, n4, ki, ti);
+        cnt = rank_count<0>(k4, t4, n4, ki, nti, cf_ge);
         if (ki == 0u) cnt -= pad;                      // padded keys (0) satisfy 0 >= 0
     } else if (tie_ids == nullptr && j0 >= i0 + RANK_ROWS) {
-        cnt = rank_count<1>(k4, t4, n4, ki, ti);
+        cnt = rank_count<1>(k4, t4, n4, ki, nti, cf_ge);
     } else {
-        cnt = rank_count<2>(k4, t4, n4, ki, ti);
+        cnt = rank_count<2>(k4, t4, n4, ki, nti, cf_ge);
     }
     if (cnt) atomicAdd(rank + i, cnt);
 }
@@ -166,43 +209,46 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ area
     __shared__ float s_area[MASK_GROUPS][64];
     __shared__ int s_cls[MASK_GROUPS][64];
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
-    const long long tile = (long long)blockIdx.x * MASK_GROUPS + grp;
-    const bool active = tile < n_tiles;
-    int rb = 0, cb = 0;
-    if (active) {
-        // tiles are numbered row block by row block: row rb holds W-rb tiles (cb = rb..W-1)
-        // start(rb) = rb*W - rb*(rb-1)/2
-        const double Wd = (double)W + 0.5;
-        rb = (int)(Wd - sqrt(Wd * Wd - 2.0 * (double)tile));
-        if (rb < 0) rb = 0;
-        if (rb > W - 1) rb = W - 1;
-        while (rb > 0 && (long long)rb * W - (long long)rb * (rb - 1) / 2 > tile) --rb;
-        while ((long long)(rb + 1) * W - (long long)(rb + 1) * rb / 2 <= tile) ++rb;
-        cb = rb + (int)(tile - ((long long)rb * W - (long long)rb * (rb - 1) / 2));
-        const int j = cb * 64 + t;
-        if (j < n) {
-            s_box[grp][t] = boxes[j];
-            s_area[grp][t] = areas[j];
-            if (CLS) s_cls[grp][t] = cls[j];
+    // grid-strided over blocks of MASK_GROUPS tiles (the grid is capped so that the "skip" exit above is cheap)
+    for (long long tb = blockIdx.x; tb * MASK_GROUPS < n_tiles; tb += gridDim.x) {
+        const long long tile = tb * MASK_GROUPS + grp;
+        const bool active = tile < n_tiles;
+        int rb = 0, cb = 0;
+        __syncthreads();                           // the previous iteration's reads of s_box are done
+        if (active) {
+            // tiles are numbered row block by row block: row rb holds W-rb tiles (cb = rb..W-1)
+            // start(rb) = rb*W - rb*(rb-1)/2
+            const double Wd = (double)W + 0.5;
+            rb = (int)(Wd - sqrt(Wd * Wd - 2.0 * (double)tile));
+            if (rb < 0) rb = 0;
+            if (rb > W - 1) rb = W - 1;
+            while (rb > 0 && (long long)rb * W - (long long)rb * (rb - 1) / 2 > tile) --rb;
+            while ((long long)(rb + 1) * W - (long long)(rb + 1) * rb / 2 <= tile) ++rb;
+            cb = rb + (int)(tile - ((long long)rb * W - (long long)rb * (rb - 1) / 2));
+            const int j = cb * 64 + t;
+            if (j < n) {
+                s_box[grp][t] = boxes[j];
+                s_area[grp][t] = areas[j];
+                if (CLS) s_cls[grp][t] = cls[j];
+            }
         }
-    }
-    __syncthreads();
-    if (!active) return;
-    const int i = rb * 64 + t;
-    if (i >= n) return;
-    const float4 bi = boxes[i];
-    const float ai = areas[i];
-    const int ci = CLS ? cls[i] : 0;
-    const int jn = min(64, n - cb * 64);
-    unsigned long long bits = 0ull;
+        __syncthreads();
+        const int i = rb * 64 + t;
+        if (!active || i >= n) continue;
+        const float4 bi = boxes[i];
+        const float ai = areas[i];
+        const int ci = CLS ? cls[i] : 0;
+        const int jn = min(64, n - cb * 64);
+        unsigned long long bits = 0ull;
 #pragma unroll 4
-    for (int k = 0; k < jn; ++k) {
-        bool hit = iou_ge(bi, ai, s_box[grp][k], s_area[grp][k], thresh);
-        if (CLS) hit = hit && (s_cls[grp][k] == ci);
-        bits |= (unsigned long long)hit << k;
+        for (int k = 0; k < jn; ++k) {
+            bool hit = iou_ge(bi, ai, s_box[grp][k], s_area[grp][k], thresh);
+            if (CLS) hit = hit && (s_cls[grp][k] == ci);
+            bits |= (unsigned long long)hit << k;
+        }
+        if (rb == cb) bits &= ~(1ull << t);
+        mask[(size_t)i * W_stride + cb] = bits;
     }
-    if (rb == cb) bits &= ~(1ull << t);
-    mask[(size_t)i * W_stride + cb] = bits;
 }
 
 // ---------------------------------------------------------------------------
@@ -673,11 +719,13 @@ constexpr int SP_MAX_CELLS = 4096;
 constexpr int SP_EDGES_PER_BOX = 16;
 constexpr int SP_BIN_THREADS = 1024;
 constexpr int SP_PAIR_WARPS = 8;
+constexpr int SP_PAIR_UNROLL = 4;          // candidates per lane in flight
+constexpr int SP_INLINE = 16;              // predecessors stored inline per box (32 bytes)
 constexpr int SP_WARP_BUF = 128;           // edges buffered per warp before one atomic allocation
 constexpr int SP_MAX_ROUNDS = 96;
 constexpr int SP_RESOLVE_THREADS = 1024;
-constexpr int SP_SMEM_EDGES = 40960;       // edges cached in shared memory by the resolve kernel (160 KB)
 constexpr float SP_MAX_COORD = 32768.f;
+constexpr int SP_CLUSTER = 8;             // CTAs of the bin and resolve clusters
 
 struct SparseHdr {
     int status;            // 1: the sparse path produced the result
@@ -694,7 +742,9 @@ struct SparseBufs {
     float *carea;
     int *cpos;
     int *ccls;
-    unsigned *edges;       // [SP_EDGES_PER_BOX * n]
+    uint4 *inl;            // [n][2] the first SP_INLINE predecessors of every box as u16 (0xffff: none)
+    int2 *seg;             // [n] (first entry, count) of the rest of the list in `edges`
+    unsigned *edges;       // [SP_EDGES_PER_BOX * n] overflow predecessor positions, grouped by box
 };
 
 static size_t nms_sparse_bytes(int n)
@@ -704,6 +754,8 @@ static size_t nms_sparse_bytes(int n)
     b += align_up(sizeof(int) * (SP_MAX_CELLS + 1), 256);
     b += align_up(sizeof(float4) * (size_t)n, 256);
     b += 3 * align_up(sizeof(int) * (size_t)n, 256);
+    b += align_up(sizeof(int2) * (size_t)n, 256);
+    b += align_up(sizeof(uint4) * 2 * (size_t)n, 256);
     b += align_up(sizeof(unsigned) * (size_t)SP_EDGES_PER_BOX * n, 256);
     return b;
 }
@@ -717,6 +769,8 @@ static void sparse_carve(void *ws, int n, SparseBufs &b)
     b.carea = reinterpret_cast<float *>(p);       p += align_up(sizeof(int) * (size_t)n, 256);
     b.cpos = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
     b.ccls = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
+    b.seg = reinterpret_cast<int2 *>(p);          p += align_up(sizeof(int2) * (size_t)n, 256);
+    b.inl = reinterpret_cast<uint4 *>(p);         p += align_up(sizeof(uint4) * 2 * (size_t)n, 256);
     b.edges = reinterpret_cast<unsigned *>(p);
 }
 
@@ -733,37 +787,44 @@ __device__ __forceinline__ bool sp_sane(const float4 b)
            fabsf(b.w) <= SP_MAX_COORD && b.z >= b.x && b.w >= b.y;       // false for NaN / inf
 }
 
-// single CTA: bounds of the centres, cell histogram, exclusive scan, scatter into cell order.
-// The three passes over the boxes keep SP_BIN_UNROLL independent 16-byte loads in flight per thread: with one
-// CTA the kernel is bound by load latency, not bandwidth (31 us -> see profiles/README.md).
-constexpr int SP_BIN_UNROLL = 8;
+// One cluster of SP_CLUSTER CTAs: bounds of the centres, cell histogram, exclusive scan, scatter into cell order
+// (a counting sort by cell).  CTA c owns the boxes i = c*1024 + tid + k*8192; partial bounds and histograms are
+// exchanged through distributed shared memory, every CTA scans the summed histogram itself, and its scatter
+// cursor of a cell starts after the boxes of lower-ranked CTAs.  A single CTA was bound by the scattered 36k
+// 4..16-byte stores of one SM (31 us at 12k boxes); the cluster spreads them over 8 SMs.
+constexpr int SP_BIN_ITEMS = (SP_MAX_N + SP_CLUSTER * SP_BIN_THREADS - 1) / (SP_CLUSTER * SP_BIN_THREADS);   // 8
 
 template <bool CLS>
-__global__ void __launch_bounds__(SP_BIN_THREADS)
+__global__ void __cluster_dims__(SP_CLUSTER, 1, 1) __launch_bounds__(SP_BIN_THREADS)
 nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls, int n,
                int G, int CB, SparseBufs sb)
 {
-    __shared__ int s_hist[SP_MAX_CELLS];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ int s_hist[SP_MAX_CELLS];           // this CTA's counts (read by the whole cluster)
+    __shared__ int s_cur[SP_MAX_CELLS];            // this CTA's scatter cursors
     __shared__ float s_red[4][SP_BIN_THREADS / 32];
+    __shared__ float s_part[5];                    // this CTA's bounds + bad flag (read by the whole cluster)
     __shared__ int s_warp[SP_BIN_THREADS / 32];
-    __shared__ int s_bad;
+    __shared__ int s_slice_tot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int crank = (int)cluster.block_rank();
     const int NC = CB * G * G;
-    constexpr int STEP = SP_BIN_THREADS * SP_BIN_UNROLL;
-    if (tid == 0) s_bad = 0;
+    constexpr int STEP = SP_CLUSTER * SP_BIN_THREADS;
     for (int k = tid; k < NC; k += SP_BIN_THREADS) s_hist[k] = 0;
-    __syncthreads();
+    // ---- my boxes: loaded once (all loads in flight), kept in registers
+    float4 v[SP_BIN_ITEMS];
+    const int first = crank * SP_BIN_THREADS + tid;
+#pragma unroll
+    for (int u = 0; u < SP_BIN_ITEMS; ++u) {
+        const int i = first + u * STEP;
+        if (i < n) v[u] = boxes[i];
+    }
     float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
     bool bad = false;
-    for (int i0 = tid; i0 < n; i0 += STEP) {
-        float4 v[SP_BIN_UNROLL];
 #pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
-            const int i = i0 + u * SP_BIN_THREADS;
-            v[u] = boxes[i < n ? i : i0];
-        }
-#pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
+    for (int u = 0; u < SP_BIN_ITEMS; ++u) {
+        if (first + u * STEP < n) {
             const float4 b = v[u];
             bad = bad || !sp_sane(b);
             const float cx = __fmul_rn(0.5f, __fadd_rn(b.x, b.z)), cy = __fmul_rn(0.5f, __fadd_rn(b.y, b.w));
@@ -771,58 +832,72 @@ nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas
             mny = fminf(mny, cy); mxy = fmaxf(mxy, cy);
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
+    auto warp_bounds = [&]() {
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+    };
+    warp_bounds();
     if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
-    if (bad) s_bad = 1;
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) { sb.hdr->status = 0; sb.hdr->bail = 1; sb.hdr->edge_count = 0u; }
-        return;
+    const int any_bad = __syncthreads_or(bad);
+    if (warp == 0) {
+        mnx = s_red[0][lane]; mny = s_red[1][lane]; mxx = s_red[2][lane]; mxy = s_red[3][lane];
+        warp_bounds();
+        if (lane == 0) { s_part[0] = mnx; s_part[1] = mny; s_part[2] = mxx; s_part[3] = mxy; s_part[4] = any_bad ? 1.f : 0.f; }
     }
-    mnx = s_red[0][lane]; mny = s_red[1][lane]; mxx = s_red[2][lane]; mxy = s_red[3][lane];
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    cluster.sync();
+    float badf = 0.f;
+    mnx = 3.0e38f; mny = 3.0e38f; mxx = -3.0e38f; mxy = -3.0e38f;
+#pragma unroll
+    for (int c = 0; c < SP_CLUSTER; ++c) {
+        const float *q = cluster.map_shared_rank(s_part, c);
+        mnx = fminf(mnx, q[0]); mny = fminf(mny, q[1]); mxx = fmaxf(mxx, q[2]); mxy = fmaxf(mxy, q[3]);
+        badf = fmaxf(badf, q[4]);
+    }
+    if (badf != 0.f) {                             // uniform over the cluster
+        if (crank == 0 && tid == 0) { sb.hdr->status = 0; sb.hdr->bail = 1; sb.hdr->edge_count = 0u; }
+        cluster.sync();                            // nobody leaves while its s_part may still be read
+        return;
     }
     const float invx = __fdiv_rn((float)G, fmaxf(__fsub_rn(mxx, mnx), 1e-3f));
     const float invy = __fdiv_rn((float)G, fmaxf(__fsub_rn(mxy, mny), 1e-3f));
-    if (tid == 0) {
+    if (crank == 0 && tid == 0) {
         sb.hdr->status = 0; sb.hdr->bail = 0; sb.hdr->edge_count = 0u;
         sb.hdr->G = G; sb.hdr->CB = CB;
         sb.hdr->minx = mnx; sb.hdr->miny = mny; sb.hdr->invx = invx; sb.hdr->invy = invy;
     }
-    auto key_of = [&](const float4 b, int c) {
-        const float cx = __fmul_rn(0.5f, __fadd_rn(b.x, b.z)), cy = __fmul_rn(0.5f, __fadd_rn(b.y, b.w));
-        const int cb = CLS ? (int)((unsigned)c % (unsigned)CB) : 0;
-        return (cb * G + sp_cell(cy, mny, invy, G)) * G + sp_cell(cx, mnx, invx, G);
-    };
-    for (int i0 = tid; i0 < n; i0 += STEP) {
-        float4 v[SP_BIN_UNROLL];
-        int c[SP_BIN_UNROLL];
+    // ---- keys and this CTA's histogram
+    int key[SP_BIN_ITEMS];
 #pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
-            const int i = i0 + u * SP_BIN_THREADS;
-            v[u] = boxes[i < n ? i : i0];
-            c[u] = CLS ? cls[i < n ? i : i0] : 0;
+    for (int u = 0; u < SP_BIN_ITEMS; ++u) {
+        const int i = first + u * STEP;
+        key[u] = 0;
+        if (i < n) {
+            const float4 b = v[u];
+            const float cx = __fmul_rn(0.5f, __fadd_rn(b.x, b.z)), cy = __fmul_rn(0.5f, __fadd_rn(b.y, b.w));
+            const int cb = CLS ? (int)((unsigned)cls[i] % (unsigned)CB) : 0;
+            key[u] = (cb * G + sp_cell(cy, mny, invy, G)) * G + sp_cell(cx, mnx, invx, G);
+            atomicAdd(&s_hist[key[u]], 1);
         }
-#pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u)
-            if (i0 + u * SP_BIN_THREADS < n) atomicAdd(&s_hist[key_of(v[u], c[u])], 1);
     }
-    __syncthreads();
-    // exclusive scan of NC <= 4096 counters: 4 per thread
+    cluster.sync();
+    // ---- CTA c sums the 8 histograms over ITS slice of the cells (one cell per thread, consecutive lanes =
+    // consecutive cells: each remote access is one coalesced row), scans the slice, and hands every CTA its
+    // scatter cursors -- 16 DSMEM accesses per thread instead of every CTA reading every histogram
     {
-        int v[4], sum = 0;
+        const int slice = (NC + SP_CLUSTER - 1) / SP_CLUSTER;   // <= 512
+        const int k = crank * slice + tid;
+        const bool mine = tid < slice && k < NC;
+        int hc[SP_CLUSTER], tot = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int k = 4 * tid + q; v[q] = k < NC ? s_hist[k] : 0; sum += v[q]; }
-        int incl = sum;
+        for (int c = 0; c < SP_CLUSTER; ++c) {
+            hc[c] = mine ? *cluster.map_shared_rank(s_hist + k, c) : 0;
+            tot += hc[c];
+        }
+        int incl = tot;
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
@@ -836,39 +911,39 @@ nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas
                 if (lane >= o) wi += t;
             }
             s_warp[lane] = wi - w;
+            if (lane == 31) s_slice_tot = wi;      // boxes in my slice of the cells
         }
         __syncthreads();
-        int run = s_warp[warp] + incl - sum;
+        const int local_excl = s_warp[warp] + incl - tot;
+        cluster.sync();                            // slice totals visible
+        int slice_off = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = 4 * tid + q;
-            if (k < NC) { s_hist[k] = run; sb.cell_start[k] = run; }
-            run += v[q];
+        for (int c = 0; c < SP_CLUSTER; ++c) {
+            const int t = *cluster.map_shared_rank(&s_slice_tot, c);
+            if (c < crank) slice_off += t;
         }
-        if (tid == 0) sb.cell_start[NC] = n;
-    }
-    __syncthreads();
-    for (int i0 = tid; i0 < n; i0 += STEP) {
-        float4 v[SP_BIN_UNROLL];
-        float a[SP_BIN_UNROLL];
-        int c[SP_BIN_UNROLL];
+        if (mine) {
+            int run = slice_off + local_excl;
+            sb.cell_start[k] = run;
 #pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
-            const int i = i0 + u * SP_BIN_THREADS, ii = i < n ? i : i0;
-            v[u] = boxes[ii];
-            a[u] = areas[ii];
-            c[u] = CLS ? cls[ii] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < SP_BIN_UNROLL; ++u) {
-            const int i = i0 + u * SP_BIN_THREADS;
-            if (i < n) {
-                const int p = atomicAdd(&s_hist[key_of(v[u], c[u])], 1);   // order inside a cell is irrelevant to the result
-                sb.cbox[p] = v[u];
-                sb.carea[p] = a[u];
-                sb.cpos[p] = i;
-                if (CLS) sb.ccls[p] = c[u];
+            for (int c = 0; c < SP_CLUSTER; ++c) {
+                *cluster.map_shared_rank(s_cur + k, c) = run;
+                run += hc[c];
             }
+        }
+        if (crank == 0 && tid == 0) sb.cell_start[NC] = n;
+    }
+    cluster.sync();                                // cursors ready; nobody reads s_hist remotely after this point
+    // ---- scatter my boxes (re-read: L1/L2 hits; keeping them in registers across the exchange spills)
+#pragma unroll
+    for (int u = 0; u < SP_BIN_ITEMS; ++u) {
+        const int i = first + u * STEP;
+        if (i < n) {
+            const int p = atomicAdd(&s_cur[key[u]], 1);        // order inside a cell is irrelevant to the result
+            sb.cbox[p] = boxes[i];
+            sb.carea[p] = areas[i];
+            sb.cpos[p] = i;
+            if (CLS) sb.ccls[p] = cls[i];
         }
     }
 }
@@ -890,19 +965,14 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *buf = s_buf[warp];
     int *rs = s_rs[warp], *ri = s_ri[warp];
-    int cnt = 0;                                   // warp-uniform
-    auto flush = [&]() {
-        unsigned base = 0u;
-        if (lane == 0) base = atomicAdd(&sb.hdr->edge_count, (unsigned)cnt);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int k = lane; k < cnt; k += 32)
-            if (base + k < edge_cap) sb.edges[base + k] = buf[k];
-        __syncwarp();
-        cnt = 0;
-    };
+    int cnt = 0;                                   // warp-uniform: predecessors of the current box found so far
     const int G = h.G;                             // <= 64
     for (int b = blockIdx.x * SP_PAIR_WARPS + warp; b < n; b += gridDim.x * SP_PAIR_WARPS) {
-        if (b == 0) continue;                      // nothing precedes the first box
+        if (b == 0) {                              // nothing precedes the first box
+            if (lane == 0) sb.seg[0] = make_int2(0, 0);
+            if (lane < SP_INLINE) reinterpret_cast<unsigned short *>(sb.inl)[lane] = 0xffffu;
+            continue;
+        }
         const float4 bb = boxes[b];
         const float ab = areas[b];
         const int cbk = CLS ? cls[b] : 0;
@@ -936,43 +1006,91 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
         }
         __syncwarp();
         int r = 0;                                 // this lane's current row (monotone in t)
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            bool hit = false;
-            int a = 0;
-            if (t < total) {
-                while (t >= ri[r]) ++r;
-                const int k = rs[r] + (t - (r ? ri[r - 1] : 0));
-                a = sb.cpos[k];
-                if (a < b && (!CLS || sb.ccls[k] == cbk)) hit = iou_ge(sb.cbox[k], sb.carea[k], bb, ab, thresh);
+        for (int t0 = 0; t0 < total; t0 += 32 * SP_PAIR_UNROLL) {
+            // SP_PAIR_UNROLL candidates per lane, every load issued before the first test
+            int a[SP_PAIR_UNROLL], cc[SP_PAIR_UNROLL];
+            float4 cb[SP_PAIR_UNROLL];
+            float ca[SP_PAIR_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SP_PAIR_UNROLL; ++u) {
+                const int t = t0 + 32 * u + lane;
+                a[u] = 0x7fffffff;                 // "not a predecessor"
+                if (t < total) {
+                    while (t >= ri[r]) ++r;
+                    const int k = rs[r] + (t - (r ? ri[r - 1] : 0));
+                    a[u] = sb.cpos[k];
+                    cb[u] = sb.cbox[k];
+                    ca[u] = sb.carea[k];
+                    if (CLS) cc[u] = sb.ccls[k];
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                const int c = __popc(m);
-                if (cnt + c > SP_WARP_BUF) flush();
-                if (hit) buf[cnt + __popc(m & ((1u << lane) - 1u))] = ((unsigned)b << 16) | (unsigned)a;
-                __syncwarp();
-                cnt += c;
+#pragma unroll
+            for (int u = 0; u < SP_PAIR_UNROLL; ++u) {
+                if (t0 + 32 * u >= total) break;   // warp-uniform
+                bool hit = false;
+                if (a[u] < b && (!CLS || cc[u] == cbk)) hit = iou_ge(cb[u], ca[u], bb, ab, thresh);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (hit && slot < SP_WARP_BUF) buf[slot] = (unsigned)a[u];
+                    cnt += __popc(m);
+                }
             }
         }
+        // the box's predecessor list: the first SP_INLINE entries inline (u16, one 32-byte row per box), the rest
+        // in one contiguous segment of `edges`
+        if (cnt > SP_WARP_BUF) {                   // more predecessors than the sparse path budgets for one box
+            if (lane == 0) sb.hdr->bail = 1;
+            cnt = 0;
+        }
+        __syncwarp();
+        if (lane < SP_INLINE)
+            reinterpret_cast<unsigned short *>(sb.inl)[(size_t)b * SP_INLINE + lane] = lane < cnt ? (unsigned short)buf[lane] : (unsigned short)0xffffu;
+        const int over = cnt > SP_INLINE ? cnt - SP_INLINE : 0;
+        unsigned base = 0u;
+        if (lane == 0 && over) base = atomicAdd(&sb.hdr->edge_count, (unsigned)over);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < over; k += 32)
+            if (base + k < edge_cap) sb.edges[base + k] = buf[SP_INLINE + k];
+        if (lane == 0) sb.seg[b] = make_int2((int)base, over);
+        cnt = 0;
+        __syncwarp();
     }
-    if (cnt) flush();
 }
 
-// one cluster of SP_CLUSTER CTAs: fixed point over the edge list, then ordered emission.
-// Every CTA keeps a full copy of the survivor set K (32-bit words) and a private `removed` set R in shared memory
-// and owns 1/SP_CLUSTER of the edges (cached in its shared memory) and of the words.  One round:
-//   edge pass    for each of my edges a->b with a in K: R[b] |= 1                       (local shared atomics)
-//   cluster.sync
-//   word pass    for each of my words: K' = valid & ~(OR of the SP_CLUSTER copies of R) read through DSMEM,
-//                written into every CTA's K; a per-CTA "changed" flag goes to every CTA
-//   cluster.sync
-// until no word changed.  Two hardware cluster barriers per round replace the software grid barrier of the dense
-// cooperative resolve; K never leaves the SMs.
-constexpr int SP_CLUSTER = 8;
-constexpr int SP_WORDS = 2048;             // 32-bit words of K / R (n <= 65535)
+// One cluster of SP_CLUSTER CTAs: the greedy survivor set from the predecessor lists, then ordered emission.
+// Two monotone sets, full copies in every CTA's shared memory:  KF = boxes known kept, DF = boxes known dead.
+//   box b is dead   as soon as one predecessor is in KF,
+//   box b is kept   as soon as all predecessors are in DF          (no predecessors: kept at once).
+// Both rules only ever state final facts, so the sets can be read while other CTAs extend them and the fixed point
+// (every box decided) is the greedy result whatever the interleaving.  Ownership: 32-box word w belongs to CTA
+// w % SP_CLUSTER, one warp per word, lane = box; the warp builds the word's new bits with ballots and stores the
+// updated words into all SP_CLUSTER copies through DSMEM.  One hardware cluster barrier per round (termination is
+// only tested every SP_CHECK_EVERY rounds); a box costs work only while it is undecided, and its inline
+// predecessor row sits in the owner's shared memory (one coalesced 32-byte load per box).
+constexpr int SP_WORDS = 2048;             // 32-bit words of KF / DF (n <= 65535)
+constexpr int SP_RES_ITEMS = SP_WORDS / SP_CLUSTER / (SP_RESOLVE_THREADS / 32);       // words per warp: 8
+constexpr int SP_CACHE_ITEMS = 4;          // items whose inline rows are cached in shared memory (32 KB each)
+constexpr int SP_CHECK_EVERY = 4;
+constexpr int SP_OV_CACHE = 16384;         // u16 overflow entries cached per resolve CTA (32 KB)
 
-__global__ void __cluster_dims__(SP_CLUSTER, 1, 1) __launch_bounds__(SP_RESOLVE_THREADS)
+// Branch-free scan of 8 inline entries: the sentinel 0xffff addresses bit 31 of word 2047 (box 65535 does not
+// exist), which is kept clear in KF and set in DF, so an empty slot reads as "dead predecessor".
+__device__ __forceinline__ void sp_scan8(const unsigned *KF, const unsigned *DF, uint4 v, unsigned &anyK, unsigned &anyN)
+{
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned a = (w[q] >> (16 * h)) & 0xffffu;
+            anyK |= KF[a >> 5] >> (a & 31u);
+            anyN |= ~DF[a >> 5] >> (a & 31u);
+        }
+    }
+}
+
+__global__ void __cluster_dims__(SP_CLUSTER, 1, 1) __launch_bounds__(SP_RESOLVE_THREADS, 1)
 nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, unsigned edge_cap, SparseBufs sb,
                           int64_t *__restrict__ keep64, int *__restrict__ keep32, int *__restrict__ num_keep)
 {
@@ -980,65 +1098,134 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_wsum[SP_RESOLVE_THREADS / 32];
+    __shared__ unsigned s_used;
     if (sb.hdr->bail) return;                      // uniform over the cluster: nobody is left at a barrier
-    const unsigned E = sb.hdr->edge_count;
-    if (E > edge_cap) return;                      // status stays 0: dense path
+    if (sb.hdr->edge_count > edge_cap) return;     // status stays 0: dense path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned crank = cluster.block_rank();
-    unsigned *K = reinterpret_cast<unsigned *>(s_raw);          // [SP_WORDS]
-    unsigned *R = K + SP_WORDS;                                 // [SP_WORDS]
-    int *flags = reinterpret_cast<int *>(R + SP_WORDS);         // [2][SP_CLUSTER] (+ padding)
-    unsigned *ecache = reinterpret_cast<unsigned *>(flags + 32);// [SP_SMEM_EDGES]
+    const int crank = (int)cluster.block_rank();
+    unsigned *KF = reinterpret_cast<unsigned *>(s_raw);         // [SP_WORDS]
+    unsigned *DF = KF + SP_WORDS;                               // [SP_WORDS]
+    int *flags = reinterpret_cast<int *>(DF + SP_WORDS);        // [SP_CLUSTER] (+ padding)
+    unsigned short *ov = reinterpret_cast<unsigned short *>(flags + 32);          // [SP_OV_CACHE] overflow entries
+    uint4 *rows = reinterpret_cast<uint4 *>(ov + SP_OV_CACHE);  // [cache items][SP_RESOLVE_THREADS][2]
     const int W32 = (n + 31) >> 5;
-    const unsigned per = (E + SP_CLUSTER - 1) / SP_CLUSTER;
-    const unsigned e0 = min(E, crank * per), e1 = min(E, e0 + per);
-    const unsigned mine = e1 - e0, Ec = mine < (unsigned)SP_SMEM_EDGES ? mine : (unsigned)SP_SMEM_EDGES;
-    const unsigned *my_edges = sb.edges + e0;
-    for (unsigned e = tid; e < Ec; e += SP_RESOLVE_THREADS) ecache[e] = my_edges[e];
-    auto valid_word = [&](int w) -> unsigned {
-        const int nb = n - w * 32;
-        return nb >= 32 ? 0xffffffffu : (nb > 0 ? ((1u << nb) - 1u) : 0u);
-    };
-    for (int w = tid; w < SP_WORDS; w += SP_RESOLVE_THREADS) { K[w] = valid_word(w); R[w] = 0u; }
+    const int n_items = (W32 + SP_CLUSTER * 32 - 1) / (SP_CLUSTER * 32);          // words per warp actually used
+    for (int w = tid; w < SP_WORDS; w += SP_RESOLVE_THREADS) { KF[w] = 0u; DF[w] = w == SP_WORDS - 1 ? 0x80000000u : 0u; }
     if (tid < 32) flags[tid] = 0;
-    const int wper = (W32 + SP_CLUSTER - 1) / SP_CLUSTER;       // <= 256
-    const int w0 = min(W32, (int)crank * wper), w1 = min(W32, w0 + wper);
-    cluster.sync();                                // every CTA's shared memory is initialised before remote access
-    bool converged = false;
-    for (int round = 0; round < SP_MAX_ROUNDS; ++round) {
-        for (unsigned e = tid; e < mine; e += SP_RESOLVE_THREADS) {
-            const unsigned ed = e < Ec ? ecache[e] : __ldg(my_edges + e);
-            const unsigned a = ed & 0xffffu, b = ed >> 16;
-            if ((K[a >> 5] >> (a & 31u)) & 1u) atomicOr(R + (b >> 5), 1u << (b & 31u));
+    if (tid == 0) s_used = 0u;
+    __syncthreads();
+    // ---- my boxes: word w = (warp + 32*u) * SP_CLUSTER + crank, box = 32*w + lane
+    unsigned undecided = 0u;                       // bit u: my box of item u is not decided yet
+    // rest of the predecessor list beyond the inline row: count << 24 | offset (bit 23 set: offset into the
+    // shared-memory cache `ov`, else into sb.edges); 0 = none.  Lists are copied by the whole warp, coalesced.
+    unsigned p_over[SP_RES_ITEMS];
+#pragma unroll
+    for (int u = 0; u < SP_RES_ITEMS; ++u) {
+        const int w = (warp + 32 * u) * SP_CLUSTER + crank;
+        const int b = 32 * w + lane;
+        int2 sg = make_int2(0, 0);
+        if (u < n_items && w < W32 && b < n) {
+            undecided |= 1u << u;
+            if (u < SP_CACHE_ITEMS) {
+                rows[(u * SP_RESOLVE_THREADS + tid) * 2] = __ldg(sb.inl + 2 * (size_t)b);
+                rows[(u * SP_RESOLVE_THREADS + tid) * 2 + 1] = __ldg(sb.inl + 2 * (size_t)b + 1);
+            }
+            sg = __ldg(sb.seg + b);
         }
-        cluster.sync();
-        int changed = 0;
-        if (tid < w1 - w0) {
-            const int w = w0 + tid;
-            unsigned r = 0u;
-#pragma unroll
-            for (int c = 0; c < SP_CLUSTER; ++c) r |= *cluster.map_shared_rank(R + w, c);
-            const unsigned kn = valid_word(w) & ~r;
-            changed = kn != K[w];
-            if (changed) {
-#pragma unroll
-                for (int c = 0; c < SP_CLUSTER; ++c) *cluster.map_shared_rank(K + w, c) = kn;
+        p_over[u] = sg.y > 0 ? ((unsigned)sg.y << 24) | (unsigned)sg.x : 0u;        // sg.x < 16 n <= 2^20
+        unsigned m = __ballot_sync(0xffffffffu, sg.y > 0);
+        while (m) {
+            const int L = __ffs(m) - 1;
+            m &= m - 1u;
+            const int st = __shfl_sync(0xffffffffu, sg.x, L), cn = __shfl_sync(0xffffffffu, sg.y, L);
+            unsigned off = 0u;
+            if (lane == 0) off = atomicAdd(&s_used, (unsigned)cn);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + (unsigned)cn <= (unsigned)SP_OV_CACHE) {
+                for (int k = lane; k < cn; k += 32) ov[off + k] = (unsigned short)__ldg(sb.edges + st + k);
+                if (lane == L) p_over[u] = ((unsigned)cn << 24) | 0x800000u | off;
             }
         }
-        const int any = __syncthreads_or(changed);
-        if (tid < SP_CLUSTER) *cluster.map_shared_rank(flags + (round & 1) * SP_CLUSTER + crank, tid) = any;
-        cluster.sync();
-        int glob = 0;
-#pragma unroll
-        for (int c = 0; c < SP_CLUSTER; ++c) glob |= flags[(round & 1) * SP_CLUSTER + c];
-        for (int w = tid; w < W32; w += SP_RESOLVE_THREADS) R[w] = 0u;
-        __syncthreads();
-        if (!glob) { converged = true; break; }    // uniform over the cluster
     }
-    if (!converged) return;
-    // emission in visiting order: every CTA scans the per-word popcounts itself (2 words per thread) and writes
-    // the survivors of the positions it owns
-    const int c0 = __popc(K[2 * tid]), c1 = __popc(K[2 * tid + 1]);
+    cluster.sync();                                // every CTA's shared memory is initialised before remote access
+    bool done = false;
+    for (int round = 0; round < SP_MAX_ROUNDS; ++round) {
+#pragma unroll
+        for (int u = 0; u < SP_RES_ITEMS; ++u) {
+            if (u >= n_items) break;
+            const int w = (warp + 32 * u) * SP_CLUSTER + crank;
+            if (w >= W32) break;                   // warp-uniform
+            if (__ballot_sync(0xffffffffu, (undecided >> u) & 1u) == 0u) continue;
+            bool dead = false, kept = false, need_rest = false, all_dead_reg = true;
+            if ((undecided >> u) & 1u) {
+                const int b = 32 * w + lane;
+                uint4 r0, r1;
+                if (u < SP_CACHE_ITEMS) {
+                    r0 = rows[(u * SP_RESOLVE_THREADS + tid) * 2];
+                    r1 = rows[(u * SP_RESOLVE_THREADS + tid) * 2 + 1];
+                } else {
+                    r0 = __ldg(sb.inl + 2 * (size_t)b);
+                    r1 = __ldg(sb.inl + 2 * (size_t)b + 1);
+                }
+                unsigned anyK = 0u, anyN = 0u;
+                sp_scan8(KF, DF, r0, anyK, anyN);
+                sp_scan8(KF, DF, r1, anyK, anyN);
+                dead = anyK & 1u;
+                const bool all_dead = !(anyN & 1u);
+                all_dead_reg = all_dead;
+                need_rest = !dead && p_over[u] != 0u;
+                kept = !dead && all_dead && !need_rest;
+                if (dead || kept) undecided &= ~(1u << u);
+            }
+            // the rest of a long list: scanned by the whole warp, 32 entries per step
+            unsigned m = __ballot_sync(0xffffffffu, need_rest);
+            while (m) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1u;
+                const unsigned po = __shfl_sync(0xffffffffu, p_over[u], L);
+                const int cn = (int)(po >> 24);
+                const unsigned off = po & 0x7fffffu;
+                bool hitK = false, notD = false;
+                for (int k = lane; k < cn; k += 32) {
+                    const unsigned a = (po & 0x800000u) ? (unsigned)ov[off + k] : __ldg(sb.edges + off + k);
+                    const unsigned bit = 1u << (a & 31u);
+                    if (KF[a >> 5] & bit) hitK = true;
+                    else if (!(DF[a >> 5] & bit)) notD = true;
+                }
+                const bool anyK = __any_sync(0xffffffffu, hitK), anyN = __any_sync(0xffffffffu, notD);
+                if (lane == L) {
+                    dead = anyK;
+                    kept = !anyK && all_dead_reg && !anyN;
+                    if (dead || kept) undecided &= ~(1u << u);
+                }
+            }
+            const unsigned kb = __ballot_sync(0xffffffffu, kept), db = __ballot_sync(0xffffffffu, dead);
+            if (kb | db) {                         // the warp owns this word: plain stores of the updated words
+                const unsigned nk = KF[w] | kb, nd = DF[w] | db;
+                if (lane < SP_CLUSTER) {
+                    *cluster.map_shared_rank(KF + w, lane) = nk;
+                    *cluster.map_shared_rank(DF + w, lane) = nd;
+                }
+            }
+        }
+        const bool check = (round % SP_CHECK_EVERY) == SP_CHECK_EVERY - 1;
+        if (check) {
+            const int open = __syncthreads_or(undecided != 0u);
+            if (tid < SP_CLUSTER) *cluster.map_shared_rank(flags + crank, tid) = open;
+        }
+        cluster.sync();
+        if (check) {
+            int glob = 0;
+#pragma unroll
+            for (int c = 0; c < SP_CLUSTER; ++c) glob |= flags[c];
+            if (!glob) { done = true; break; }     // uniform over the cluster
+            cluster.sync();                        // flags are rewritten only after everybody has read them
+        }
+    }
+    if (!done) return;
+    // ---- emission in visiting order: every CTA scans the per-word popcounts itself (2 words per thread) and
+    // writes the survivors of the positions it owns
+    const int c0 = __popc(KF[2 * tid]), c1 = __popc(KF[2 * tid + 1]);
     const int mine2 = c0 + c1;
     int incl = mine2;
     for (int o = 1; o < 32; o <<= 1) {
@@ -1056,13 +1243,13 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
         s_wsum[lane] = wi - w;
     }
     __syncthreads();
-    int *pre = reinterpret_cast<int *>(R);         // R is free now
+    int *pre = reinterpret_cast<int *>(DF);        // DF is free now
     const int excl = s_wsum[warp] + incl - mine2;
     pre[2 * tid] = excl;
     pre[2 * tid + 1] = excl + c0;
     __syncthreads();
-    for (int pos = (int)crank * SP_RESOLVE_THREADS + tid; pos < n; pos += SP_CLUSTER * SP_RESOLVE_THREADS) {
-        const unsigned kw = K[pos >> 5];
+    for (int pos = crank * SP_RESOLVE_THREADS + tid; pos < n; pos += SP_CLUSTER * SP_RESOLVE_THREADS) {
+        const unsigned kw = KF[pos >> 5];
         if ((kw >> (pos & 31)) & 1u) {
             const int slot = pre[pos >> 5] + __popc(kw & ((1u << (pos & 31)) - 1u));
             if (slot < max_keep) {
@@ -1094,15 +1281,17 @@ static int launch_sparse(const float4 *boxes, const float *areas, const int *cls
     const float t = thresh > 1.f ? 1.f : thresh;
     const float ct = (1.f - t) * (t < 0.5f ? 0.5f / t : 1.f) * 1.01f;
     const unsigned edge_cap = (unsigned)SP_EDGES_PER_BOX * (unsigned)n;
-    if (cls) nms_bin_kernel<true><<<1, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
-    else nms_bin_kernel<false><<<1, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
+    if (cls) nms_bin_kernel<true><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
+    else nms_bin_kernel<false><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
     SLN_LAUNCH_OK("nms_bin_kernel");
     int ctas = cdiv(n, SP_PAIR_WARPS);
     if (ctas > 8 * sm_count()) ctas = 8 * sm_count();
     if (cls) nms_pairs_kernel<true><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
     else nms_pairs_kernel<false><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
     SLN_LAUNCH_OK("nms_pairs_kernel");
-    const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32 + SP_SMEM_EDGES);
+    int items = cdiv(cdiv(n, 32), SP_CLUSTER * 32);
+    if (items > SP_CACHE_ITEMS) items = SP_CACHE_ITEMS;
+    const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32) + 2 * SP_OV_CACHE + (size_t)items * SP_RESOLVE_THREADS * 32;
     SLN_CUDA_OK(cudaFuncSetAttribute(nms_sparse_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_sparse_resolve_kernel<<<SP_CLUSTER, SP_RESOLVE_THREADS, smem, st>>>(order, n, max_keep, edge_cap, sb, keep64, keep32, num_keep);
     SLN_LAUNCH_OK("nms_sparse_resolve_kernel");
@@ -1182,8 +1371,8 @@ static int launch_mask(const float4 *boxes, const float *areas, const int *cls, 
 {
     const int W = cdiv(n_max, 64);
     const long long n_tiles = (long long)W * (W + 1) / 2;
-    const long long n_blocks = (n_tiles + MASK_GROUPS - 1) / MASK_GROUPS;
-    SLN_REQUIRE(n_blocks < (1ll << 31), SLN_ERR_ARG, "nms: n=%d too large", n_max);
+    long long n_blocks = (n_tiles + MASK_GROUPS - 1) / MASK_GROUPS;
+    if (n_blocks > 16LL * sm_count()) n_blocks = 16LL * sm_count();
     if (cls)
         nms_mask_kernel<true><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip);
     else

@@ -292,7 +292,7 @@ def _nms_both_paths(dets, thr, cls=None, max_keep=0):
 @pytest.mark.parametrize("kind,n,thr,sparse", [
     ("rpn", 65, 0.7, True), ("rpn", 1000, 0.7, True), ("rpn", 12000, 0.7, True), ("uniform", 12000, 0.7, True),
     ("rpn", 6000, 0.5, None), ("rpn", 6000, 0.3, None), ("uniform", 6000, 0.3, True), ("rpn", 4000, 0.05, None),
-    ("uniform", 4000, 0.05, None), ("rpn", 3000, 0.95, True), ("rpn", 3000, 1.0, True), ("rpn", 40000, 0.7, True),
+    ("uniform", 4000, 0.05, None), ("rpn", 3000, 0.95, True), ("rpn", 3000, 1.0, True), ("rpn", 40000, 0.7, None), ("uniform", 40000, 0.7, True),
     ("uniform", 65535, 0.6, True)])
 def test_nms_sparse_path_equals_dense_and_oracle(kind, n, thr, sparse):
     """The binned pipeline must take the inputs marked True (path == 1) -- the others may exceed its edge budget and
