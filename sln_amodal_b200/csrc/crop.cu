@@ -626,6 +626,277 @@ crop_bwd_nhwc_kernel(const float *__restrict__ grads, const Tap *__restrict__ ta
 }
 
 // ===========================================================================
+// backward, NHWC, tile-owner form (default)
+// ===========================================================================
+// warp  = one 4x4 pixel tile of one image and level (BWD_TILE_WARPS independent warps per CTA, no barriers)
+// lanes = channel vectors (NV per lane); the tile's accumulators live in the warp's slice of shared memory
+//         ([16 pixels][32*NV vectors]: consecutive lanes = consecutive vectors, conflict-free)
+// The warp walks its supertile's ROI list in original box order; for every ROI whose window meets the tile it
+// takes the ROI's tap tables (lane k = tap k of each axis), ballots the sample rows / columns that touch the tile,
+// and visits those samples in (y, x) order.  One visit = one coalesced load of the sample's gradient vector (all
+// loads of a sample row are issued before the first use) + up to four read-modify-writes of the warp's own shared
+// memory, in the reference's tap order TL, TR, BL, BR.  Per destination pixel the summation order is therefore
+// (ROI, y, x, tap) -- the reference's serial order (crop_and_resize.c:190-250) -- without atomics; every pixel is
+// written exactly once at the end (zeros included: no memset).
+// Versus the strip form above: the search "which samples touch me" is paid once per (ROI, 16 pixels) instead of
+// once per (ROI, 4 pixels), and a visit carries no per-pixel switch -- 2.5x fewer warp instructions per byte.
+constexpr int BWD_TILE = 4;                 // tile side in pixels
+#ifndef SLN_BWD_TILE_WARPS
+#define SLN_BWD_TILE_WARPS 2
+#endif
+#ifndef SLN_BWD_BATCH
+#define SLN_BWD_BATCH 8
+#endif
+constexpr int BWD_TILE_WARPS = SLN_BWD_TILE_WARPS;   // warps (tiles) per CTA: tiles side by side along x
+constexpr int BWD_BATCH = SLN_BWD_BATCH;             // samples whose gradient loads are issued together
+
+// one sample's contribution to the warp's tile (see the kernel comment)
+template <int VEC, int NV, bool EXACT>
+__device__ __forceinline__ void bwd_tile_visit(typename VecT<VEC>::type *acc, const typename VecT<VEC>::type (&gv)[NV],
+                                               int ylo, float yl, int xlo, float xl, int y0, int y1, int x0, int x1)
+{
+    using V = typename VecT<VEC>::type;
+    constexpr int T = BWD_TILE, ROWV = 32 * NV;
+    const int yhi = ylo + (yl != 0.f), xhi = xlo + (xl != 0.f);
+    const float wt = __fsub_rn(1.f, yl), wb = yl, wl = __fsub_rn(1.f, xl), wr = xl;
+    const bool top_in = ylo >= y0 && ylo <= y1, bot_in = yhi >= y0 && yhi <= y1;
+    const bool l_in = xlo >= x0 && xlo <= x1, r_in = xhi >= x0 && xhi <= x1;
+    const int rt = (ylo - y0) * T, rb = (yhi - y0) * T, cl = xlo - x0, cr = xhi - x0;
+    if (EXACT) {
+        // reference order TL, TR, BL, BR, one read-modify-write after the other: taps coincide when the sample
+        // position is integral on an axis, and the reference still adds their "0 * g" terms
+#define SLN_TAP(IN, POFF, WY, WX)                                                                  \
+    if (IN) {                                                                                     \
+        _Pragma("unroll") for (int j = 0; j < NV; ++j) {                                          \
+            V a_ = acc[(POFF) * ROWV + 32 * j];                                                   \
+            a_ = accum<true>(a_, gv[j], (WY), (WX), 0.f);                                          \
+            acc[(POFF) * ROWV + 32 * j] = a_;                                                     \
+        }                                                                                         \
+    }
+        SLN_TAP(top_in && l_in, rt + cl, wt, wl)
+        SLN_TAP(top_in && r_in, rt + cr, wt, wr)
+        SLN_TAP(bot_in && l_in, rb + cl, wb, wl)
+        SLN_TAP(bot_in && r_in, rb + cr, wb, wr)
+#undef SLN_TAP
+    } else {
+        // zero-weight taps are skipped, so the (up to) four destinations are distinct pixels: all loads, then all
+        // fused multiply-adds, then all stores
+        const bool t0 = top_in && l_in, t1 = top_in && r_in && wr != 0.f;
+        const bool t2 = bot_in && l_in && wb != 0.f, t3 = bot_in && r_in && wb != 0.f && wr != 0.f;
+        const float w0 = __fmul_rn(wt, wl), w1 = __fmul_rn(wt, wr), w2 = __fmul_rn(wb, wl), w3 = __fmul_rn(wb, wr);
+        const V zero = make_splat(0.f, (V *)nullptr);
+        V a0[NV], a1[NV], a2[NV], a3[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            a0[j] = t0 ? acc[(rt + cl) * ROWV + 32 * j] : zero;
+            a1[j] = t1 ? acc[(rt + cr) * ROWV + 32 * j] : zero;
+            a2[j] = t2 ? acc[(rb + cl) * ROWV + 32 * j] : zero;
+            a3[j] = t3 ? acc[(rb + cr) * ROWV + 32 * j] : zero;
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            a0[j] = accum<false>(a0[j], gv[j], 0.f, 0.f, w0);
+            a1[j] = accum<false>(a1[j], gv[j], 0.f, 0.f, w1);
+            a2[j] = accum<false>(a2[j], gv[j], 0.f, 0.f, w2);
+            a3[j] = accum<false>(a3[j], gv[j], 0.f, 0.f, w3);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (t0) acc[(rt + cl) * ROWV + 32 * j] = a0[j];
+            if (t1) acc[(rt + cr) * ROWV + 32 * j] = a1[j];
+            if (t2) acc[(rb + cl) * ROWV + 32 * j] = a2[j];
+            if (t3) acc[(rb + cr) * ROWV + 32 * j] = a3[j];
+        }
+    }
+}
+
+template <int VEC, int NV, bool EXACT>
+__global__ void __launch_bounds__(32 * BWD_TILE_WARPS)
+crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ taps,
+                     const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
+                     const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
+                     BwdTileBases TB, int C, int ph, int pw)
+{
+    using V = typename VecT<VEC>::type;
+    extern __shared__ __align__(16) unsigned char s_bwd_raw[];
+    constexpr int T = BWD_TILE, NPX = T * T, ROWV = 32 * NV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    V *acc = reinterpret_cast<V *>(s_bwd_raw) + (size_t)warp * NPX * ROWV + lane;   // acc[p * ROWV + 32 * j]
+
+    int l = TB.lvl[0];
+#pragma unroll
+    for (int k = 1; k < BWD_MAX_LEVELS; ++k)
+        if (k < TB.n_levels && (int)blockIdx.x >= TB.base[k]) l = TB.lvl[k];
+    const BwdLevel L = lv_table[l];
+    const int t = blockIdx.x - L.tile_base;
+    const int q1 = fast_div(t, L.tiles_x, L.rcp_tiles_x);
+    const int tx_i = t - q1 * L.tiles_x;
+    const int b = fast_div(q1, L.tiles_y, L.rcp_tiles_y);
+    const int ty_i = q1 - b * L.tiles_y;
+    const int H = L.H, W = L.W;
+    const int y0 = ty_i * T, x0 = (tx_i * BWD_TILE_WARPS + warp) * T;
+    if (y0 >= H || x0 >= W) return;            // no barriers in this kernel
+    const int y1 = min(y0 + T, H) - 1, x1 = min(x0 + T, W) - 1;
+    const int CV = C / VEC;
+    const int cvbase = blockIdx.y * ROWV + lane;
+    bool ok[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) ok[j] = cvbase + 32 * j < CV;
+
+    const V zero = make_splat(0.f, (V *)nullptr);
+    bool touched = false;                      // warp-uniform: accumulators initialised and in use
+
+    const int st = L.st_base + (b * L.sg.ny + (y0 >> L.sg_shift)) * L.sg.nx + (x0 >> L.sg_shift);
+    const int n_list = st_count[st];
+    const ListEntry *__restrict__ list = entries + (n_list ? st_off[st] : 0);
+    const V *__restrict__ g = reinterpret_cast<const V *>(grads) + cvbase;
+    const int S = ph * pw;
+    const bool small = ph <= 32 && pw <= 32;   // one tap per lane and axis: the pipelined path
+
+    for (int base = 0; base < n_list; base += 32) {
+        const int li = base + lane;
+        int my_roi = -1;
+        bool take = false;
+        if (li < n_list) {
+            const ListEntry e = list[li];
+            my_roi = e.roi;
+            take = !(e.win.y1 < y0 || e.win.y0 > y1 || e.win.x1 < x0 || e.win.x0 > x1);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, take);
+        if (!todo) continue;
+        if (small) {
+            // ---- taps of the next ROI are in flight while the current one is accumulated
+            Tap ty_n, tx_n;
+            auto fetch_taps = [&](int r) {
+                const Tap *__restrict__ tp = taps + (size_t)r * (ph + pw);
+                ty_n.lo = INVALID_TAP; ty_n.lerp = 0.f; tx_n.lo = INVALID_TAP; tx_n.lerp = 0.f;
+                if (lane < ph) ty_n = ld_tap(tp + lane);
+                if (lane < pw) tx_n = ld_tap(tp + ph + lane);
+            };
+            int r_n = __shfl_sync(0xffffffffu, my_roi, __ffs(todo) - 1);
+            todo &= todo - 1;
+            fetch_taps(r_n);
+            while (r_n >= 0) {
+                const int r = r_n;
+                const Tap ty = ty_n, tx = tx_n;
+                r_n = -1;
+                if (todo) {
+                    r_n = __shfl_sync(0xffffffffu, my_roi, __ffs(todo) - 1);
+                    todo &= todo - 1;
+                    fetch_taps(r_n);
+                }
+                const unsigned ym = __ballot_sync(0xffffffffu, ty.lo != INVALID_TAP && ty.lo <= y1 && ty.lo + (ty.lerp != 0.f) >= y0);
+                const unsigned xm = __ballot_sync(0xffffffffu, tx.lo != INVALID_TAP && tx.lo <= x1 && tx.lo + (tx.lerp != 0.f) >= x0);
+                if (!ym || !xm) continue;
+                if (!touched) {                // first contribution: clear the accumulators
+#pragma unroll
+                    for (int p = 0; p < NPX; ++p)
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) acc[p * ROWV + 32 * j] = zero;
+                    touched = true;
+                }
+                const V *gr = g + (size_t)r * S * CV;
+                // samples in (y, x) order, BWD_BATCH at a time: every gradient load of a batch is issued before
+                // the first accumulation
+                unsigned yrem = ym, xrem = xm;
+                while (yrem) {
+                    int sb[BWD_BATCH];         // yb << 8 | xb, -1: none
+                    V gv[BWD_BATCH][NV];
+#pragma unroll
+                    for (int u = 0; u < BWD_BATCH; ++u) {
+                        sb[u] = -1;
+                        if (yrem) {
+                            const int yb = __ffs(yrem) - 1, xb = __ffs(xrem) - 1;
+                            sb[u] = (yb << 8) | xb;
+                            xrem &= xrem - 1;
+                            if (!xrem) { yrem &= yrem - 1; xrem = xm; }
+#pragma unroll
+                            for (int j = 0; j < NV; ++j) {
+                                gv[u][j] = zero;
+                                if (ok[j]) gv[u][j] = ldg_vec(gr + (size_t)(yb * pw + xb) * CV + 32 * j);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < BWD_BATCH; ++u) {
+                        if (sb[u] < 0) break;  // warp-uniform
+                        const int yb = sb[u] >> 8, xb = sb[u] & 0xff;
+                        const int ylo = __shfl_sync(0xffffffffu, ty.lo, yb), xlo = __shfl_sync(0xffffffffu, tx.lo, xb);
+                        const float yl = __shfl_sync(0xffffffffu, ty.lerp, yb), xl = __shfl_sync(0xffffffffu, tx.lerp, xb);
+                        bwd_tile_visit<VEC, NV, EXACT>(acc, gv[u], ylo, yl, xlo, xl, y0, y1, x0, x1);
+                    }
+                }
+            }
+        } else {
+            // ---- crops larger than 32 samples per side: tap tables in chunks of 32, one sample at a time
+            while (todo) {
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int r = __shfl_sync(0xffffffffu, my_roi, bit);
+                const Tap *__restrict__ tp = taps + (size_t)r * (ph + pw);
+                const V *gr = g + (size_t)r * S * CV;
+                for (int ky0 = 0; ky0 < ph; ky0 += 32) {
+                    Tap ty;
+                    ty.lo = INVALID_TAP; ty.lerp = 0.f;
+                    if (ky0 + lane < ph) ty = ld_tap(tp + ky0 + lane);
+                    unsigned ym = __ballot_sync(0xffffffffu, ty.lo != INVALID_TAP && ty.lo <= y1 && ty.lo + (ty.lerp != 0.f) >= y0);
+                    while (ym) {
+                        const int yb = __ffs(ym) - 1;
+                        ym &= ym - 1;
+                        const int ylo = __shfl_sync(0xffffffffu, ty.lo, yb);
+                        const float yl = __shfl_sync(0xffffffffu, ty.lerp, yb);
+                        for (int kx0 = 0; kx0 < pw; kx0 += 32) {
+                            Tap tx;
+                            tx.lo = INVALID_TAP; tx.lerp = 0.f;
+                            if (kx0 + lane < pw) tx = ld_tap(tp + ph + kx0 + lane);
+                            unsigned xm = __ballot_sync(0xffffffffu, tx.lo != INVALID_TAP && tx.lo <= x1 && tx.lo + (tx.lerp != 0.f) >= x0);
+                            if (xm && !touched) {
+#pragma unroll
+                                for (int p = 0; p < NPX; ++p)
+#pragma unroll
+                                    for (int j = 0; j < NV; ++j) acc[p * ROWV + 32 * j] = zero;
+                                touched = true;
+                            }
+                            while (xm) {
+                                const int xb = __ffs(xm) - 1;
+                                xm &= xm - 1;
+                                const int xlo = __shfl_sync(0xffffffffu, tx.lo, xb);
+                                const float xl = __shfl_sync(0xffffffffu, tx.lerp, xb);
+                                V gv[NV];
+#pragma unroll
+                                for (int j = 0; j < NV; ++j) {
+                                    gv[j] = zero;
+                                    if (ok[j]) gv[j] = ldg_vec(gr + (size_t)((ky0 + yb) * pw + kx0 + xb) * CV + 32 * j);
+                                }
+                                bwd_tile_visit<VEC, NV, EXACT>(acc, gv, ylo, yl, xlo, xl, y0, y1, x0, x1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- write every pixel of the tile exactly once (zeros included)
+    V *__restrict__ o = reinterpret_cast<V *>(L.out) + (((size_t)b * H + y0) * W + x0) * CV + cvbase;
+#pragma unroll
+    for (int py = 0; py < T; ++py) {
+        if (y0 + py > y1) break;
+#pragma unroll
+        for (int px = 0; px < T; ++px) {
+            if (x0 + px > x1) break;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if (!ok[j]) continue;
+                V v = zero;
+                if (touched) v = acc[(py * T + px) * ROWV + 32 * j];
+                __stcs(o + ((size_t)py * W + px) * CV + 32 * j, v);
+            }
+        }
+    }
+}
+
+// ===========================================================================
 // layout converters: per image, [C][HW] <-> [HW][C]
 // ===========================================================================
 __global__ void __launch_bounds__(256)
@@ -734,6 +1005,44 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
            align_up(sizeof(ListEntry) * (size_t)N * BWD_MAX_ST, 256);
 }
 
+// Which gather kernel serves a call (A/B on B200, 8 x 1000 ROIs, C = 256, all four levels, ms per call incl. prep):
+//   7x7    strip 0.382   tile 0.352        14x14   strip 0.793   tile 0.874
+// A tile visit pays shared-memory read-modify-writes the strip form keeps in registers, which costs more than the
+// cheaper search saves once a tile sees ~9+ samples of a ROI (14x14 crops), so: tile form for crops of at most
+// BWD_TILE_MAX_SAMPLES samples, strip form above.  SLN_BWD_IMPL forces one of them (0 strip, 1 tile) for A/B runs.
+#ifndef SLN_BWD_IMPL
+#define SLN_BWD_IMPL 2
+#endif
+constexpr int BWD_TILE_MAX_SAMPLES = 64;
+static bool bwd_use_tile(int ph, int pw)
+{
+#if SLN_BWD_IMPL == 2
+    return ph * pw <= BWD_TILE_MAX_SAMPLES;
+#else
+    return SLN_BWD_IMPL == 1;
+#endif
+}
+
+template <int VEC, int NV, bool EXACT>
+static int launch_bwd_tile(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
+                           cudaStream_t st)
+{
+    const int chunks = cdiv(C / VEC, 32 * NV);
+    SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
+    if (tiles == 0) return SLN_OK;
+    BwdTileBases TB{};
+    TB.n_levels = P.n_levels;
+    for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
+    dim3 grid((unsigned)tiles, chunks);
+    const size_t smem = (size_t)BWD_TILE_WARPS * BWD_TILE * BWD_TILE * 32 * NV * sizeof(float) * VEC;
+    auto kern = crop_bwd_tile_kernel<VEC, NV, EXACT>;
+    SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<grid, 32 * BWD_TILE_WARPS, smem, st>>>(grads, ws.taps, ws.entries, ws.st_off, ws.st_count, ws.lv_table, TB, C, ph, pw);
+    SLN_LAUNCH_OK("crop_bwd_tile_kernel");
+    return SLN_OK;
+}
+
 template <int VEC, int NV, bool EXACT>
 static int launch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
                       cudaStream_t st)
@@ -756,6 +1065,10 @@ static int dispatch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P,
                         cudaStream_t st)
 {
     const int CV = C / VEC;
+    if (bwd_use_tile(ph, pw)) {
+        if (CV > 32) return launch_bwd_tile<VEC, 2, EXACT>(grads, ws, P, tiles, C, ph, pw, st);
+        return launch_bwd_tile<VEC, 1, EXACT>(grads, ws, P, tiles, C, ph, pw, st);
+    }
     // two channel vectors per lane halve the control work per byte, but also the CTA count:
     // only use them when the maps provide enough strips to fill the machine
     if (CV > 32 && tiles >= 6LL * sm_count()) return launch_bwd<VEC, 2, EXACT>(grads, ws, P, tiles, C, ph, pw, st);
@@ -786,8 +1099,13 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         while ((1 << L.sg_shift) < L.sg.side) ++L.sg_shift;
         L.st_base = n_st;
         n_st += B * L.sg.nx * L.sg.ny;
-        L.tiles_x = cdiv(L.W, BWD_TW);
-        L.tiles_y = cdiv(L.H, BWD_ROWS);
+        if (bwd_use_tile(ph, pw)) {
+            L.tiles_x = cdiv(L.W, BWD_TILE_WARPS * BWD_TILE);
+            L.tiles_y = cdiv(L.H, BWD_TILE);
+        } else {
+            L.tiles_x = cdiv(L.W, BWD_TW);
+            L.tiles_y = cdiv(L.H, BWD_ROWS);
+        }
         L.rcp_tiles_x = L.tiles_x ? 1.0f / (float)L.tiles_x : 0.f;
         L.rcp_tiles_y = L.tiles_y ? 1.0f / (float)L.tiles_y : 0.f;
         vec4 = vec4 && aligned16(maps[l]);

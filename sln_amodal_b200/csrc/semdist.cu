@@ -486,7 +486,10 @@ __device__ __forceinline__ int env_backward_row(ColState &c, const ColCtx &k, in
     return val;
 }
 
-constexpr int ENV_AHEAD = 8;     // rows of g fetched per batch (independent loads in flight)
+#ifndef SLN_ENV_AHEAD
+#define SLN_ENV_AHEAD 4
+#endif
+constexpr int ENV_AHEAD = SLN_ENV_AHEAD;     // rows of g fetched per batch (independent loads in flight)
 
 // thread = one column; the warp (32 adjacent columns = one flag segment) walks the rows in lock step
 // (coalesced g reads and output writes), 32-row tile by tile: tiles whose flag word is zero hold only
@@ -570,9 +573,13 @@ edt_cols_envelope_kernel(const unsigned short *__restrict__ g, const unsigned *_
 // With the stack out of the way the output is written exactly once: non-empty tiles by the envelope warps,
 // background tiles by the fill blocks (blockIdx.z == 1) that run beside them -- the bandwidth-bound zero
 // fill overlaps the latency-bound envelope chains.
+#ifndef SLN_EDT_MIRROR
+#define SLN_EDT_MIRROR 3
+#endif
+constexpr int PK_D = SLN_EDT_MIRROR;   // stack entries mirrored in registers
 struct PCol {
     int q, base, ystart;
-    unsigned e0, e1, e2;        // entries q, q-1, q-2 (garbage where the index is < 0)
+    unsigned e[PK_D];           // entries q, q-1, .. q-PK_D+1 (garbage where the index is < 0); e[0] is the top
     bool open;
 };
 
@@ -584,20 +591,22 @@ __device__ __forceinline__ unsigned pk_make(int sidx, int t, int gq) { return (u
 __device__ __forceinline__ void pk_pop(PCol &c, const unsigned *sc, int W)
 {
     --c.q;
-    c.e0 = c.e1;
-    c.e1 = c.e2;
+#pragma unroll
+    for (int i = 0; i + 1 < PK_D; ++i) c.e[i] = c.e[i + 1];
     // plain (L1-cached) accesses on purpose: a sector holds the entries of 8 neighbouring columns, which pop
     // at nearly the same time -- with L2-only loads the kernel is 3.8x slower (2.66 ms vs 0.70 ms, 320 maps).
     // g is read with ld.cs (coherent), never ld.nc, so a thread always sees the entry it wrote over g.
-    if (c.q >= 2) c.e2 = sc[(size_t)(c.q - 2) * W];
+    // The refill is consumed PK_D-1 pops later and reads an entry pushed at least PK_D-1 pushes ago: with a
+    // shallow mirror the load chased the thread's own store through L2 (store -> load round trip per pop).
+    if (c.q >= PK_D - 1) c.e[PK_D - 1] = sc[(size_t)(c.q - (PK_D - 1)) * W];
 }
 
 __device__ __forceinline__ void pk_push(PCol &c, unsigned *sc, int W, unsigned e)
 {
     ++c.q;
-    c.e2 = c.e1;
-    c.e1 = c.e0;
-    c.e0 = e;
+#pragma unroll
+    for (int i = PK_D - 1; i > 0; --i) c.e[i] = c.e[i - 1];
+    c.e[0] = e;
     sc[(size_t)c.q * W] = e;
 }
 
@@ -610,19 +619,23 @@ __device__ __forceinline__ int floor_div_small(int a, int b)
     return q;
 }
 
+#ifdef SLN_EDT_NOINLINE
+__device__ __noinline__ void pk_insert(PCol &c, unsigned *sc, int W, int u, int gq, int limit)
+#else
 __device__ __forceinline__ void pk_insert(PCol &c, unsigned *sc, int W, int u, int gq, int limit)
+#endif
 {
     const int gu2 = gq * gq;
     while (c.q >= c.base) {
-        const int t = pk_t(c.e0);
-        if (env_f(t, pk_s(c.e0), pk_g2(c.e0)) > env_f(t, u, gu2)) pk_pop(c, sc, W);
+        const int t = pk_t(c.e[0]);
+        if (env_f(t, pk_s(c.e[0]), pk_g2(c.e[0])) > env_f(t, u, gu2)) pk_pop(c, sc, W);
         else break;
     }
     if (c.q < c.base) {
         pk_push(c, sc, W, pk_make(u, c.ystart, gq));
     } else {
-        const int st = pk_s(c.e0);
-        const int w = 1 + floor_div_small(u * u - st * st + gu2 - pk_g2(c.e0), 2 * (u - st));
+        const int st = pk_s(c.e[0]);
+        const int w = 1 + floor_div_small(u * u - st * st + gu2 - pk_g2(c.e[0]), 2 * (u - st));
         if (w <= limit) pk_push(c, sc, W, pk_make(u, w, gq));
     }
 }
@@ -655,20 +668,46 @@ edt_cols_envelope_packed_kernel(unsigned *__restrict__ g, const unsigned *__rest
                                   ((unsigned long long)__ballot_sync(FULL, fw1 != 0u) << 32);
     int *__restrict__ oc = out + (size_t)m * H * W + x;
 
-    if (blockIdx.z == 1) {                          // ---- fill role: zero the background tiles of this segment
+    if (blockIdx.z == 1) {                          // ---- fill role: zero the background tiles
+        // warp = tile rows (32 output rows each), walked along x: one store instruction covers four adjacent
+        // segments = 512 contiguous bytes of one row, so runs of background are written as long bursts
+        // (A/B on 320 maps: 704 -> 676 us against column-wise 128-byte pieces at a 4 KB stride).
         // (a segment cut by the right border is flagged on every row, so only full-width tiles get here)
-        for (int ty = 0; ty < tiles_y; ++ty) {
-            if ((ne >> ty) & 1ull) continue;
-            const int yb = ty << 5;
-            zero_tile(oc - lane + (size_t)yb * W, W, min(H, yb + 32) - yb, lane);
+        const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+        const unsigned *__restrict__ flm = flags + (size_t)m * tiles_y * tiles_x;
+        int *__restrict__ om = out + (size_t)m * H * W;
+        for (int ty = wid; ty < tiles_y; ty += nw) {
+            const int yb = ty << 5, rows = min(H, yb + 32) - yb;
+            for (int s0 = 0; s0 < tiles_x; s0 += 32) {
+                const unsigned f = s0 + lane < tiles_x ? __ldg(flm + (size_t)ty * tiles_x + s0 + lane) : 1u;
+                const unsigned emp = __ballot_sync(FULL, f == 0u);          // empty segments s0 .. s0+31
+                if (!emp) continue;
+#pragma unroll
+                for (int grp = 0; grp < 8; ++grp) {                         // 4 segments = 128 columns
+                    if (!((emp >> (4 * grp)) & 0xfu)) continue;
+                    const bool mine = (emp >> (4 * grp + (lane >> 3))) & 1u;
+                    int *p = om + (size_t)yb * W + (size_t)(s0 + 4 * grp) * 32 + 4 * lane;
+                    if (mine) {
+#pragma unroll 8
+                        for (int y = 0; y < rows; ++y)
+                            asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p + (size_t)y * W) : "memory");
+                    }
+                }
+            }
         }
         return;
     }
+#ifdef SLN_EDT_PROBE_NOENV
+    return;                                         // timing probe (wrong output): fill role alone
+#endif
     if (ne == 0ull) return;
 
     unsigned *__restrict__ sc = g + (size_t)m * H * W + x;                    // g column, then the entry stack
     unsigned *__restrict__ fgc = fgcol + (size_t)m * tiles_y * W + x;
-    PCol c{-1, 0, 0, 0u, 0u, 0u, false};
+    PCol c;
+    c.q = -1; c.base = 0; c.ystart = 0; c.open = false;
+#pragma unroll
+    for (int i = 0; i < PK_D; ++i) c.e[i] = 0u;
 
     // ---- forward: build the envelopes
     {
@@ -756,8 +795,8 @@ edt_cols_envelope_packed_kernel(unsigned *__restrict__ g, const unsigned *__rest
                     if (c.q < 0) {
                         v = cap;                    // no zero pixel anywhere on this column's runs
                     } else {
-                        v = min(env_f(y, pk_s(c.e0), pk_g2(c.e0)), cap);
-                        if (y == pk_t(c.e0)) pk_pop(c, sc, W);
+                        v = min(env_f(y, pk_s(c.e[0]), pk_g2(c.e[0])), cap);
+                        if (y == pk_t(c.e[0])) pk_pop(c, sc, W);
                     }
                 }
                 if (valid) __stcs(oc + (size_t)y * W, v);
@@ -811,7 +850,9 @@ extern "C" int sln_layer_decode(const uint64_t *label, int B, int H, int W, int 
     layer_decode_kernel<<<dim3((unsigned)((threads + 255) / 256), B), 256, 0, st>>>(
         reinterpret_cast<const unsigned long long *>(label), px, L, n_max, out, scratch);
     SLN_LAUNCH_OK("layer_decode_kernel");
-    layer_fixup_kernel<<<dim3(4 * sm_count(), B), 256, 0, st>>>(scratch, px, L, n_max, out, n_obj);
+    // few CTAs per image: the clearing loop is grid-strided and almost never runs; 9472 CTAs that only read the
+    // flags and leave cost 19 us
+    layer_fixup_kernel<<<dim3(32, B), 256, 0, st>>>(scratch, px, L, n_max, out, n_obj);
     SLN_LAUNCH_OK("layer_fixup_kernel");
     return SLN_OK;
 }
