@@ -720,7 +720,8 @@ constexpr int SP_EDGES_PER_BOX = 16;
 constexpr int SP_BIN_THREADS = 1024;
 constexpr int SP_PAIR_WARPS = 8;
 constexpr int SP_PAIR_UNROLL = 4;          // candidates per lane in flight
-constexpr int SP_INLINE = 16;              // predecessors stored inline per box (32 bytes)
+constexpr int SP_INLINE = 32;              // predecessors stored inline per box (one 64-byte row)
+constexpr int SP_INL_V = SP_INLINE / 8;    // uint4 per row
 constexpr int SP_WARP_BUF = 128;           // edges buffered per warp before one atomic allocation
 constexpr int SP_MAX_ROUNDS = 96;
 constexpr int SP_RESOLVE_THREADS = 1024;
@@ -742,7 +743,7 @@ struct SparseBufs {
     float *carea;
     int *cpos;
     int *ccls;
-    uint4 *inl;            // [n][2] the first SP_INLINE predecessors of every box as u16 (0xffff: none)
+    uint4 *inl;            // [n][SP_INL_V] the first SP_INLINE predecessors of every box as u16 (0xffff: none)
     int2 *seg;             // [n] (first entry, count) of the rest of the list in `edges`
     unsigned *edges;       // [SP_EDGES_PER_BOX * n] overflow predecessor positions, grouped by box
 };
@@ -755,7 +756,7 @@ static size_t nms_sparse_bytes(int n)
     b += align_up(sizeof(float4) * (size_t)n, 256);
     b += 3 * align_up(sizeof(int) * (size_t)n, 256);
     b += align_up(sizeof(int2) * (size_t)n, 256);
-    b += align_up(sizeof(uint4) * 2 * (size_t)n, 256);
+    b += align_up(sizeof(uint4) * SP_INL_V * (size_t)n, 256);
     b += align_up(sizeof(unsigned) * (size_t)SP_EDGES_PER_BOX * n, 256);
     return b;
 }
@@ -770,7 +771,7 @@ static void sparse_carve(void *ws, int n, SparseBufs &b)
     b.cpos = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
     b.ccls = reinterpret_cast<int *>(p);          p += align_up(sizeof(int) * (size_t)n, 256);
     b.seg = reinterpret_cast<int2 *>(p);          p += align_up(sizeof(int2) * (size_t)n, 256);
-    b.inl = reinterpret_cast<uint4 *>(p);         p += align_up(sizeof(uint4) * 2 * (size_t)n, 256);
+    b.inl = reinterpret_cast<uint4 *>(p);         p += align_up(sizeof(uint4) * SP_INL_V * (size_t)n, 256);
     b.edges = reinterpret_cast<unsigned *>(p);
 }
 
@@ -1070,9 +1071,9 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
 // predecessor row sits in the owner's shared memory (one coalesced 32-byte load per box).
 constexpr int SP_WORDS = 2048;             // 32-bit words of KF / DF (n <= 65535)
 constexpr int SP_RES_ITEMS = SP_WORDS / SP_CLUSTER / (SP_RESOLVE_THREADS / 32);       // words per warp: 8
-constexpr int SP_CACHE_ITEMS = 4;          // items whose inline rows are cached in shared memory (32 KB each)
-constexpr int SP_CHECK_EVERY = 4;
-constexpr int SP_OV_CACHE = 16384;         // u16 overflow entries cached per resolve CTA (32 KB)
+constexpr int SP_CACHE_ITEMS = 2;          // items whose inline rows are cached in shared memory (64 KB each)
+constexpr int SP_CHECK_EVERY = 2;
+constexpr int SP_OV_CACHE = 8192;          // u16 overflow entries cached per resolve CTA (16 KB)
 
 // Branch-free scan of 8 inline entries: the sentinel 0xffff addresses bit 31 of word 2047 (box 65535 does not
 // exist), which is kept clear in KF and set in DF, so an empty slot reads as "dead predecessor".
@@ -1127,8 +1128,9 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
         if (u < n_items && w < W32 && b < n) {
             undecided |= 1u << u;
             if (u < SP_CACHE_ITEMS) {
-                rows[(u * SP_RESOLVE_THREADS + tid) * 2] = __ldg(sb.inl + 2 * (size_t)b);
-                rows[(u * SP_RESOLVE_THREADS + tid) * 2 + 1] = __ldg(sb.inl + 2 * (size_t)b + 1);
+#pragma unroll
+                for (int v = 0; v < SP_INL_V; ++v)
+                    rows[(u * SP_RESOLVE_THREADS + tid) * SP_INL_V + v] = __ldg(sb.inl + SP_INL_V * (size_t)b + v);
             }
             sg = __ldg(sb.seg + b);
         }
@@ -1162,17 +1164,16 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
             bool dead = false, kept = false, need_rest = false, all_dead_reg = true;
             if ((undecided >> u) & 1u) {
                 const int b = 32 * w + lane;
-                uint4 r0, r1;
-                if (u < SP_CACHE_ITEMS) {
-                    r0 = rows[(u * SP_RESOLVE_THREADS + tid) * 2];
-                    r1 = rows[(u * SP_RESOLVE_THREADS + tid) * 2 + 1];
-                } else {
-                    r0 = __ldg(sb.inl + 2 * (size_t)b);
-                    r1 = __ldg(sb.inl + 2 * (size_t)b + 1);
-                }
                 unsigned anyK = 0u, anyN = 0u;
-                sp_scan8(KF, DF, r0, anyK, anyN);
-                sp_scan8(KF, DF, r1, anyK, anyN);
+                // 8 entries at a time; rows are filled front to back, so the scan stops at the first chunk that
+                // starts with the sentinel
+#pragma unroll
+                for (int v = 0; v < SP_INL_V; ++v) {
+                    const uint4 rv = u < SP_CACHE_ITEMS ? rows[(u * SP_RESOLVE_THREADS + tid) * SP_INL_V + v]
+                                                        : __ldg(sb.inl + SP_INL_V * (size_t)b + v);
+                    if ((rv.x & 0xffffu) == 0xffffu) break;
+                    sp_scan8(KF, DF, rv, anyK, anyN);
+                }
                 dead = anyK & 1u;
                 const bool all_dead = !(anyN & 1u);
                 all_dead_reg = all_dead;
@@ -1294,7 +1295,7 @@ static int launch_sparse(const float4 *boxes, const float *areas, const int *cls
     SLN_LAUNCH_OK("nms_pairs_kernel");
     int items = cdiv(cdiv(n, 32), SP_CLUSTER * 32);
     if (items > SP_CACHE_ITEMS) items = SP_CACHE_ITEMS;
-    const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32) + 2 * SP_OV_CACHE + (size_t)items * SP_RESOLVE_THREADS * 32;
+    const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32) + 2 * SP_OV_CACHE + (size_t)items * SP_RESOLVE_THREADS * sizeof(uint4) * SP_INL_V;
     SLN_CUDA_OK(cudaFuncSetAttribute(nms_sparse_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_sparse_resolve_kernel<<<SP_CLUSTER, SP_RESOLVE_THREADS, smem, st>>>(order, n, max_keep, edge_cap, sb, keep64, keep32, num_keep);
     SLN_LAUNCH_OK("nms_sparse_resolve_kernel");
