@@ -261,7 +261,8 @@ def run_ours(args):
                         "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6})
         ms = time_op(lambda: ops.pyramid_crop_backward(grads[p], boxes, box_ind, level, sizes))
         by = sum(bwd_bytes(int((level_np == l).sum()), side, p) for l, side in enumerate(LEVEL_SIDES))
-        kernels.append({"kernel": "crop_bwd_nhwc_kernel", "what": "pyramid bwd %dx%d, all levels (incl. 2 prep launches)" % (p, p),
+        kernels.append({"kernel": "crop_bwd_tile_kernel" if p * p <= 64 else "crop_bwd_nhwc_kernel",
+                        "what": "pyramid bwd %dx%d, all levels (incl. 2 prep launches)" % (p, p),
                         "ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6})
     for k in kernels:
         k["frac"] = k["achieved_gbs"] / peak
@@ -294,19 +295,45 @@ def run_ours(args):
            + sum(t.numel() for p in POOLS for t in h_grads[p])) * 4
     d2h = (sum(t.numel() for p in POOLS for t in h_out[p]) + len(POOLS) * sum(hm.numel() for hm in h_gmaps)) * 4
 
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
     def e2e_step():
-        # the call a reference user makes (modals.py:96): CropAndResizeFunction(ph,pw,0)(P_l, boxes_l, ind_l), then backward
-        d_maps = [hm.to(dev, non_blocking=True).requires_grad_(True) for hm in h_maps]
-        d_boxes = [t.to(dev, non_blocking=True) for t in h_boxes]
-        d_ind = [t.to(dev, non_blocking=True) for t in h_ind]
+        # the call a reference user makes (modals.py:96): CropAndResizeFunction(ph,pw,0)(P_l, boxes_l, ind_l), then
+        # backward.  Host->device copies run on their own stream, device->host copies on another, so the two PCIe
+        # directions and the kernels overlap; every byte still moves inside the timed region.
+        cur = torch.cuda.current_stream()
+        s_in.wait_stream(cur)
+        with torch.cuda.stream(s_in):
+            d_maps = [hm.to(dev, non_blocking=True) for hm in h_maps]
+            d_boxes = [t.to(dev, non_blocking=True) for t in h_boxes]
+            d_ind = [t.to(dev, non_blocking=True) for t in h_ind]
+            ev_maps = torch.cuda.Event()
+            ev_maps.record(s_in)
+            d_g, ev_g = {}, {}
+            for p in POOLS:
+                for l in range(4):
+                    d_g[p, l] = h_grads[p][l].to(dev, non_blocking=True)
+                    ev_g[p, l] = torch.cuda.Event()
+                    ev_g[p, l].record(s_in)
+        cur.wait_event(ev_maps)
+        for t in d_maps + d_boxes + d_ind:
+            t.record_stream(cur)
+        d_maps = [m.requires_grad_(True) for m in d_maps]
         for p in POOLS:
             for l in range(4):
-                d_g = h_grads[p][l].to(dev, non_blocking=True)
+                cur.wait_event(ev_g[p, l])
+                d_g[p, l].record_stream(cur)
                 out = CropAndResizeFunction(p, p, 0)(d_maps[l], d_boxes[l], d_ind[l])
-                out.backward(d_g)
-                h_out[p][l].copy_(out.detach(), non_blocking=True)
-                h_gmaps[l].copy_(d_maps[l].grad, non_blocking=True)
+                out.backward(d_g[p, l])
+                gm = d_maps[l].grad
                 d_maps[l].grad = None
+                s_out.wait_stream(cur)
+                with torch.cuda.stream(s_out):
+                    h_out[p][l].copy_(out.detach(), non_blocking=True)
+                    h_gmaps[l].copy_(gm, non_blocking=True)
+                out.record_stream(s_out)
+                gm.record_stream(s_out)
+        cur.wait_stream(s_out)
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -320,7 +347,8 @@ def run_ours(args):
     e2e_ms = sdist.max_over_ranks(a.elapsed_time(b)) / e2e_steps
     e2e = {"value": round(crops_per_step / (e2e_ms * 1e-3), 1), "unit": "roi_crops/s", "ms_per_step": round(e2e_ms, 3),
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-           "api": "CropAndResizeFunction(ph,pw,0)(image,boxes,box_ind) + .backward per FPN level; pinned host buffers in and out"}
+           "api": "CropAndResizeFunction(ph,pw,0)(image,boxes,box_ind) + .backward per FPN level; pinned host buffers in and out; "
+                  "H2D, kernels and D2H on three streams (both PCIe directions overlap)"}
     del h_maps, h_grads, h_out, h_gmaps
 
     extra = {}
