@@ -680,18 +680,17 @@ __device__ __forceinline__ void bwd_tile_visit(typename VecT<VEC>::type *acc, co
 #undef SLN_TAP
     } else {
         // zero-weight taps are skipped, so the (up to) four destinations are distinct pixels: all loads, then all
-        // fused multiply-adds, then all stores
+        // fused multiply-adds, then all stores.  A tap that is not ours reads pixel 0 of the tile (any valid address)
+        // and is simply not stored: no selects, no register zeroing.
         const bool t0 = top_in && l_in, t1 = top_in && r_in && wr != 0.f;
         const bool t2 = bot_in && l_in && wb != 0.f, t3 = bot_in && r_in && wb != 0.f && wr != 0.f;
         const float w0 = __fmul_rn(wt, wl), w1 = __fmul_rn(wt, wr), w2 = __fmul_rn(wb, wl), w3 = __fmul_rn(wb, wr);
-        const V zero = make_splat(0.f, (V *)nullptr);
+        V *q0 = acc + (t0 ? (rt + cl) * ROWV : 0), *q1 = acc + (t1 ? (rt + cr) * ROWV : 0);
+        V *q2 = acc + (t2 ? (rb + cl) * ROWV : 0), *q3 = acc + (t3 ? (rb + cr) * ROWV : 0);
         V a0[NV], a1[NV], a2[NV], a3[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            a0[j] = t0 ? acc[(rt + cl) * ROWV + 32 * j] : zero;
-            a1[j] = t1 ? acc[(rt + cr) * ROWV + 32 * j] : zero;
-            a2[j] = t2 ? acc[(rb + cl) * ROWV + 32 * j] : zero;
-            a3[j] = t3 ? acc[(rb + cr) * ROWV + 32 * j] : zero;
+            a0[j] = q0[32 * j]; a1[j] = q1[32 * j]; a2[j] = q2[32 * j]; a3[j] = q3[32 * j];
         }
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -702,15 +701,15 @@ __device__ __forceinline__ void bwd_tile_visit(typename VecT<VEC>::type *acc, co
         }
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (t0) acc[(rt + cl) * ROWV + 32 * j] = a0[j];
-            if (t1) acc[(rt + cr) * ROWV + 32 * j] = a1[j];
-            if (t2) acc[(rb + cl) * ROWV + 32 * j] = a2[j];
-            if (t3) acc[(rb + cr) * ROWV + 32 * j] = a3[j];
+            if (t0) q0[32 * j] = a0[j];
+            if (t1) q1[32 * j] = a1[j];
+            if (t2) q2[32 * j] = a2[j];
+            if (t3) q3[32 * j] = a3[j];
         }
     }
 }
 
-template <int VEC, int NV, bool EXACT>
+template <int VEC, int NV, bool EXACT, bool FULL>
 __global__ void __launch_bounds__(32 * BWD_TILE_WARPS)
 crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ taps,
                      const ListEntry *__restrict__ entries, const int *__restrict__ st_off,
@@ -739,9 +738,9 @@ crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ ta
     const int y1 = min(y0 + T, H) - 1, x1 = min(x0 + T, W) - 1;
     const int CV = C / VEC;
     const int cvbase = blockIdx.y * ROWV + lane;
-    bool ok[NV];
+    bool ok[NV];                               // FULL: every lane's vectors exist (CV is a multiple of 32 * NV)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) ok[j] = cvbase + 32 * j < CV;
+    for (int j = 0; j < NV; ++j) ok[j] = FULL || cvbase + 32 * j < CV;
 
     const V zero = make_splat(0.f, (V *)nullptr);
     bool touched = false;                      // warp-uniform: accumulators initialised and in use
@@ -812,7 +811,7 @@ crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ ta
                             if (!xrem) { yrem &= yrem - 1; xrem = xm; }
 #pragma unroll
                             for (int j = 0; j < NV; ++j) {
-                                gv[u][j] = zero;
+                                if (!FULL) gv[u][j] = zero;
                                 if (ok[j]) gv[u][j] = ldg_vec(gr + (size_t)(yb * pw + xb) * CV + 32 * j);
                             }
                         }
@@ -1035,7 +1034,7 @@ static int launch_bwd_tile(const float *grads, const BwdWs &ws, const BwdParams 
     for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
     dim3 grid((unsigned)tiles, chunks);
     const size_t smem = (size_t)BWD_TILE_WARPS * BWD_TILE * BWD_TILE * 32 * NV * sizeof(float) * VEC;
-    auto kern = crop_bwd_tile_kernel<VEC, NV, EXACT>;
+    auto kern = (C / VEC) % (32 * NV) == 0 ? crop_bwd_tile_kernel<VEC, NV, EXACT, true> : crop_bwd_tile_kernel<VEC, NV, EXACT, false>;
     SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     kern<<<grid, 32 * BWD_TILE_WARPS, smem, st>>>(grads, ws.taps, ws.entries, ws.st_off, ws.st_count, ws.lv_table, TB, C, ph, pw);

@@ -719,7 +719,10 @@ constexpr int SP_MAX_CELLS = 4096;
 constexpr int SP_EDGES_PER_BOX = 16;
 constexpr int SP_BIN_THREADS = 1024;
 constexpr int SP_PAIR_WARPS = 8;
-constexpr int SP_PAIR_UNROLL = 4;          // candidates per lane in flight
+#ifndef SLN_SP_PAIR_UNROLL
+#define SLN_SP_PAIR_UNROLL 4
+#endif
+constexpr int SP_PAIR_UNROLL = SLN_SP_PAIR_UNROLL;   // candidates per lane in flight
 constexpr int SP_INLINE = 32;              // predecessors stored inline per box (one 64-byte row)
 constexpr int SP_INL_V = SP_INLINE / 8;    // uint4 per row
 constexpr int SP_WARP_BUF = 128;           // edges buffered per warp before one atomic allocation
@@ -1165,19 +1168,23 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
             if ((undecided >> u) & 1u) {
                 const int b = 32 * w + lane;
                 unsigned anyK = 0u, anyN = 0u;
+                bool row_empty = false;
                 // 8 entries at a time; rows are filled front to back, so the scan stops at the first chunk that
-                // starts with the sentinel
+                // starts with the sentinel.  Round 0 knows (almost) nothing yet: only the first chunk is looked at,
+                // a box without predecessors is kept at once, and no other box may be declared kept from a partial
+                // scan (bits published by faster CTAs can already be visible).
 #pragma unroll
                 for (int v = 0; v < SP_INL_V; ++v) {
+                    if (round == 0 && v > 0) break;
                     const uint4 rv = u < SP_CACHE_ITEMS ? rows[(u * SP_RESOLVE_THREADS + tid) * SP_INL_V + v]
                                                         : __ldg(sb.inl + SP_INL_V * (size_t)b + v);
-                    if ((rv.x & 0xffffu) == 0xffffu) break;
+                    if ((rv.x & 0xffffu) == 0xffffu) { row_empty = v == 0; break; }
                     sp_scan8(KF, DF, rv, anyK, anyN);
                 }
                 dead = anyK & 1u;
-                const bool all_dead = !(anyN & 1u);
+                const bool all_dead = round == 0 ? row_empty : !(anyN & 1u);
                 all_dead_reg = all_dead;
-                need_rest = !dead && p_over[u] != 0u;
+                need_rest = !dead && p_over[u] != 0u && round > 0;
                 kept = !dead && all_dead && !need_rest;
                 if (dead || kept) undecided &= ~(1u << u);
             }

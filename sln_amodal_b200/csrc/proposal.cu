@@ -30,16 +30,68 @@ constexpr int SEL_THREADS = 256;
 
 __device__ __forceinline__ unsigned fg_key(const float *probs, int i) { return score_key(__ldg(probs + 2 * (size_t)i + 1)); }
 
-// pass 0: bits 31..21, pass 1: bits 20..10 (keys matching 11-bit prefix), pass 2: bits 9..0
+// Walk a 2048-bin histogram from the top bin down to the bin holding the k_rem-th element (whole CTA of
+// SEL_THREADS threads, 8 bins per thread); fold that bin into the prefix and reduce k_rem.  Every CTA of the kernel
+// that consumes the result does this itself (the histogram is 8 KB in L2), which removes the three single-CTA
+// "pick" launches of the first version; each pass has its own histogram, so nothing has to be cleared in between.
+struct Pick {
+    unsigned prefix;
+    int k_rem;
+};
+
+template <int PASS>
+__device__ Pick cta_pick(const unsigned *__restrict__ hist, unsigned prev_prefix, int k_rem)
+{
+    __shared__ unsigned s_wsum[SEL_THREADS / 32];
+    __shared__ unsigned s_found[2];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int PER = SEL_BINS / SEL_THREADS;     // 8
+    unsigned h[PER], sum = 0u;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { h[q] = hist[PER * t + q]; sum += h[q]; }
+    unsigned incl = sum;                            // inclusive suffix sum over the threads above (higher bins)
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+    }
+    __syncthreads();                                // the statics may still be read from a previous call
+    if (lane == 0) s_wsum[warp] = incl;
+    __syncthreads();
+    unsigned above = incl - sum;                    // elements in bins above this thread's, same warp
+    for (int w = warp + 1; w < SEL_THREADS / 32; ++w) above += s_wsum[w];
+#pragma unroll
+    for (int q = PER - 1; q >= 0; --q) {            // highest bin first
+        if (above < (unsigned)k_rem && (unsigned)k_rem <= above + h[q]) { s_found[0] = (unsigned)(PER * t + q); s_found[1] = above; }
+        above += h[q];
+    }
+    __syncthreads();
+    Pick p;
+    p.prefix = (prev_prefix << (PASS == 0 ? 0 : (PASS == 1 ? 11 : 10))) | s_found[0];
+    p.k_rem = k_rem - (int)s_found[1];
+    return p;
+}
+
+// pass 0: bits 31..21, pass 1: bits 20..10 (keys matching the 11-bit prefix), pass 2: bits 9..0.
+// hist = three histograms [3][SEL_BINS], zeroed once per call.  Pass P > 0 first picks the bin of pass P-1 (from the
+// state the previous launch left + that pass's histogram); CTA 0 publishes the new state for the next launch.
 template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS)
-select_hist_kernel(const float *__restrict__ probs, int A, const SelectState *__restrict__ state,
+select_hist_kernel(const float *__restrict__ probs, int A, int K, SelectState *__restrict__ state,
                    unsigned *__restrict__ hist)
 {
     __shared__ unsigned s_hist[SEL_BINS];
     for (int t = threadIdx.x; t < SEL_BINS; t += SEL_THREADS) s_hist[t] = 0u;
+    unsigned prefix = 0u;
+    if (PASS > 0) {
+        const unsigned prev = PASS == 1 ? 0u : state[(PASS - 1) & 1].prefix;
+        const int k_rem = PASS == 1 ? K : state[(PASS - 1) & 1].k_rem;
+        const Pick p = PASS == 1 ? cta_pick<0>(hist, prev, k_rem) : cta_pick<1>(hist + SEL_BINS, prev, k_rem);
+        prefix = p.prefix;
+        // (the state words this launch reads are not the ones it writes: double-buffered by pass parity)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { state[PASS & 1].prefix = p.prefix; state[PASS & 1].k_rem = p.k_rem; }
+    }
     __syncthreads();
-    const unsigned prefix = PASS == 0 ? 0u : state->prefix;
+    unsigned *out = hist + PASS * SEL_BINS;
     for (int i = blockIdx.x * SEL_THREADS + threadIdx.x; i < A; i += gridDim.x * SEL_THREADS) {
         const unsigned k = fg_key(probs, i);
         if (PASS == 0) atomicAdd(&s_hist[k >> 21], 1u);
@@ -49,49 +101,8 @@ select_hist_kernel(const float *__restrict__ probs, int A, const SelectState *__
     __syncthreads();
     for (int t = threadIdx.x; t < SEL_BINS; t += SEL_THREADS) {
         const unsigned v = s_hist[t];
-        if (v) atomicAdd(hist + t, v);
+        if (v) atomicAdd(out + t, v);
     }
-}
-
-// Single CTA: walk the histogram from the top bin down to the bin holding the k_rem-th
-// element; fold that bin into the prefix, reduce k_rem, clear the histogram.
-template <int PASS>
-__global__ void __launch_bounds__(1024)
-select_pick_kernel(unsigned *__restrict__ hist, SelectState *__restrict__ state, int k_init)
-{
-    __shared__ unsigned s_sum[1024];
-    const int t = threadIdx.x;
-    const int k_rem = PASS == 0 ? k_init : state->k_rem;
-    // thread t owns bins 2t, 2t+1; suffix sums over threads (top bins first)
-    const unsigned h0 = hist[2 * t], h1 = hist[2 * t + 1];
-    s_sum[t] = h0 + h1;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {       // inclusive suffix scan
-        const unsigned add = (t + off < 1024) ? s_sum[t + off] : 0u;
-        __syncthreads();
-        s_sum[t] += add;
-        __syncthreads();
-    }
-    const unsigned above_thread = (t + 1 < 1024) ? s_sum[t + 1] : 0u;   // elements in bins > 2t+1
-    // bin 2t+1 first (higher), then 2t
-    const unsigned above1 = above_thread, above0 = above_thread + h1;
-    int found = -1;
-    unsigned above = 0;
-    if (above1 < (unsigned)k_rem && (unsigned)k_rem <= above1 + h1) { found = 2 * t + 1; above = above1; }
-    else if (above0 < (unsigned)k_rem && (unsigned)k_rem <= above0 + h0) { found = 2 * t; above = above0; }
-    __syncthreads();
-    if (found >= 0) {
-        const unsigned prev = PASS == 0 ? 0u : state->prefix;
-        const int shift = PASS == 2 ? 10 : 11;
-        state->prefix = (prev << shift) | (unsigned)found;
-        state->k_rem = k_rem - (int)above;
-        if (PASS == 2) {
-            state->count_gt = k_init - (k_rem - (int)above);
-            state->counter = 0;
-        }
-    }
-    hist[2 * t] = 0u;
-    hist[2 * t + 1] = 0u;
 }
 
 // Each CTA owns a contiguous slice of the anchors so that "ordered" means index order.
@@ -103,13 +114,21 @@ __device__ __forceinline__ void slice_of(int A, int &lo, int &hi)
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_count_eq_kernel(const float *__restrict__ probs, int A, const SelectState *__restrict__ state,
-                       int *__restrict__ blk_eq)
+select_count_eq_kernel(const float *__restrict__ probs, int A, int K, SelectState *__restrict__ state,
+                       const unsigned *__restrict__ hist, int *__restrict__ blk_eq)
 {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
+    // pick of pass 2: the exact k-th key T and how many keys equal to T are still wanted
+    const Pick p = cta_pick<2>(hist + 2 * SEL_BINS, state[0].prefix, state[0].k_rem);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        state[1].prefix = p.prefix;
+        state[1].k_rem = p.k_rem;
+        state[1].count_gt = K - p.k_rem;
+        state[1].counter = 0;
+    }
     __syncthreads();
-    const unsigned T = state->prefix;
+    const unsigned T = p.prefix;
     int lo, hi;
     slice_of(A, lo, hi);
     int c = 0;
@@ -120,35 +139,35 @@ select_count_eq_kernel(const float *__restrict__ probs, int A, const SelectState
     if (threadIdx.x == 0) blk_eq[blockIdx.x] = s_cnt;
 }
 
-// exclusive scan of blk_eq (nblk <= 1024) in place
-__global__ void __launch_bounds__(1024) select_scan_eq_kernel(int *__restrict__ blk_eq, int nblk)
-{
-    __shared__ int s[1024];
-    const int t = threadIdx.x;
-    const int v = t < nblk ? blk_eq[t] : 0;
-    s[t] = v;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const int add = t >= off ? s[t - off] : 0;
-        __syncthreads();
-        s[t] += add;
-        __syncthreads();
-    }
-    if (t < nblk) blk_eq[t] = s[t] - v;
-}
-
 __global__ void __launch_bounds__(SEL_THREADS)
 select_compact_kernel(const float *__restrict__ probs, int A, SelectState *__restrict__ state,
-                      const int *__restrict__ blk_off, float *__restrict__ cand_score,
+                      const int *__restrict__ blk_eq, float *__restrict__ cand_score,
                       int *__restrict__ cand_idx)
 {
     __shared__ int s_warp[SEL_THREADS / 32];
+    __shared__ int s_base;
+    state += 1;                                     // final state, published by select_count_eq_kernel
     const unsigned T = state->prefix;
     const int count_gt = state->count_gt, need_eq = state->k_rem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int lo, hi;
     slice_of(A, lo, hi);
-    int eq_base = blk_off[blockIdx.x];
+    // keys equal to T in the slices before mine (replaces the single-CTA scan launch)
+    {
+        int part = 0;
+        for (int k = threadIdx.x; k < (int)blockIdx.x; k += SEL_THREADS) part += blk_eq[k];
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_warp[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < SEL_THREADS / 32; ++w) tot += s_warp[w];
+            s_base = tot;
+        }
+        __syncthreads();
+    }
+    int eq_base = s_base;
+    __syncthreads();
     for (int start = lo; start < hi; start += SEL_THREADS) {
         const int i = start + threadIdx.x;
         unsigned k = 0;
@@ -267,7 +286,7 @@ static size_t proposal_ws_bytes(int K)
 {
     size_t b = 0;
     b += 256;                                                    // state
-    b += align_up(sizeof(unsigned) * SEL_BINS, 256);             // hist
+    b += align_up(sizeof(unsigned) * 3 * SEL_BINS, 256);         // hist (one per pass)
     b += align_up(sizeof(int) * SEL_MAX_BLOCKS, 256);            // blk_eq
     b += align_up(sizeof(float) * (size_t)K, 256);               // cand_score
     b += 2 * align_up(sizeof(int) * (size_t)K, 256);             // cand_idx, keep
@@ -280,7 +299,7 @@ static void proposal_carve(void *ws, int K, ProposalBuffers &b)
 {
     unsigned char *p = static_cast<unsigned char *>(ws);
     b.state = reinterpret_cast<SelectState *>(p);  p += 256;
-    b.hist = reinterpret_cast<unsigned *>(p);      p += align_up(sizeof(unsigned) * SEL_BINS, 256);
+    b.hist = reinterpret_cast<unsigned *>(p);      p += align_up(sizeof(unsigned) * 3 * SEL_BINS, 256);
     b.blk_eq = reinterpret_cast<int *>(p);         p += align_up(sizeof(int) * SEL_MAX_BLOCKS, 256);
     b.cand_score = reinterpret_cast<float *>(p);   p += align_up(sizeof(float) * (size_t)K, 256);
     b.cand_idx = reinterpret_cast<int *>(p);       p += align_up(sizeof(int) * (size_t)K, 256);
@@ -333,15 +352,11 @@ extern "C" int sln_proposal_layer(const float *probs, const float *deltas, const
         int nblk = 4 * sm_count();
         if (nblk > SEL_MAX_BLOCKS) nblk = SEL_MAX_BLOCKS;
         if (nblk > cdiv(A, SEL_THREADS)) nblk = cdiv(A, SEL_THREADS);
-        SLN_CUDA_OK(cudaMemsetAsync(b.hist, 0, sizeof(unsigned) * SEL_BINS, st));
-        select_hist_kernel<0><<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.hist);
-        select_pick_kernel<0><<<1, 1024, 0, st>>>(b.hist, b.state, K);
-        select_hist_kernel<1><<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.hist);
-        select_pick_kernel<1><<<1, 1024, 0, st>>>(b.hist, b.state, K);
-        select_hist_kernel<2><<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.hist);
-        select_pick_kernel<2><<<1, 1024, 0, st>>>(b.hist, b.state, K);
-        select_count_eq_kernel<<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.blk_eq);
-        select_scan_eq_kernel<<<1, 1024, 0, st>>>(b.blk_eq, nblk);
+        SLN_CUDA_OK(cudaMemsetAsync(b.hist, 0, sizeof(unsigned) * 3 * SEL_BINS, st));
+        select_hist_kernel<0><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);
+        select_hist_kernel<1><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);      // picks pass 0 -> state[1]
+        select_hist_kernel<2><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);      // picks pass 1 -> state[0]
+        select_count_eq_kernel<<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist, b.blk_eq);   // picks pass 2 -> state[1]
         select_compact_kernel<<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.blk_eq, b.cand_score, b.cand_idx);
         SLN_LAUNCH_OK("select kernels");
     }
