@@ -134,6 +134,11 @@ SLN_API int sln_nms(const float *dets, const int *class_ids, int n, float thresh
  * SLN_NMS_DENSE_ONLY forces the dense pipeline.  *path_out (device i32, may be NULL) receives 1 when the
  * sparse pipeline produced the result, else 0.                                                        */
 #define SLN_NMS_DENSE_ONLY 1
+/* SLN_NMS_SPARSE_ONLY: launch the sparse pipeline alone (3 kernels instead of 6).  If the input turns out to be
+ * outside its contract *num_keep is set to -1 and `keep` is undefined: call again with SLN_NMS_DENSE_ONLY.  For
+ * callers that read num_keep on the host anyway (the reference's nms() does, pth_nms.py:24); ignored when the
+ * sparse pipeline is not attempted at all (then the dense one runs as usual).                           */
+#define SLN_NMS_SPARSE_ONLY 2
 SLN_API int sln_nms_ex(const float *dets, const int *class_ids, int n, float thresh, int max_keep, int flags,
                int64_t *keep, int *num_keep, int *path_out, void *workspace, size_t workspace_bytes,
                void *stream);

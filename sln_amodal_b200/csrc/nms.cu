@@ -78,9 +78,22 @@ __device__ __forceinline__ int rank_count(const uint4 *__restrict__ k4, const ui
     return cf_is_ge ? all - c : c;
 }
 
+// Optional epilogue of the rank kernel (sln_nms path): once the last column tile of a 256-row tile has added its
+// counts -- detected with a ticket per row tile -- that CTA permutes its rows' boxes into visiting order.  This
+// replaces a separate gather launch.  rank[] and the tickets are zeroed by one memset.
+struct RankGather {
+    const float *dets;         // [n][5]; nullptr: no gather
+    const int *class_ids;      // may be nullptr
+    float4 *boxes;
+    float *areas;
+    int *cls;
+    int *order;
+    int *tickets;              // [ceil(n / RANK_ROWS)]
+};
+
 __global__ void __launch_bounds__(RANK_ROWS)
 rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict__ tie_ids, int n,
-            int *__restrict__ rank)
+            int *__restrict__ rank, RankGather ga)
 {
     __shared__ __align__(16) unsigned s_key[RANK_COLS];
     __shared__ __align__(16) unsigned s_tie[RANK_COLS];     // ~tie id
@@ -115,14 +128,14 @@ rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict_
         s_tie[t] = ~(unsigned)tie[q];
     }
     __syncthreads();
-    if (i >= n) return;
+    int cnt = 0;
+    if (i < n) {
     const unsigned ki = score_key(si);
     const int n4 = (jn + 3) >> 2, pad = n4 * 4 - jn;
     const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key);
     const uint4 *t4 = reinterpret_cast<const uint4 *>(s_tie);
     const unsigned nti = ~(unsigned)ti;
     const bool cf_ge = carry_counts_ge((unsigned)(stride > 0));
-    int cnt;
     if (tie_ids == nullptr && j0 + jn <= i0) {
         cnt = rank_count<0>(k4, t4, n4, ki, nti, cf_ge);
         if (ki == 0u) cnt -= pad;                      // padded keys (0) satisfy 0 >= 0
@@ -132,35 +145,40 @@ rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict_
         cnt = rank_count<2>(k4, t4, n4, ki, nti, cf_ge);
     }
     if (cnt) atomicAdd(rank + i, cnt);
+    }
+    if (ga.dets == nullptr) return;
+    // ---- fused gather: the CTA that takes the last ticket of this row tile sees every column tile's counts
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ga.tickets + blockIdx.x, 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!s_last || i >= n) return;
+    __threadfence();
+    const int r = __ldcg(rank + i);
+    const float c0 = ga.dets[5 * (size_t)i + 0], c1 = ga.dets[5 * (size_t)i + 1];
+    const float c2 = ga.dets[5 * (size_t)i + 2], c3 = ga.dets[5 * (size_t)i + 3];
+    ga.boxes[r] = make_float4(c0, c1, c2, c3);
+    // pth_nms.py:16  areas = (x2 - x1 + 1) * (y2 - y1 + 1), one rounding per op
+    ga.areas[r] = __fmul_rn(__fadd_rn(__fsub_rn(c3, c1), 1.f), __fadd_rn(__fsub_rn(c2, c0), 1.f));
+    ga.order[r] = i;
+    if (ga.class_ids) ga.cls[r] = ga.class_ids[i];
 }
 
-int rank_sort_launch(const float *scores, int stride, const int *tie_ids, int n, int *rank, cudaStream_t st)
+static int rank_launch(const float *scores, int stride, const int *tie_ids, int n, int *rank, const RankGather &ga,
+                       cudaStream_t st)
 {
     if (n <= 0) return SLN_OK;
     dim3 grid(cdiv(n, RANK_ROWS), cdiv(n, RANK_COLS));
     SLN_REQUIRE(grid.y <= 65535, SLN_ERR_ARG, "rank sort: n=%d too large", n);
-    rank_kernel<<<grid, RANK_ROWS, 0, st>>>(scores, stride, tie_ids, n, rank);
+    rank_kernel<<<grid, RANK_ROWS, 0, st>>>(scores, stride, tie_ids, n, rank, ga);
     SLN_LAUNCH_OK("rank_kernel");
     return SLN_OK;
 }
 
-// ---------------------------------------------------------------------------
-// 2. gather into visiting order
-// ---------------------------------------------------------------------------
-__global__ void nms_gather_kernel(const float *__restrict__ dets, const int *__restrict__ class_ids,
-                                  const int *__restrict__ rank, int n, float4 *__restrict__ boxes,
-                                  float *__restrict__ areas, int *__restrict__ cls, int *__restrict__ order)
+int rank_sort_launch(const float *scores, int stride, const int *tie_ids, int n, int *rank, cudaStream_t st)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float c0 = dets[5 * (size_t)i + 0], c1 = dets[5 * (size_t)i + 1];
-    const float c2 = dets[5 * (size_t)i + 2], c3 = dets[5 * (size_t)i + 3];
-    const int r = rank[i];
-    boxes[r] = make_float4(c0, c1, c2, c3);
-    // pth_nms.py:16  areas = (x2 - x1 + 1) * (y2 - y1 + 1), one rounding per op
-    areas[r] = __fmul_rn(__fadd_rn(__fsub_rn(c3, c1), 1.f), __fadd_rn(__fsub_rn(c2, c0), 1.f));
-    order[r] = i;
-    if (class_ids) cls[r] = class_ids[i];
+    return rank_launch(scores, stride, tie_ids, n, rank, RankGather{}, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -197,9 +215,13 @@ template <bool CLS>
 __global__ void __launch_bounds__(64 * MASK_GROUPS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls,
                 int n_host, const int *__restrict__ n_dev, int W_stride, float thresh,
-                unsigned long long *__restrict__ mask, const int *__restrict__ skip)
+                unsigned long long *__restrict__ mask, const int *__restrict__ skip,
+                unsigned long long *__restrict__ fix_zero, int fix_words)
 {
     if (skip && *skip == 1) return;                // the sparse path already produced the result
+    // scratch of the resolve kernels that follow (removed sets, K, state): zeroed here instead of by a memset launch
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < fix_words; k += blockDim.x) fix_zero[k] = 0ull;
     // n may live in device memory (second stage of the two-stage pipeline): the grid is sized for the
     // worst case and surplus CTAs leave at once
     const int n = n_dev ? *n_dev : n_host;
@@ -718,7 +740,13 @@ constexpr int SP_MIN_N = 65;
 constexpr int SP_MAX_CELLS = 4096;
 constexpr int SP_EDGES_PER_BOX = 16;
 constexpr int SP_BIN_THREADS = 1024;
-constexpr int SP_PAIR_WARPS = 8;
+#ifndef SLN_SP_PAIR_WARPS
+#define SLN_SP_PAIR_WARPS 8
+#endif
+#ifndef SLN_SP_PAIR_CTAS_PER_SM
+#define SLN_SP_PAIR_CTAS_PER_SM 8
+#endif
+constexpr int SP_PAIR_WARPS = SLN_SP_PAIR_WARPS;
 #ifndef SLN_SP_PAIR_UNROLL
 #define SLN_SP_PAIR_UNROLL 4
 #endif
@@ -801,7 +829,7 @@ constexpr int SP_BIN_ITEMS = (SP_MAX_N + SP_CLUSTER * SP_BIN_THREADS - 1) / (SP_
 template <bool CLS>
 __global__ void __cluster_dims__(SP_CLUSTER, 1, 1) __launch_bounds__(SP_BIN_THREADS)
 nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas, const int *__restrict__ cls, int n,
-               int G, int CB, SparseBufs sb)
+               int G, int CB, SparseBufs sb, int *__restrict__ num_keep_preset)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -815,6 +843,8 @@ nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas
     const int crank = (int)cluster.block_rank();
     const int NC = CB * G * G;
     constexpr int STEP = SP_CLUSTER * SP_BIN_THREADS;
+    // sparse-only mode (SLN_NMS_SPARSE_ONLY): no dense kernels follow, a bail-out is reported as num_keep = -1
+    if (num_keep_preset && crank == 0 && tid == 0) *num_keep_preset = -1;
     for (int k = tid; k < NC; k += SP_BIN_THREADS) s_hist[k] = 0;
     // ---- my boxes: loaded once (all loads in flight), kept in registers
     float4 v[SP_BIN_ITEMS];
@@ -1279,7 +1309,7 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
 // returns the device address of the status word the dense kernels test (nullptr: sparse path not taken)
 static int launch_sparse(const float4 *boxes, const float *areas, const int *cls, const int *order, int n, float thresh,
                          int max_keep, int64_t *keep64, int *keep32, int *num_keep, void *sparse, cudaStream_t st,
-                         const int **skip_out)
+                         const int **skip_out, bool sparse_only)
 {
     *skip_out = nullptr;
     if (sparse == nullptr || n < SP_MIN_N || n > SP_MAX_N || !(thresh >= 0.05f)) return SLN_OK;
@@ -1292,11 +1322,11 @@ static int launch_sparse(const float4 *boxes, const float *areas, const int *cls
     const float t = thresh > 1.f ? 1.f : thresh;
     const float ct = (1.f - t) * (t < 0.5f ? 0.5f / t : 1.f) * 1.01f;
     const unsigned edge_cap = (unsigned)SP_EDGES_PER_BOX * (unsigned)n;
-    if (cls) nms_bin_kernel<true><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
-    else nms_bin_kernel<false><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb);
+    if (cls) nms_bin_kernel<true><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb, sparse_only ? num_keep : nullptr);
+    else nms_bin_kernel<false><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb, sparse_only ? num_keep : nullptr);
     SLN_LAUNCH_OK("nms_bin_kernel");
     int ctas = cdiv(n, SP_PAIR_WARPS);
-    if (ctas > 8 * sm_count()) ctas = 8 * sm_count();
+    if (ctas > SLN_SP_PAIR_CTAS_PER_SM * sm_count()) ctas = SLN_SP_PAIR_CTAS_PER_SM * sm_count();
     if (cls) nms_pairs_kernel<true><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
     else nms_pairs_kernel<false><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
     SLN_LAUNCH_OK("nms_pairs_kernel");
@@ -1347,6 +1377,7 @@ size_t nms_buffers_bytes(int n)
     b += align_up(sizeof(float4) * (size_t)n, 256);
     b += align_up(sizeof(float) * (size_t)n, 256);
     b += 3 * align_up(sizeof(int) * (size_t)n, 256);
+    b += align_up(sizeof(int) * (size_t)cdiv(n, RANK_ROWS), 256);          // tickets (right after rank: one memset)
     b += align_up(sizeof(unsigned long long) * nm * W, 256);
     b += 2 * nms_fix_bytes(n);
     b += nms_sparse_bytes(n);
@@ -1371,6 +1402,7 @@ void nms_carve(void *ws, int n, NmsBuffers &b)
     b.cls = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * (size_t)n, 256);
     b.order = reinterpret_cast<int *>(p);    p += align_up(sizeof(int) * (size_t)n, 256);
     b.rank = reinterpret_cast<int *>(p);     p += align_up(sizeof(int) * (size_t)n, 256);
+    b.tickets = reinterpret_cast<int *>(p);  p += align_up(sizeof(int) * (size_t)cdiv(n, RANK_ROWS), 256);
     b.mask = reinterpret_cast<unsigned long long *>(p); p += align_up(sizeof(unsigned long long) * nm * W, 256);
     b.fix = p;                               p += 2 * nms_fix_bytes(n);
     b.sparse = p;                            p += nms_sparse_bytes(n);
@@ -1378,16 +1410,19 @@ void nms_carve(void *ws, int n, NmsBuffers &b)
 }
 
 static int launch_mask(const float4 *boxes, const float *areas, const int *cls, int n_max, const int *n_dev,
-                       int W_stride, float thresh, unsigned long long *mask, const int *skip, cudaStream_t st)
+                       int W_stride, float thresh, unsigned long long *mask, const int *skip, void *fix, cudaStream_t st)
 {
+    // words of the resolve scratch the kernel zeroes (see launch_scan): 4 W_stride + FixState
+    unsigned long long *fz = static_cast<unsigned long long *>(fix);
+    const int fw = (int)((align_up(sizeof(unsigned long long) * 4 * (size_t)W_stride, 256) + align_up(sizeof(FixState), 8)) / 8);
     const int W = cdiv(n_max, 64);
     const long long n_tiles = (long long)W * (W + 1) / 2;
     long long n_blocks = (n_tiles + MASK_GROUPS - 1) / MASK_GROUPS;
     if (n_blocks > 16LL * sm_count()) n_blocks = 16LL * sm_count();
     if (cls)
-        nms_mask_kernel<true><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip);
+        nms_mask_kernel<true><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip, fz, fw);
     else
-        nms_mask_kernel<false><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip);
+        nms_mask_kernel<false><<<(unsigned)n_blocks, 64 * MASK_GROUPS, 0, st>>>(boxes, areas, cls, n_max, n_dev, W_stride, thresh, mask, skip, fz, fw);
     SLN_LAUNCH_OK("nms_mask_kernel");
     return SLN_OK;
 }
@@ -1408,8 +1443,7 @@ static int launch_scan(const unsigned long long *mask, const int *order, int n_m
     unsigned long long *removed = static_cast<unsigned long long *>(fix);
     unsigned long long *Kbuf = removed + 3 * (size_t)W_stride;
     FixState *state = reinterpret_cast<FixState *>(static_cast<unsigned char *>(fix) + align_up(sizeof(unsigned long long) * 4 * (size_t)W_stride, 256));
-    // zero the three `removed` buffers, K and the state in one memset
-    SLN_CUDA_OK(cudaMemsetAsync(fix, 0, align_up(sizeof(unsigned long long) * 4 * (size_t)W_stride, 256) + sizeof(FixState), st));
+    // (the three `removed` buffers, K and the state were zeroed by the mask kernel that precedes this call)
     static int max_ctas = 0;
     if (max_ctas == 0) {
         int per_sm = 0;
@@ -1440,7 +1474,7 @@ static int launch_scan(const unsigned long long *mask, const int *order, int n_m
 // are visiting positions.
 int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, const int *order, int n,
                       float thresh, int max_keep, unsigned long long *mask, int64_t *keep64, int *keep32,
-                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse)
+                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse, bool sparse_only)
 {
     if (max_keep <= 0 || max_keep > n) max_keep = n;
     if (n == 0) {
@@ -1449,11 +1483,13 @@ int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, c
     }
     // sparse path first; the dense kernels below are launched regardless and leave at once when it succeeded
     const int *skip = nullptr;
-    int rc = launch_sparse(boxes, areas, cls, order, n, thresh, max_keep, keep64, keep32, num_keep, sparse, st, &skip);
+    int rc = launch_sparse(boxes, areas, cls, order, n, thresh, max_keep, keep64, keep32, num_keep, sparse, st, &skip,
+                           sparse_only);
     if (rc != SLN_OK) return rc;
+    if (sparse_only && skip != nullptr) return SLN_OK;      // the caller retries with SLN_NMS_DENSE_ONLY on num_keep < 0
     if (!nms_two_stage(n) || stage == nullptr) {
         const int W = cdiv(n, 64);
-        rc = launch_mask(boxes, areas, cls, n, nullptr, W, thresh, mask, skip, st);
+        rc = launch_mask(boxes, areas, cls, n, nullptr, W, thresh, mask, skip, fix, st);
         if (rc != SLN_OK) return rc;
         return launch_scan(mask, order, n, nullptr, W, max_keep, nullptr, keep64, keep32, num_keep, fix, skip, st);
     }
@@ -1470,7 +1506,7 @@ int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, c
     int *numA = reinterpret_cast<int *>(p);
     int *n2 = numA + 1;
     // stage A: exact NMS of the first T boxes; survivors go straight to the output
-    rc = launch_mask(boxes, areas, cls, T, nullptr, T / 64, thresh, maskA, skip, st);
+    rc = launch_mask(boxes, areas, cls, T, nullptr, T / 64, thresh, maskA, skip, fix, st);
     if (rc != SLN_OK) return rc;
     rc = launch_scan(maskA, nullptr, T, nullptr, T / 64, max_keep, nullptr, nullptr, keepA, numA, fix, skip, st);
     if (rc != SLN_OK) return rc;
@@ -1484,7 +1520,8 @@ int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, c
     nms_emit_stageA_kernel<<<cdiv(T, 256), 256, 0, st>>>(keepA, numA, order, keep64, keep32, skip);
     SLN_LAUNCH_OK("nms_emit_stageA_kernel");
     // stage B on the compacted remainder, appended after the stage-A survivors
-    rc = launch_mask(boxes2, areas2, cls ? cls2 : nullptr, nm, n2, W2, thresh, mask, skip, st);
+    rc = launch_mask(boxes2, areas2, cls ? cls2 : nullptr, nm, n2, W2, thresh, mask, skip,
+                     static_cast<unsigned char *>(fix) + nms_fix_bytes(n), st);
     if (rc != SLN_OK) return rc;
     return launch_scan(mask, order2, nm, n2, W2, max_keep, numA, keep64, keep32, num_keep,
                        static_cast<unsigned char *>(fix) + nms_fix_bytes(n), skip, st);
@@ -1518,13 +1555,15 @@ extern "C" int sln_nms_ex(const float *dets, const int *class_ids, int n, float 
     NmsBuffers b;
     nms_carve(workspace, n, b);
     const bool try_sparse = !(flags & SLN_NMS_DENSE_ONLY) && n >= SP_MIN_N && n <= SP_MAX_N && thresh >= 0.05f;
-    SLN_CUDA_OK(cudaMemsetAsync(b.rank, 0, sizeof(int) * (size_t)n, st));
-    int rc = rank_sort_launch(dets + 4, 5, nullptr, n, b.rank, st);
+    // rank[] and the row-tile tickets are adjacent: one memset
+    SLN_CUDA_OK(cudaMemsetAsync(b.rank, 0, (size_t)(reinterpret_cast<unsigned char *>(b.tickets) - reinterpret_cast<unsigned char *>(b.rank)) +
+                                               sizeof(int) * (size_t)cdiv(n, RANK_ROWS), st));
+    RankGather ga{dets, class_ids, b.boxes, b.areas, b.cls, b.order, b.tickets};
+    int rc = rank_launch(dets + 4, 5, nullptr, n, b.rank, ga, st);
     if (rc != SLN_OK) return rc;
-    nms_gather_kernel<<<cdiv(n, 256), 256, 0, st>>>(dets, class_ids, b.rank, n, b.boxes, b.areas, b.cls, b.order);
-    SLN_LAUNCH_OK("nms_gather_kernel");
     rc = nms_sorted_launch(b.boxes, b.areas, class_ids ? b.cls : nullptr, b.order, n, thresh, max_keep, b.mask,
-                           keep, nullptr, num_keep, st, b.stage, b.fix, try_sparse ? b.sparse : nullptr);
+                           keep, nullptr, num_keep, st, b.stage, b.fix, try_sparse ? b.sparse : nullptr,
+                           (flags & SLN_NMS_SPARSE_ONLY) != 0);
     if (rc != SLN_OK) return rc;
     if (path_out && try_sparse)      // SparseHdr.status: 1 when the sparse path produced the result
         SLN_CUDA_OK(cudaMemcpyAsync(path_out, b.sparse, sizeof(int), cudaMemcpyDeviceToDevice, st));

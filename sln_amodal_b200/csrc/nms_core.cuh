@@ -13,6 +13,7 @@ struct NmsBuffers {
     int *cls;                      // [n] class id in visiting order (only if class-aware)
     int *order;                    // [n] original index of the box at each visiting position
     int *rank;                     // [n] visiting position of each original box
+    int *tickets;                  // [ceil(n/256)] row-tile tickets of the rank kernel's fused gather
     unsigned long long *mask;      // [n][W] IoU>=thresh bitmask, W = ceil(n/64)
     void *stage;                   // scratch of the two-stage pipeline (see nms.cu)
     void *fix;                     // scratch of the parallel fixed-point resolve
@@ -27,7 +28,7 @@ void nms_carve(void *ws, int n, NmsBuffers &b);
 //   keep64 / keep32  : either may be nullptr
 int nms_sorted_launch(const float4 *boxes, const float *areas, const int *cls, const int *order, int n,
                       float thresh, int max_keep, unsigned long long *mask, int64_t *keep64, int *keep32,
-                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse);
+                      int *num_keep, cudaStream_t st, void *stage, void *fix, void *sparse, bool sparse_only = false);
 
 // Total order used everywhere a "descending score, stable" sort is needed:
 // larger key first; NaN sorts as the largest value (torch.sort's convention);

@@ -17,9 +17,14 @@ from . import ops
 
 def pth_nms(dets, thresh):
     """dets has to be a CUDA tensor."""
-    keep, num = ops.nms_device(dets, thresh)
-    # one host read, like the reference's `keep[:num_out[0]]` (pth_nms.py:24)
-    return keep[: int(num.item())]
+    # the sparse pipeline alone; one host read, like the reference's `keep[:num_out[0]]` (pth_nms.py:24), which also
+    # tells whether the input was outside the sparse contract (k < 0): then the dense pipeline produces the result
+    keep, num = ops.nms_device(dets, thresh, sparse_only=True)
+    k = int(num.item())
+    if k < 0:
+        keep, num = ops.nms_device(dets, thresh, dense_only=True)
+        k = int(num.item())
+    return keep[:k]
 
 
 def nms(dets, thresh):
@@ -32,5 +37,9 @@ def batched_nms(boxes, scores, class_ids, thresh, max_keep=0):
     a box can only be suppressed by a higher-scoring box of the same class.  Returns the kept
     indices, score-descending across all classes."""
     dets = torch.cat((boxes.float(), scores.float().unsqueeze(1)), dim=1)
-    keep, num = ops.nms_device(dets, thresh, class_ids=class_ids, max_keep=max_keep)
-    return keep[: int(num.item())]
+    keep, num = ops.nms_device(dets, thresh, class_ids=class_ids, max_keep=max_keep, sparse_only=True)
+    k = int(num.item())
+    if k < 0:
+        keep, num = ops.nms_device(dets, thresh, class_ids=class_ids, max_keep=max_keep, dense_only=True)
+        k = int(num.item())
+    return keep[:k]

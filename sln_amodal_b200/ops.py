@@ -221,11 +221,13 @@ def pyramid_crop_forward(feature_maps, boxes, box_ind, level, crop_height, crop_
 # ---------------------------------------------------------------------------
 # NMS
 # ---------------------------------------------------------------------------
-def nms_device(dets, thresh, class_ids=None, max_keep=0, dense_only=False, return_path=False):
+def nms_device(dets, thresh, class_ids=None, max_keep=0, dense_only=False, return_path=False, sparse_only=False):
     """Greedy NMS fully on the device.  Returns (keep int64[n] padded, num_keep int32[1]) -- both
     device tensors, no host sync.  keep[:num_keep] are indices into dets, score-descending.
     dense_only forces the dense bit-matrix pipeline; return_path appends a device int32[1] that is 1 when
-    the sparse (binned) pipeline produced the result (include/sln_b200.h, sln_nms_ex)."""
+    the sparse (binned) pipeline produced the result (include/sln_b200.h, sln_nms_ex).
+    sparse_only launches the sparse pipeline alone: num_keep < 0 then means "outside its contract, call again with
+    dense_only=True" (what `nms()` does, which reads num_keep on the host anyway)."""
     _require_cuda(dets, "dets")
     dets = _f32c(dets)
     if dets.dim() != 2 or dets.shape[1] != 5:
@@ -241,7 +243,7 @@ def nms_device(dets, thresh, class_ids=None, max_keep=0, dense_only=False, retur
     with torch.cuda.device(dets.device):
         ws = _workspace(lib().sln_nms_workspace_bytes(n), dets.device)
         path = torch.zeros(1, dtype=torch.int32, device=dets.device) if return_path else None
-        check(lib().sln_nms_ex(ptr(dets), ptr(cls), n, float(thresh), int(max_keep), 1 if dense_only else 0,
+        check(lib().sln_nms_ex(ptr(dets), ptr(cls), n, float(thresh), int(max_keep), (1 if dense_only else 0) | (2 if sparse_only else 0),
                                ptr(keep), ptr(num), ptr(path), ptr(ws), ws.numel(), stream_ptr()), "sln_nms_ex")
     if n:
         _lib.count_launches(4)

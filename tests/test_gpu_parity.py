@@ -349,6 +349,31 @@ def test_nms_sparse_path_bails_out_to_dense():
         assert path == 0 and np.array_equal(got, oracle.nms(dets, thr))
 
 
+def test_nms_sparse_only_flag_and_host_retry():
+    """SLN_NMS_SPARSE_ONLY: the sparse pipeline alone; num_keep = -1 reports a bail-out, and the reference-facing
+    nms() retries with the dense pipeline."""
+    from sln_amodal_b200 import ops
+    from nms.nms_wrapper import nms
+    n = 5000
+    sc = synth.nms_scores(n, seed=51)
+    dets = np.concatenate([synth.nms_boxes(n, seed=50), sc[:, None]], 1)
+    want = oracle.nms(dets, 0.7)
+    keep, num = ops.nms_device(cuda(dets), 0.7, sparse_only=True)
+    assert int(num.item()) == want.size and np.array_equal(keep[: want.size].cpu().numpy(), want)
+    keep, num = ops.nms_device(cuda(dets), 0.7, sparse_only=True, max_keep=37)
+    assert int(num.item()) == 37 and np.array_equal(keep[:37].cpu().numpy(), want[:37])
+    # heavy duplication: outside the sparse contract
+    rng = np.random.default_rng(52)
+    dup = np.concatenate([(np.array([100, 100, 300, 300], np.float32) + rng.normal(0, 1.0, (n, 4))).astype(np.float32), sc[:, None]], 1)
+    keep, num = ops.nms_device(cuda(dup), 0.7, sparse_only=True)
+    assert int(num.item()) == -1
+    assert np.array_equal(nms(cuda(dup), 0.7).cpu().numpy(), oracle.nms(dup, 0.7))
+    # inputs the sparse pipeline never attempts run dense even with the flag
+    keep, num = ops.nms_device(cuda(dets), 0.01, sparse_only=True)
+    w2 = oracle.nms(dets, 0.01)
+    assert int(num.item()) == w2.size and np.array_equal(keep[: w2.size].cpu().numpy(), w2)
+
+
 def test_nms_sparse_chain_falls_back():
     """A 3000-long dependency chain exceeds the sparse resolve's round budget: dense takes over, still exact."""
     n = 3000

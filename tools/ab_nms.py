@@ -17,7 +17,7 @@ def t(fn, reps=20):
 out = {}
 for n, kind in ((12000, "rpn"), (12000, "uniform"), (6000, "rpn"), (1000, "rpn")):
     dets = torch.from_numpy(np.concatenate([synth.nms_boxes(n, seed=7, kind=kind), synth.nms_scores(n, seed=8)[:, None]], 1)).to(dev)
-    out["%%d %%s" %% (n, kind)] = t(lambda: ops.nms_device(dets, 0.7))
+    out["%%d %%s" %% (n, kind)] = (t(lambda: ops.nms_device(dets, 0.7, sparse_only=True)), t(lambda: ops.nms_device(dets, 0.7)))
 rng = np.random.default_rng(81)
 dets = torch.from_numpy(np.concatenate([synth.nms_boxes(12000, seed=9, rounded=True), synth.nms_scores(12000, seed=8)[:, None]], 1)).to(dev)
 cls = torch.from_numpy(rng.integers(1, 81, 12000).astype(np.int32)).to(dev)
