@@ -1099,13 +1099,11 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
 // Both rules only ever state final facts, so the sets can be read while other CTAs extend them and the fixed point
 // (every box decided) is the greedy result whatever the interleaving.  Ownership: 32-box word w belongs to CTA
 // w % SP_CLUSTER, one warp per word, lane = box; the warp builds the word's new bits with ballots and stores the
-// updated words into all SP_CLUSTER copies through DSMEM.  One hardware cluster barrier per round (termination is
-// only tested every SP_CHECK_EVERY rounds); a box costs work only while it is undecided, and its inline
+// updated words into all SP_CLUSTER copies through DSMEM.  One hardware cluster barrier per round; a box costs work only while it is undecided, and its inline
 // predecessor row sits in the owner's shared memory (one coalesced 32-byte load per box).
 constexpr int SP_WORDS = 2048;             // 32-bit words of KF / DF (n <= 65535)
 constexpr int SP_RES_ITEMS = SP_WORDS / SP_CLUSTER / (SP_RESOLVE_THREADS / 32);       // words per warp: 8
 constexpr int SP_CACHE_ITEMS = 2;          // items whose inline rows are cached in shared memory (64 KB each)
-constexpr int SP_CHECK_EVERY = 2;
 constexpr int SP_OV_CACHE = 8192;          // u16 overflow entries cached per resolve CTA (16 KB)
 
 // Branch-free scan of 8 inline entries: the sentinel 0xffff addresses bit 31 of word 2047 (box 65535 does not
@@ -1139,7 +1137,7 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
     const int crank = (int)cluster.block_rank();
     unsigned *KF = reinterpret_cast<unsigned *>(s_raw);         // [SP_WORDS]
     unsigned *DF = KF + SP_WORDS;                               // [SP_WORDS]
-    int *flags = reinterpret_cast<int *>(DF + SP_WORDS);        // [SP_CLUSTER] (+ padding)
+    int *flags = reinterpret_cast<int *>(DF + SP_WORDS);        // [2][SP_CLUSTER] (+ padding)
     unsigned short *ov = reinterpret_cast<unsigned short *>(flags + 32);          // [SP_OV_CACHE] overflow entries
     uint4 *rows = reinterpret_cast<uint4 *>(ov + SP_OV_CACHE);  // [cache items][SP_RESOLVE_THREADS][2]
     const int W32 = (n + 31) >> 5;
@@ -1249,19 +1247,16 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
                 }
             }
         }
-        const bool check = (round % SP_CHECK_EVERY) == SP_CHECK_EVERY - 1;
-        if (check) {
-            const int open = __syncthreads_or(undecided != 0u);
-            if (tid < SP_CLUSTER) *cluster.map_shared_rank(flags + crank, tid) = open;
-        }
+        // termination: every CTA tells every CTA whether it still has open boxes.  The flag words are double-buffered
+        // by round parity, so the single barrier of the round is enough: a buffer is rewritten two rounds later, after
+        // a barrier every CTA only reaches once it has read the old value.
+        const int open = __syncthreads_or(undecided != 0u);
+        if (tid < SP_CLUSTER) *cluster.map_shared_rank(flags + (round & 1) * SP_CLUSTER + crank, tid) = open;
         cluster.sync();
-        if (check) {
-            int glob = 0;
+        int glob = 0;
 #pragma unroll
-            for (int c = 0; c < SP_CLUSTER; ++c) glob |= flags[c];
-            if (!glob) { done = true; break; }     // uniform over the cluster
-            cluster.sync();                        // flags are rewritten only after everybody has read them
-        }
+        for (int c = 0; c < SP_CLUSTER; ++c) glob |= flags[(round & 1) * SP_CLUSTER + c];
+        if (!glob) { done = true; break; }         // uniform over the cluster
     }
     if (!done) return;
     // ---- emission in visiting order: every CTA scans the per-word popcounts itself (2 words per thread) and

@@ -1,8 +1,17 @@
-set -x
-for f in crop nms proposal semdist; do
+#!/bin/bash
+# One gpurun call that refreshes the ncu evidence under gpurun_out/ (summarised into profiles/ by
+# tools/summarize_ncu.py).  usage: bash tools/collect_profiles.sh [families...]   (default: all four)
+fams="${@:-crop nms proposal semdist}"
+for f in $fams; do
   ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/r01_launches_$f.csv python tools/prof_driver.py $f 1 > /dev/null 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:"crop_" -c 10 -o gpurun_out/r01_full_crop -f python tools/prof_driver.py crop 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"nms_|rank_" -c 8 -o gpurun_out/r01_full_nms -f python tools/prof_driver.py nms 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"layer_|edt_" -c 4 -o gpurun_out/r01_full_semdist -f python tools/prof_driver.py semdist 1 > /dev/null 2>&1
+for f in $fams; do
+  case $f in
+    crop) rx="crop_"; cnt=10;;
+    nms) rx="nms_|rank_"; cnt=8;;
+    semdist) rx="layer_|edt_"; cnt=4;;
+    *) continue;;
+  esac
+  ncu --set full --clock-control none --import-source on -k regex:"$rx" -c $cnt -o gpurun_out/r01_full_$f -f python tools/prof_driver.py $f 1 > /dev/null 2>&1
+done
 ls -la gpurun_out
