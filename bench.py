@@ -398,8 +398,24 @@ def side_metrics(dev, peak):
             ts.append(a.elapsed_time(b) * 1e3)
         return float(np.median(ts)), float(np.min(ts))
 
+    def graphed(fn):
+        """One call captured in a CUDA graph (the whole C-ABI path is stream-ordered: cluster and cooperative launches
+        included); replays measure device time without per-launch host latency."""
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keepalive = fn()
+        g.keepalive = keepalive
+        return g
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    out = {"nms": [], "note": "median / min over 20 runs, CUDA events; L2 flushed between runs"}
+    out = {"nms": [], "note": "median / min over 20 runs, CUDA events; L2 flushed between runs; us_graph = the same call "
+                              "captured once in a CUDA graph and replayed"}
     for n in (1000, 2000, 4000, 6000, 8000, 12000):
         for kind, thr in (("rpn", 0.7), ("uniform", 0.7)):
             dets = torch.from_numpy(np.concatenate([synth.nms_boxes(n, seed=7, kind=kind), synth.nms_scores(n, seed=8)[:, None]], 1)).to(dev)
@@ -409,8 +425,11 @@ def side_metrics(dev, peak):
             # num_keep < 0 and be retried dense); us_with_fallback = the sync-free call that also enqueues the dense kernels
             med, mn = time_us(lambda: ops.nms_device(dets, thr, sparse_only=sparse), flush=flush)
             med_fb, _ = time_us(lambda: ops.nms_device(dets, thr), flush=flush)
+            g = graphed(lambda: ops.nms_device(dets, thr, sparse_only=sparse))
+            med_g, _ = time_us(g.replay, flush=flush)
+            del g
             out["nms"].append({"n": n, "boxes": kind, "thresh": thr, "kept": int(num.item()), "us_median": round(med, 1),
-                               "us_min": round(mn, 1), "us_with_fallback": round(med_fb, 1),
+                               "us_min": round(mn, 1), "us_with_fallback": round(med_fb, 1), "us_graph": round(med_g, 1),
                                "pairs_per_s": round(n * (n - 1) / 2 / (med * 1e-6), 0),
                                "pipeline": "sparse" if sparse else "dense"})
     for K in (81, 61):
@@ -431,8 +450,13 @@ def side_metrics(dev, peak):
     fg = rng.permutation(np.linspace(0, 1, A)).astype(np.float32)
     probs = torch.from_numpy(np.stack([1 - fg, fg], 1).astype(np.float32)).to(dev)
     dl = torch.from_numpy((rng.standard_normal((A, 4)) * 0.5).astype(np.float32)).to(dev)
-    med, mn = time_us(lambda: ops.proposal_device(probs, dl, an, 1000, 0.7, (0.1, 0.1, 0.2, 0.2), (1024, 1024)), flush=flush)
-    out["proposal_layer"] = {"anchors": A, "pre_nms": 6000, "post_nms": 1000, "us_median": round(med, 1), "us_min": round(mn, 1)}
+    prop = lambda: ops.proposal_device(probs, dl, an, 1000, 0.7, (0.1, 0.1, 0.2, 0.2), (1024, 1024))
+    med, mn = time_us(prop, flush=flush)
+    g = graphed(prop)
+    med_g, _ = time_us(g.replay, flush=flush)
+    del g
+    out["proposal_layer"] = {"anchors": A, "pre_nms": 6000, "post_nms": 1000, "us_median": round(med, 1), "us_min": round(mn, 1),
+                             "us_graph": round(med_g, 1)}
     # sem-dist encode: config 4 = 16 images x 20 instances x L planes of 1024^2
     Bn, n_inst, L = 16, 20, 1
     labels = np.stack([synth.label_map(1024, 1024, n=n_inst, seed=2024 + (i % 4)) for i in range(4)])

@@ -409,6 +409,30 @@ def test_per_class_nms_matches_reference_loop(K, n):
     assert np.all(np.diff(scores[got]) <= 0)
 
 
+def test_nms_and_proposal_replay_from_a_cuda_graph():
+    """Every entry point is stream-ordered with no host round trip, so a call can be captured once in a CUDA graph
+    and replayed on new data in the same buffers (cluster launches, the cooperative launch and the memsets included)."""
+    from sln_amodal_b200 import ops
+    n = 3000
+    dets = cuda(np.concatenate([synth.nms_boxes(n, seed=60), synth.nms_scores(n, seed=61)[:, None]], 1))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.nms_device(dets, 0.7)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep, num = ops.nms_device(dets, 0.7)
+    for seed in (62, 63):                     # new boxes and scores in the captured input buffer
+        new = np.concatenate([synth.nms_boxes(n, seed=seed, kind="uniform" if seed == 63 else "rpn"),
+                              synth.nms_scores(n, seed=seed + 10)[:, None]], 1).astype(np.float32)
+        dets.copy_(torch.from_numpy(new))
+        g.replay()
+        torch.cuda.synchronize()
+        want = oracle.nms(new, 0.7)
+        assert int(num.item()) == want.size and np.array_equal(keep[: want.size].cpu().numpy(), want)
+
+
 # --------------------------------------------------------------------------- proposal layer
 class _Cfg:
     RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
