@@ -1239,6 +1239,9 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
                 }
             }
             const unsigned kb = __ballot_sync(0xffffffffu, kept), db = __ballot_sync(0xffffffffu, dead);
+            // (compute-sanitizer racecheck flags these stores against the reads in sp_scan8: that is the documented,
+            // deliberate overlap -- 32-bit words, a single writer per word, bits only ever set, and either value a
+            // reader can see is a valid state of the monotone sets)
             if (kb | db) {                         // the warp owns this word: plain stores of the updated words
                 const unsigned nk = KF[w] | kb, nd = DF[w] | db;
                 if (lane < SP_CLUSTER) {
