@@ -358,6 +358,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0:
         extra = side_metrics(dev, peak)
+        extra["head_pipeline"] = head_pipeline(dev, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -485,6 +486,86 @@ def side_metrics(dev, peak):
                   "frac_graph": round(by / med_g / 1e3 / peak, 4)}
     del flush
     return out
+
+
+# --------------------------------------------------------------------------------------
+# config 1: the detection-head hot path of one image through the drop-in operator API
+# --------------------------------------------------------------------------------------
+class _HeadCfg:
+    RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    IMAGE_SHAPE = np.array([1024, 1024, 3])
+    USE_NMS = True
+    DETECTION_MIN_CONFIDENCE = 0          # inference setting (amodal_train.py:571)
+    DETECTION_NMS_THRESHOLD = 0.3
+
+
+def head_pipeline(dev, cpu=True):
+    """BASELINE.json configs[0] without the (out-of-scope) convolutions: 261 888 anchors -> proposal_layer (top 6000,
+    NMS 0.7, 1000 ROIs) -> pyramid_roi_align 7x7 -> refine_detections (per-class NMS 0.3, K=81) -> pyramid_roi_align
+    14x14 on the detections, every call through the reference's own function signatures.  RPN / classifier outputs and
+    the FPN maps are synthetic.  Returns images/s on one GPU (images are independent: ranks shard them) and, on the host,
+    the same sequence through the oracle (numpy + the reference's C crop / NMS)."""
+    import torch
+    from sln_amodal_b200 import proposal_layer, pyramid_roi_align, refine_detections
+    A, K = 261888, 81
+    rng = np.random.default_rng(101)
+    anchors_np = synth.nms_boxes(A, seed=4, kind="rpn")
+    fg = rng.permutation(np.linspace(0, 1, A)).astype(np.float32)
+    probs_np = np.stack([1 - fg, fg], 1).astype(np.float32)
+    deltas_np = (rng.standard_normal((A, 4)) * 0.5).astype(np.float32)
+    maps_np = [rng.standard_normal((1, CHANNELS, s_, s_), dtype=np.float32) for s_ in LEVEL_SIDES]
+    cls_logits = rng.standard_normal((1000, K)).astype(np.float32) * 3.0
+    cls_probs_np = (np.exp(cls_logits) / np.exp(cls_logits).sum(1, keepdims=True)).astype(np.float32)
+    cls_deltas_np = (rng.standard_normal((1000, K, 4)) * 0.3).astype(np.float32)
+    window = (0.0, 0.0, 1024.0, 1024.0)
+    cfg = _HeadCfg()
+    t = lambda a: torch.from_numpy(a).to(dev)
+    anchors, probs, deltas = t(anchors_np), t(probs_np).unsqueeze(0), t(deltas_np).unsqueeze(0)
+    maps = [t(m).contiguous(memory_format=torch.channels_last) for m in maps_np]
+    cls_probs, cls_deltas = t(cls_probs_np), t(cls_deltas_np)
+
+    def one_image():
+        rois = proposal_layer([probs, deltas], 1000, 0.7, anchors, cfg)                     # [1,k,4]
+        k = rois.shape[1]
+        pooled = pyramid_roi_align([rois] + maps, 7, cfg.IMAGE_SHAPE)                       # classifier input
+        det, keep = refine_detections(rois[0], cls_probs[:k], cls_deltas[:k], window, cfg)
+        boxes = det[:, :4] / 1024.0
+        masks_in = pyramid_roi_align([boxes.unsqueeze(0)] + maps, 14, cfg.IMAGE_SHAPE)      # mask / sem-dist head input
+        return rois, pooled, det, masks_in
+
+    out = one_image()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        one_image()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts)) * 1e3
+    res = {"what": "proposal_layer -> pyramid_roi_align 7x7 -> refine_detections (per-class NMS) -> pyramid_roi_align 14x14, "
+                   "one 1024^2 image, 261888 anchors, K=81, synthetic RPN / classifier outputs (convolutions out of scope)",
+           "rois": int(out[0].shape[1]), "detections": int(out[2].shape[0]), "ms_per_image": round(ms, 3),
+           "images_per_s_per_gpu": round(1e3 / ms, 1), "timing": "host wall clock incl. the API's own host reads, median of 20"}
+    if cpu:
+        from oracle import oracle
+        t0 = time.perf_counter()
+        rois_c = oracle.proposal_layer(probs_np, deltas_np, anchors_np, 1000, 0.7)
+        pooled_c = oracle.pyramid_roi_align(rois_c, maps_np, 7)
+        kc = rois_c.shape[0]
+        det_c, _ = oracle.refine_detections(rois_c, cls_probs_np[:kc], cls_deltas_np[:kc], window, min_confidence=0, nms_threshold=0.3)
+        masks_c = oracle.pyramid_roi_align(det_c[:, :4] / np.float32(1024.0), maps_np, 14)
+        cpu_s = time.perf_counter() - t0
+        rois_g, det_g = out[0][0].cpu().numpy(), out[2].cpu().numpy()
+        checks = {"rois_max_abs_diff": float(np.abs(rois_c - rois_g).max()) if rois_c.shape == rois_g.shape else None,
+                  # (proposal boxes agree to 1 ulp -- exp through double vs torch's CPU exp -- so the crops are compared
+                  # by value, not bit for bit)
+                  "crops7_max_abs_diff": float(np.abs(pooled_c - out[1].contiguous().cpu().numpy()).max())
+                  if pooled_c.shape == tuple(out[1].shape) else None,
+                  "detections_identical": bool(det_c.shape == det_g.shape and np.array_equal(det_c, det_g)),
+                  "detections": [int(det_c.shape[0]), int(det_g.shape[0])]}
+        res["cpu_oracle"] = {"ms_per_image": round(cpu_s * 1e3, 1), "images_per_s": round(1.0 / cpu_s, 3), "cores": os.cpu_count(),
+                             "kind": "port (numpy) + the reference's C crop / NMS", "parity": checks}
+    return res
 
 
 # --------------------------------------------------------------------------------------
