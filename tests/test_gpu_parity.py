@@ -349,6 +349,28 @@ def test_nms_sparse_path_bails_out_to_dense():
         assert path == 0 and np.array_equal(got, oracle.nms(dets, thr))
 
 
+def test_nms_sparse_vs_dense_random_configs():
+    """Randomised sweep over sizes, thresholds, box statistics, score ties and class counts: whatever pipeline runs must
+    agree with the dense bit-matrix pipeline (and with nms.c on the smaller cases)."""
+    rng = np.random.default_rng(2025)
+    for case in range(24):
+        n = int(rng.choice([65, 66, 100, 257, 511, 1024, 3000, 7777]))
+        thr = float(rng.choice([0.05, 0.1, 0.3, 0.5, 0.7, 0.9]))
+        kind = "rpn" if rng.random() < 0.6 else "uniform"
+        boxes = synth.nms_boxes(n, seed=1000 + case, kind=kind, rounded=bool(rng.random() < 0.3))
+        if rng.random() < 0.25:                                   # collapse the centres onto a line / a point
+            boxes[:, [1, 3]] = boxes[:1, [1, 3]]
+        scores = synth.nms_scores(n, seed=2000 + case, ties=bool(rng.random() < 0.5))
+        dets = np.concatenate([boxes, scores[:, None]], 1).astype(np.float32)
+        cls = None
+        if rng.random() < 0.4:
+            cls = rng.integers(-3, int(rng.choice([2, 7, 200])), n).astype(np.int32)
+        got, dense, path = _nms_both_paths(dets, thr, cls=cls)
+        assert np.array_equal(got, dense), (case, n, thr, kind, path)
+        if cls is None and n <= 3000:
+            assert np.array_equal(got, oracle.nms(dets, thr)), (case, n, thr, kind, path)
+
+
 def test_nms_sparse_only_flag_and_host_retry():
     """SLN_NMS_SPARSE_ONLY: the sparse pipeline alone; num_keep = -1 reports a bail-out, and the reference-facing
     nms() retries with the dense pipeline."""
