@@ -105,6 +105,11 @@ SLN_API int sln_pyramid_crop_bwd(const float *grads, const float *boxes, const i
                          float *const *grad_maps_host, const int *H_host, const int *W_host, int n_levels,
                          int B, int flags, void *workspace, size_t workspace_bytes, void *stream);
 
+/* FPN level of each ROI (modal/modals.py:53-64): level_out[i] = clamp(round(4 + log2(sqrt(h*w) / (224 / sqrt(H*W)))),
+ * 2, 5) - 2, evaluated with the same fp32 operation sequence as the reference's torch expression on a CUDA tensor.
+ * boxes f32 [N,4] normalised (y1,x1,y2,x2), 16-byte aligned; level_out i32 [N] in 0..3 (P2..P5).               */
+SLN_API int sln_roi_levels(const float *boxes, int N, int image_h, int image_w, int *level_out, void *stream);
+
 /* Layout converters (f32).  src and dst must not alias.                            */
 SLN_API int sln_nchw_to_nhwc(const float *src, float *dst, int B, int C, int H, int W, void *stream);
 SLN_API int sln_nhwc_to_nchw(const float *src, float *dst, int B, int C, int H, int W, void *stream);
@@ -142,6 +147,20 @@ SLN_API int sln_nms(const float *dets, const int *class_ids, int n, float thresh
 SLN_API int sln_nms_ex(const float *dets, const int *class_ids, int n, float thresh, int max_keep, int flags,
                int64_t *keep, int *num_keep, int *path_out, void *workspace, size_t workspace_bytes,
                void *stream);
+
+/* ---- refine_detections, elementwise front --------------------------------- *
+ * Replaces the ~25 small torch kernels at the top of refine_detections (modal/Functions.py:453-493): per ROI the
+ * argmax class (first maximum), class-specific deltas * std_dev (:436-450), apply_box_deltas (:77-98), scale to
+ * pixels, clip to `window` (y1,x1,y2,x2) (:423-433), round half-to-even (:485) and the keep filter `class_id > 0 [and
+ * score >= min_confidence]` (min_confidence == 0 disables the score test, :490).
+ * rois f32 [N,4] normalised, probs f32 [N,K], deltas f32 [N,K,4]  ->  dets f32 [N,5] (y1,x1,y2,x2,score) and
+ * cls_nms i32 [N], ready for sln_nms: filtered-out boxes carry score -inf and a unique negative class, so the
+ * class-aware NMS returns them at the tail of its output; *n_excluded (device i32) counts them.  class_ids i32 [N] =
+ * the argmax class of every ROI.                                                                        */
+SLN_API int sln_refine_decode(const float *rois, const float *probs, const float *deltas, int N, int K,
+                      const float *std_dev_host, float img_h, float img_w, const float *window_host,
+                      float min_confidence, float *dets, int *cls_nms, int *class_ids, int *n_excluded,
+                      void *stream);
 
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:

@@ -31,11 +31,13 @@ PROTOTYPES = {
     "sln_pyramid_crop_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sln_pyramid_crop_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i,
                                   _i, _vp, _sz, _vp]),
+    "sln_roi_levels": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sln_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sln_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sln_nms_workspace_bytes": (_sz, [_i]),
     "sln_nms": (_i, [_vp, _vp, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "sln_nms_ex": (_i, [_vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sln_refine_decode": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_f), _f, _f, C.POINTER(_f), _f, _vp, _vp, _vp, _vp, _vp]),
     "sln_proposal_workspace_bytes": (_sz, [_i, _i]),
     "sln_proposal_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, C.POINTER(_f), _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "sln_layer_decode": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -1254,6 +1254,41 @@ extern "C" int sln_pyramid_crop_bwd(const float *grads, const float *boxes, cons
                          (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// FPN level of every ROI, modal/modals.py:53-64, with the exact fp32 operation sequence the reference's torch
+// expression evaluates on a CUDA tensor (`224.0 / t` is reciprocal-then-multiply in torch; sqrt, divide and log are the
+// IEEE / libdevice ones; round is half-to-even; the float -> int conversion maps NaN to 0 before the clamp):
+//   lvl = clamp(int(round(4 + log(sqrt(h*w) / (224 / sqrt(H*W))) / log(2))), 2, 5)          -> level_out = lvl - 2
+// One launch instead of the ten elementwise launches of the torch expression.
+namespace sln {
+__global__ void roi_level_kernel(const float *__restrict__ boxes, int N, float image_area, int *__restrict__ level_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 b = *reinterpret_cast<const float4 *>(boxes + 4 * (size_t)i);
+    const float h = __fsub_rn(b.z, b.x), w = __fsub_rn(b.w, b.y);
+    const float d = __fmul_rn(__fdiv_rn(1.f, __fsqrt_rn(image_area)), 224.f);
+    const float q = __fdiv_rn(__fsqrt_rn(__fmul_rn(h, w)), d);
+    const float v = __fadd_rn(__fdiv_rn(logf(q), logf(2.f)), 4.f);
+    const float r = rintf(v);
+    int lv = (r != r) ? 0 : (r >= 2147483648.f ? 2147483647 : (r <= -2147483648.f ? (-2147483647 - 1) : (int)r));
+    lv = lv < 2 ? 2 : (lv > 5 ? 5 : lv);
+    level_out[i] = lv - 2;
+}
+}  // namespace sln
+
+extern "C" int sln_roi_levels(const float *boxes, int N, int image_h, int image_w, int *level_out, void *stream)
+{
+    SLN_REQUIRE(N >= 0, SLN_ERR_ARG, "negative N");
+    if (N == 0) return SLN_OK;
+    SLN_REQUIRE(boxes && level_out, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15u) == 0, SLN_ERR_LAYOUT, "boxes must be 16-byte aligned");
+    // torch.tensor([float(H * W)], dtype=float32): the product in exact integer arithmetic, rounded once
+    const float area = (float)((double)image_h * (double)image_w);
+    sln::roi_level_kernel<<<cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, N, area, level_out);
+    SLN_LAUNCH_OK("roi_level_kernel");
+    return SLN_OK;
+}
+
 extern "C" int sln_nchw_to_nhwc(const float *src, float *dst, int B, int C, int H, int W, void *stream)
 {
     SLN_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, SLN_ERR_ARG, "negative size");

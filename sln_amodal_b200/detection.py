@@ -29,10 +29,36 @@ def apply_box_deltas(boxes, deltas):
     return torch.stack([y1, x1, y2, x2], dim=1)
 
 
+def _refine_detections_fused(rois, probs, deltas, window, config):
+    """CUDA path with USE_NMS: one decode launch (argmax, delta decode, clip, round, keep filter), one class-aware
+    NMS call, one host read.  Filtered-out boxes ride through the NMS with score -inf and a private class and are
+    dropped from the tail of its score-ordered output."""
+    from . import ops
+    height, width = config.IMAGE_SHAPE[:2]
+    std_dev = np.reshape(config.RPN_BBOX_STD_DEV, [4])
+    min_conf = float(config.DETECTION_MIN_CONFIDENCE or 0.0)
+    dets, cls_nms, class_ids, n_excl = ops.refine_decode_device(rois, probs, deltas, std_dev, (height, width), window, min_conf)
+    thr = config.DETECTION_NMS_THRESHOLD
+    keep, num = ops.nms_device(dets, thr, class_ids=cls_nms, sparse_only=True)
+    k, n_ex = (int(v) for v in torch.cat((num, n_excl)).tolist())          # the one host read
+    if k < 0:                                                               # outside the sparse NMS contract
+        keep, num = ops.nms_device(dets, thr, class_ids=cls_nms, dense_only=True)
+        k = int(num.item())
+    k -= n_ex
+    if k <= 0:
+        return [], []
+    keep = keep[:k]                                                         # score-descending (:538-546)
+    sel = dets[keep]
+    result = torch.cat((sel[:, :4], class_ids[keep].unsqueeze(1).float(), sel[:, 4:5]), dim=1)
+    return result, keep
+
+
 def refine_detections(rois, probs, deltas, window, config):
     """rois [N,4] normalised, probs [N,K], deltas [N,K,4], window (y1,x1,y2,x2) pixels
     -> (detections [M,6] (y1,x1,y2,x2,class_id,score), keep indices) or ([], [])."""
     dev = rois.device
+    if rois.is_cuda and config.USE_NMS and rois.shape[0] > 0:
+        return _refine_detections_fused(rois, probs, deltas, window, config)
     _, class_ids = torch.max(probs, dim=1)
     idx = torch.arange(class_ids.size(0), device=dev)
     class_scores = probs[idx, class_ids]

@@ -218,6 +218,20 @@ def pyramid_crop_forward(feature_maps, boxes, box_ind, level, crop_height, crop_
     return out
 
 
+def roi_levels_device(boxes, image_hw):
+    """FPN level index (0..3 for P2..P5) of each ROI, modals.py:53-64, in one launch.  boxes [N,4] normalised (CUDA)."""
+    _require_cuda(boxes, "boxes")
+    boxes = _f32c(boxes).view(-1, 4)
+    N = boxes.shape[0]
+    out = torch.empty(N, dtype=torch.int32, device=boxes.device)
+    if N:
+        with torch.cuda.device(boxes.device):
+            check(lib().sln_roi_levels(ptr(boxes), N, int(image_hw[0]), int(image_hw[1]), ptr(out), stream_ptr()),
+                  "sln_roi_levels")
+        _lib.count_launches(1)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # NMS
 # ---------------------------------------------------------------------------
@@ -250,6 +264,32 @@ def nms_device(dets, thresh, class_ids=None, max_keep=0, dense_only=False, retur
     if return_path:
         return keep, num, path
     return keep, num
+
+
+def refine_decode_device(rois, probs, deltas, std_dev, image_hw, window, min_confidence=0.0):
+    """Elementwise front of refine_detections in one launch (include/sln_b200.h, sln_refine_decode).
+    Returns (dets [N,5], cls_nms int32[N], class_ids int32[N], n_excluded int32[1]) on the device."""
+    _require_cuda(rois, "rois")
+    rois = _f32c(rois).view(-1, 4)
+    probs = _f32c(probs)
+    deltas = _f32c(deltas)
+    N, K = probs.shape
+    if rois.shape[0] != N or deltas.shape[0] != N or deltas.shape[1] != K:
+        raise _lib.SlnError("rois / probs / deltas disagree")
+    dev = rois.device
+    dets = torch.empty((N, 5), dtype=torch.float32, device=dev)
+    cls_nms = torch.empty(N, dtype=torch.int32, device=dev)
+    class_ids = torch.empty(N, dtype=torch.int32, device=dev)
+    n_excl = torch.empty(1, dtype=torch.int32, device=dev)
+    sd = (C.c_float * 4)(*[float(v) for v in std_dev])
+    win = (C.c_float * 4)(*[float(v) for v in window])
+    with torch.cuda.device(dev):
+        check(lib().sln_refine_decode(ptr(rois), ptr(probs), ptr(deltas), N, K, sd, float(image_hw[0]), float(image_hw[1]),
+                                      win, float(min_confidence), ptr(dets), ptr(cls_nms), ptr(class_ids), ptr(n_excl),
+                                      stream_ptr()), "sln_refine_decode")
+    if N:
+        _lib.count_launches(1)
+    return dets, cls_nms, class_ids, n_excl
 
 
 # ---------------------------------------------------------------------------

@@ -20,7 +20,10 @@ def log2(x):
 
 
 def roi_level(boxes, image_shape):
-    """modals.py:53-64.  boxes [N,4] normalised -> int32 [N] in {2,3,4,5}."""
+    """modals.py:53-64.  boxes [N,4] normalised -> int32 [N] in {2,3,4,5}.  CUDA tensors take one kernel launch
+    (ops.roi_levels_device: the same fp32 operation sequence); CPU tensors the reference's torch expression."""
+    if boxes.is_cuda and boxes.dtype == torch.float32:
+        return ops.roi_levels_device(boxes, image_shape) + 2
     y1, x1, y2, x2 = boxes.chunk(4, dim=1)
     h = y2 - y1
     w = x2 - x1

@@ -193,6 +193,32 @@ def test_pyramid_roi_align_matches_oracle():
             assert_close_rel(tm[i].grad.contiguous().cpu().numpy(), wb, rtol=2e-6)
 
 
+def test_roi_level_kernel_matches_the_torch_expression():
+    """sln_roi_levels against the reference's torch expression (modals.py:53-64) evaluated on the same CUDA tensor
+    and against the oracle (torch CPU), incl. zero-area, inverted and non-finite boxes."""
+    from sln_amodal_b200 import ops
+    from sln_amodal_b200.pyramid import log2
+    rng = np.random.default_rng(77)
+    boxes = synth.roi_boxes(20000, seed=78)
+    boxes[:50, 2] = boxes[:50, 0]                      # zero height
+    boxes[50:100, [0, 2]] = boxes[50:100, [2, 0]]      # inverted
+    boxes[100, 0] = np.nan
+    boxes[101, 3] = np.inf
+    # boxes sitting on level boundaries: sqrt(h*w) = 224 * 2^(k-4) / 1024
+    for j, k in enumerate((2.5, 3.5, 4.5)):
+        side = np.float32(224.0 * 2.0 ** (k - 4) / 1024.0)
+        boxes[200 + j] = (0.1, 0.1, np.float32(0.1) + side, np.float32(0.1) + side)
+    for hw in ((1024, 1024), (768, 1280)):
+        t = cuda(boxes)
+        y1, x1, y2, x2 = t.chunk(4, dim=1)
+        area = torch.tensor([float(hw[0] * hw[1])], dtype=torch.float32, device=dev())
+        want = (4 + log2(torch.sqrt((y2 - y1) * (x2 - x1)) / (224.0 / torch.sqrt(area)))).round().int().clamp(2, 5).view(-1) - 2
+        got = ops.roi_levels_device(t, hw)
+        assert torch.equal(got, want)
+        fin = np.isfinite(boxes).all(1)
+        assert np.array_equal(got.cpu().numpy()[fin] + 2, oracle.roi_levels(boxes[fin], hw))
+
+
 # --------------------------------------------------------------------------- NMS
 @pytest.mark.parametrize("kind", ["rpn", "uniform"])
 @pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 129, 1000, 2500, 6000])
@@ -453,6 +479,37 @@ def test_nms_and_proposal_replay_from_a_cuda_graph():
         torch.cuda.synchronize()
         want = oracle.nms(new, 0.7)
         assert int(num.item()) == want.size and np.array_equal(keep[: want.size].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("min_conf", [0.0, 0.3])
+@pytest.mark.parametrize("n,K", [(1000, 81), (300, 61), (40, 2)])
+def test_refine_detections_fused_matches_oracle(n, K, min_conf):
+    """The fused front (sln_refine_decode) + class-aware NMS against the oracle's restatement of
+    refine_detections (Functions.py:453-557): same detections, same order, same keep indices."""
+    from sln_amodal_b200 import refine_detections
+    rng = np.random.default_rng(n + K)
+    rois = synth.roi_boxes(n, seed=n)
+    logits = rng.standard_normal((n, K)).astype(np.float32) * 3.0
+    probs = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(np.float32)
+    probs[:5] = probs[0]                                   # exact ties across rows
+    probs[5, :] = np.float32(1.0 / K)                      # tie inside a row: first maximum wins (class 0 -> filtered)
+    deltas = (rng.standard_normal((n, K, 4)) * 0.3).astype(np.float32)
+    window = (0.0, 0.0, 1024.0, 1024.0)
+
+    class Cfg:
+        RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+        IMAGE_SHAPE = np.array([1024, 1024, 3])
+        USE_NMS = True
+        DETECTION_MIN_CONFIDENCE = min_conf
+        DETECTION_NMS_THRESHOLD = 0.3
+
+    want_det, want_keep = oracle.refine_detections(rois, probs, deltas, window, min_confidence=min_conf, nms_threshold=0.3)
+    det, keep = refine_detections(cuda(rois), cuda(probs), cuda(deltas), window, Cfg())
+    if want_keep.size == 0:
+        assert len(det) == 0
+        return
+    assert np.array_equal(keep.cpu().numpy(), want_keep)
+    assert np.array_equal(det.cpu().numpy(), want_det)
 
 
 # --------------------------------------------------------------------------- proposal layer
