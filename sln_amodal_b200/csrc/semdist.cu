@@ -850,9 +850,8 @@ extern "C" int sln_layer_decode(const uint64_t *label, int B, int H, int W, int 
     layer_decode_kernel<<<dim3((unsigned)((threads + 255) / 256), B), 256, 0, st>>>(
         reinterpret_cast<const unsigned long long *>(label), px, L, n_max, out, scratch);
     SLN_LAUNCH_OK("layer_decode_kernel");
-    // few CTAs per image: the clearing loop is grid-strided and almost never runs; 9472 CTAs that only read the
-    // flags and leave cost 19 us
-    layer_fixup_kernel<<<dim3(32, B), 256, 0, st>>>(scratch, px, L, n_max, out, n_obj);
+    // grid-strided clearing loop; one CTA per SM and image is enough to stream the zeros when an image needs them
+    layer_fixup_kernel<<<dim3(sm_count(), B), 256, 0, st>>>(scratch, px, L, n_max, out, n_obj);
     SLN_LAUNCH_OK("layer_fixup_kernel");
     return SLN_OK;
 }
