@@ -412,7 +412,8 @@ def side_metrics(dev, peak):
                 fn()
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads of the process (e.g. the NCCL watchdog under torchrun) may keep making CUDA calls
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             keepalive = fn()
         g.keepalive = keepalive
         return g
