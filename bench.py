@@ -359,6 +359,7 @@ def run_ours(args):
     if rank == 0:
         extra = side_metrics(dev, peak)
         extra["head_pipeline"] = head_pipeline(dev, cpu=(world == 1))
+        extra["detection_targets"] = detection_targets_metric(dev, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -566,6 +567,59 @@ def head_pipeline(dev, cpu=True):
                   "detections": [int(det_c.shape[0]), int(det_g.shape[0])]}
         res["cpu_oracle"] = {"ms_per_image": round(cpu_s * 1e3, 1), "images_per_s": round(1.0 / cpu_s, 3), "cores": os.cpu_count(),
                              "kind": "port (numpy) + the reference's C crop / NMS", "parity": checks}
+    return res
+
+
+def detection_targets_metric(dev, cpu=True):
+    """detection_target_layer for one training image (1000 proposals, 12 GT instances, L = 1, 1024^2
+    GT masks, 100 sampled ROIs -> 32x32 mask targets) through the reference's signature, next to the oracle on the host."""
+    import torch
+    from sln_amodal_b200 import detection_target_layer
+    rng = np.random.default_rng(303)
+    G_, N_ = 12, 1000
+    gt = np.zeros((G_, 4), np.float32)
+    masks = np.zeros((1, G_, 1024, 1024), np.uint8)
+    for i in range(G_):
+        h, w = rng.uniform(0.1, 0.4, 2)
+        y1, x1 = rng.uniform(0, 1 - h), rng.uniform(0, 1 - w)
+        gt[i] = (y1, x1, y1 + h, x1 + w)
+        masks[0, i, int(y1 * 1024):int((y1 + h) * 1024), int(x1 * 1024):int((x1 + w) * 1024)] = 1
+    jit = gt[rng.integers(0, G_, 240)] + rng.normal(0, 0.02, (240, 4)).astype(np.float32)       # 20 per GT, like config 5
+    props = np.clip(np.concatenate([jit, synth.roi_boxes(N_ - 240, seed=9)], 0), 0, 1).astype(np.float32)
+    ids = np.ones(G_, np.int32)
+
+    class Cfg:
+        BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+        TRAIN_ROIS_PER_IMAGE = 100
+        ROI_POSITIVE_RATIO = 0.7
+        MASK_SHAPE = [32, 32]
+        USE_MINI_MASK = False
+
+    t = lambda a: torch.from_numpy(a).to(dev)
+    args = (t(props).unsqueeze(0), t(ids).unsqueeze(0), t(gt).unsqueeze(0), t(masks).unsqueeze(0))
+    torch.manual_seed(5)
+    out = detection_target_layer(*args, Cfg())
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        detection_target_layer(*args, Cfg())
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts)) * 1e3
+    res = {"what": "detection_target_layer, 1000 proposals, 12 GT, L=1, 1024^2 masks -> 100 ROIs with 32x32 mask targets",
+           "ms_per_image": round(ms, 3), "images_per_s_per_gpu": round(1e3 / ms, 1), "sampled_rois": int(out[0].shape[0])}
+    if cpu:
+        from oracle import oracle
+        torch.manual_seed(5)
+        t0 = time.perf_counter()
+        ro, co, do, mo = oracle.detection_target_layer(props, ids, gt, masks)
+        cpu_s = time.perf_counter() - t0
+        res["cpu_oracle"] = {"ms_per_image": round(cpu_s * 1e3, 1), "cores": os.cpu_count(),
+                             "parity": {"rois_identical": bool(np.array_equal(ro, out[0].cpu().numpy())),
+                                        "class_ids_identical": bool(np.array_equal(co, out[1].cpu().numpy())),
+                                        "masks_identical": bool(np.array_equal(mo, out[3].cpu().numpy())),
+                                        "deltas_max_abs_diff": float(np.abs(do - out[2].cpu().numpy()).max()) if do.size else 0.0}}
     return res
 
 

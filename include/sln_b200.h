@@ -162,6 +162,25 @@ SLN_API int sln_refine_decode(const float *rois, const float *probs, const float
                       float min_confidence, float *dets, int *cls_nms, int *class_ids, int *n_excluded,
                       void *stream);
 
+/* ---- detection targets -------------------------------------- *
+ * sln_bbox_overlaps replaces bbox_overlaps (modal/Functions.py:184-218): IoU of boxes1 [N,4] against boxes2 [G,4]
+ * (y1,x1,y2,x2; no "+1"; every operation rounded separately; 0/0 -> NaN).  Any of the three outputs may be NULL:
+ * overlaps f32 [N,G]; iou_max f32 [N] and argmax i32 [N] = torch.max(overlaps, dim=1) (first maximum; NaN wins), the
+ * two reductions detection_target_layer takes from the matrix (:277, :297).
+ * sln_box_refinement replaces utils.box_refinement (utils.py:96-117) for M box pairs; std_dev_host (4 floats, may be
+ * NULL) additionally divides the result by BBOX_STD_DEV (Functions.py:309-313).                           */
+SLN_API int sln_bbox_overlaps(const float *boxes1, int N, const float *boxes2, int G, float *overlaps,
+                      float *iou_max, int *argmax, void *stream);
+SLN_API int sln_box_refinement(const float *box, const float *gt_box, int M, const float *std_dev_host, float *out,
+                       void *stream);
+
+/* Mask targets of detection_target_layer (modal/Functions.py:327-346): for positive ROI p,
+ * out[p, l] = round(crop_and_resize(gt_masks[l, assignment[p]], boxes[p], mh x mw, extrapolation 0)), sampled straight
+ * from the u8 planes (the reference converts every assigned 1-MiB plane to float first).  gt_masks u8 [L,G,H,W],
+ * assignment i32 [P], boxes f32 [P,4] normalised -> out f32 [P,L,mh,mw].  Same tap arithmetic as sln_crop_and_resize_fwd. */
+SLN_API int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, int W, const int *assignment,
+                     const float *boxes, int P, int mh, int mw, float *out, void *stream);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

@@ -352,6 +352,107 @@ def refine_detections(rois, probs, deltas, window, image_hw=(1024, 1024), std_de
 
 
 # ---------------------------------------------------------------------------
+# detection targets (modal/Functions.py:184-416, utils.py:96-117)
+# ---------------------------------------------------------------------------
+def bbox_overlaps(boxes1, boxes2):
+    """Functions.py:184-218: IoU matrix f32[N1,N2]; no +1 convention, one fp32 rounding per op, 0/0 -> NaN."""
+    b1, b2 = _f32(boxes1).reshape(-1, 4), _f32(boxes2).reshape(-1, 4)
+    y1 = np.maximum(b1[:, None, 0], b2[None, :, 0])
+    x1 = np.maximum(b1[:, None, 1], b2[None, :, 1])
+    y2 = np.minimum(b1[:, None, 2], b2[None, :, 2])
+    x2 = np.minimum(b1[:, None, 3], b2[None, :, 3])
+    zero = np.float32(0)
+    inter = np.maximum(x2 - x1, zero) * np.maximum(y2 - y1, zero)
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    union = a1[:, None] + a2[None, :] - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (inter / union).astype(np.float32)
+
+
+def box_refinement(box, gt_box):
+    """utils.py:96-117 (log from torch CPU)."""
+    import torch
+    box, gt = _f32(box).reshape(-1, 4), _f32(gt_box).reshape(-1, 4)
+    half = np.float32(0.5)
+    h, w = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
+    cy, cx = box[:, 0] + half * h, box[:, 1] + half * w
+    gh, gw = gt[:, 2] - gt[:, 0], gt[:, 3] - gt[:, 1]
+    gcy, gcx = gt[:, 0] + half * gh, gt[:, 1] + half * gw
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dy, dx = (gcy - cy) / h, (gcx - cx) / w
+        dh = torch.log(torch.from_numpy(gh / h)).numpy()
+        dw = torch.log(torch.from_numpy(gw / w)).numpy()
+    return np.stack([dy, dx, dh, dw], 1).astype(np.float32)
+
+
+def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, train_rois=100, positive_ratio=0.7,
+                           bbox_std_dev=(0.1, 0.1, 0.2, 0.2), mask_shape=(32, 32)):
+    """Functions.py:223-416 for one image, USE_MINI_MASK off.  proposals f32[N,4], gt_class_ids i32[G],
+    gt_boxes f32[G,4], gt_masks u8[L,G,H,W] -> (rois f32[R,4], class_ids i32[R], deltas f32[R,4],
+    masks f32[R,L,mh,mw]); empty arrays when nothing is sampled.  Sampling draws torch.randperm from the CPU
+    generator exactly where the reference does (:288, :361)."""
+    import torch
+    props = _f32(proposals).reshape(-1, 4)
+    ids = np.asarray(gt_class_ids).astype(np.int32).reshape(-1)
+    gtb = _f32(gt_boxes).reshape(-1, 4)
+    masks = np.asarray(gt_masks)
+    n = props.shape[0]
+    if (ids < 0).any():                                                   # COCO crowds :253-267
+        crowd = np.nonzero(ids < 0)[0]
+        keep = np.nonzero(ids > 0)[0]
+        crowd_boxes = gtb[crowd]
+        ids, gtb, masks = ids[keep], gtb[keep], masks[:, keep]
+        no_crowd = np.nanmax(np.where(np.isnan(bbox_overlaps(props, crowd_boxes)), np.inf, bbox_overlaps(props, crowd_boxes)), 1) < np.float32(0.001)
+    else:
+        no_crowd = np.ones(n, bool)
+    ov = bbox_overlaps(props, gtb)                                        # :274
+    ovm = np.where(np.isnan(ov), np.inf, ov)                              # torch.max propagates NaN as the maximum
+    iou_max = ovm.max(1)
+    pos_bool = iou_max >= np.float32(0.5)                                 # NaN >= 0.5 is False in torch; inf stands for NaN here
+    pos_bool &= ~np.isnan(ov).any(1)
+    L = masks.shape[0]
+    mh, mw = mask_shape
+    positive_count = 0
+    if pos_bool.any():                                                    # :284-346
+        pos_idx = np.nonzero(pos_bool)[0]
+        want = int(train_rois * positive_ratio)
+        perm = torch.randperm(pos_idx.size).numpy()[:want]
+        pos_idx = pos_idx[perm]
+        positive_count = pos_idx.size
+        pos_rois = props[pos_idx]
+        assign = ovm[pos_idx].argmax(1)                                   # first maximum
+        roi_gt = gtb[assign]
+        roi_cls = ids[assign]
+        deltas = box_refinement(pos_rois, roi_gt) / np.asarray(bbox_std_dev, np.float32).reshape(1, 4)
+        roi_masks = masks[:, assign]                                      # [L,P,H,W]
+        box_ids = np.arange(positive_count, dtype=np.int32)
+        tm = np.stack([crop_and_resize_fwd(roi_masks[i][:, None].astype(np.float32), pos_rois, box_ids, mh, mw, 0.0)
+                       for i in range(L)], 1)                             # [P,L,1,mh,mw]
+        tmasks = np.rint(tm[:, :, 0]).astype(np.float32)                  # torch.round: half to even
+    neg_bool = (iou_max < np.float32(0.5)) & ~np.isnan(ov).any(1) & no_crowd   # :351-352
+    negative_count = 0
+    if positive_count > 0 and neg_bool.any():                             # :354-364 (`.size()` is always truthy)
+        neg_idx = np.nonzero(neg_bool)[0]
+        r = 1.0 / positive_ratio
+        negative_count = int(r * positive_count - positive_count)
+        perm = torch.randperm(neg_idx.size).numpy()[:negative_count]
+        neg_idx = neg_idx[perm]
+        negative_count = neg_idx.size
+        neg_rois = props[neg_idx]
+    if positive_count > 0 and negative_count > 0:                         # :370-384
+        rois = np.concatenate([pos_rois, neg_rois], 0)
+        cls = np.concatenate([roi_cls, np.zeros(negative_count, np.int32)])
+        deltas = np.concatenate([deltas, np.zeros((negative_count, 4), np.float32)], 0)
+        tmasks = np.concatenate([tmasks, np.zeros((negative_count, L, mh, mw), np.float32)], 0)
+        return rois, cls, deltas.astype(np.float32), tmasks
+    if positive_count > 0:
+        return pos_rois, roi_cls, deltas.astype(np.float32), tmasks
+    return (np.zeros((0, 4), np.float32), np.zeros(0, np.int32), np.zeros((0, 4), np.float32),
+            np.zeros((0, L, mh, mw), np.float32))
+
+
+# ---------------------------------------------------------------------------
 # the reference's own C, unmodified (oracle/_ref)
 # ---------------------------------------------------------------------------
 class _TH(C.Structure):

@@ -88,3 +88,145 @@ extern "C" int sln_refine_decode(const float *rois, const float *probs, const fl
     SLN_LAUNCH_OK("refine_decode_kernel");
     return SLN_OK;
 }
+
+// ---------------------------------------------------------------------------
+// detection targets -- IoU matching and box refinement
+// ---------------------------------------------------------------------------
+// bbox_overlaps (modal/Functions.py:184-218): IoU of every box of set 1 against every box of set 2, no "+1"
+// convention, each operation rounded separately, 0/0 -> NaN like the torch expression.  The reference materialises
+// two [N*G,4] repeat tensors and ~20 elementwise kernels; here one thread walks the G boxes of a row and optionally
+// also produces what detection_target_layer wants from the matrix: the row maximum and its first index
+// (torch.max semantics: a NaN in the row is the maximum).
+namespace sln {
+
+__global__ void __launch_bounds__(128)
+bbox_overlaps_kernel(const float *__restrict__ b1, int N, const float *__restrict__ b2, int G,
+                     float *__restrict__ overlaps, float *__restrict__ iou_max, int *__restrict__ argmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 a = *reinterpret_cast<const float4 *>(b1 + 4 * (size_t)i);          // (y1, x1, y2, x2)
+    const float area1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    float best = -INFINITY;
+    int arg = 0;
+    bool best_nan = false;
+    for (int j = 0; j < G; ++j) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(b2) + j);
+        const float y1 = fmaxf(a.x, g.x), x1 = fmaxf(a.y, g.y), y2 = fminf(a.z, g.z), x2 = fminf(a.w, g.w);
+        // torch.max(x2 - x1, zeros): NaN-propagating in torch, fmaxf is not -- handled through `inter != inter` below
+        const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1);
+        float inter = __fmul_rn(dx > 0.f ? dx : (dx != dx ? dx : 0.f), dy > 0.f ? dy : (dy != dy ? dy : 0.f));
+        const float area2 = __fmul_rn(__fsub_rn(g.z, g.x), __fsub_rn(g.w, g.y));
+        const float uni = __fsub_rn(__fadd_rn(area1, area2), inter);
+        const float v = __fdiv_rn(inter, uni);
+        if (overlaps) overlaps[(size_t)i * G + j] = v;
+        const bool vnan = v != v;
+        if (!best_nan && (vnan || v > best)) { best = v; arg = j; best_nan = vnan; }
+    }
+    if (iou_max) iou_max[i] = best;
+    if (argmax) argmax[i] = arg;
+}
+
+// utils.box_refinement (utils.py:96-117), optionally divided by BBOX_STD_DEV (Functions.py:309-313)
+__global__ void __launch_bounds__(128)
+box_refinement_kernel(const float *__restrict__ box, const float *__restrict__ gt, int M, int use_std, float s0,
+                      float s1, float s2, float s3, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float4 b = *reinterpret_cast<const float4 *>(box + 4 * (size_t)i);
+    const float4 g = *reinterpret_cast<const float4 *>(gt + 4 * (size_t)i);
+    const float h = __fsub_rn(b.z, b.x), w = __fsub_rn(b.w, b.y);
+    const float cy = __fadd_rn(b.x, __fmul_rn(0.5f, h)), cx = __fadd_rn(b.y, __fmul_rn(0.5f, w));
+    const float gh = __fsub_rn(g.z, g.x), gw = __fsub_rn(g.w, g.y);
+    const float gcy = __fadd_rn(g.x, __fmul_rn(0.5f, gh)), gcx = __fadd_rn(g.y, __fmul_rn(0.5f, gw));
+    float dy = __fdiv_rn(__fsub_rn(gcy, cy), h), dx = __fdiv_rn(__fsub_rn(gcx, cx), w);
+    float dh = (float)log((double)__fdiv_rn(gh, h)), dw = (float)log((double)__fdiv_rn(gw, w));   // within 1 ulp of torch's CPU log
+    if (use_std) { dy = __fdiv_rn(dy, s0); dx = __fdiv_rn(dx, s1); dh = __fdiv_rn(dh, s2); dw = __fdiv_rn(dw, s3); }
+    *reinterpret_cast<float4 *>(out + 4 * (size_t)i) = make_float4(dy, dx, dh, dw);
+}
+
+}  // namespace sln
+
+extern "C" int sln_bbox_overlaps(const float *boxes1, int N, const float *boxes2, int G, float *overlaps,
+                                 float *iou_max, int *argmax, void *stream)
+{
+    SLN_REQUIRE(N >= 0 && G >= 0, SLN_ERR_ARG, "negative size");
+    if (N == 0) return SLN_OK;
+    SLN_REQUIRE(boxes1 && (boxes2 || G == 0), SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE((reinterpret_cast<uintptr_t>(boxes1) & 15u) == 0 && (reinterpret_cast<uintptr_t>(boxes2) & 15u) == 0,
+                SLN_ERR_LAYOUT, "boxes must be 16-byte aligned");
+    sln::bbox_overlaps_kernel<<<sln::cdiv(N, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(boxes1, N, boxes2, G,
+                                                                                              overlaps, iou_max, argmax);
+    SLN_LAUNCH_OK("bbox_overlaps_kernel");
+    return SLN_OK;
+}
+
+extern "C" int sln_box_refinement(const float *box, const float *gt_box, int M, const float *std_dev_host, float *out,
+                                  void *stream)
+{
+    SLN_REQUIRE(M >= 0, SLN_ERR_ARG, "negative size");
+    if (M == 0) return SLN_OK;
+    SLN_REQUIRE(box && gt_box && out, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE(((reinterpret_cast<uintptr_t>(box) | reinterpret_cast<uintptr_t>(gt_box) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                SLN_ERR_LAYOUT, "box / gt_box / out must be 16-byte aligned");
+    const float *s = std_dev_host;
+    sln::box_refinement_kernel<<<sln::cdiv(M, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        box, gt_box, M, s != nullptr, s ? s[0] : 1.f, s ? s[1] : 1.f, s ? s[2] : 1.f, s ? s[3] : 1.f, out);
+    SLN_LAUNCH_OK("box_refinement_kernel");
+    return SLN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// mask targets (SURVEY 8a row A12 inside detection_target_layer, Functions.py:327-346)
+// ---------------------------------------------------------------------------
+// The reference gathers the assigned GT masks ([L,P,H,W] u8), converts every 1-MiB plane to float (280 MB per layer at
+// P = 70), crops each with crop_and_resize and rounds.  Only mh*mw samples of a plane are ever read: one launch gathers
+// by `assignment`, samples the u8 plane directly with the crop's exact tap arithmetic (common.cuh: axis_tap / lerp2;
+// u8 -> f32 is exact) and rounds half-to-even.  out f32 [P, L, mh, mw].
+namespace sln {
+
+__global__ void __launch_bounds__(256)
+mask_targets_kernel(const unsigned char *__restrict__ masks, int L, int G, int H, int W, const int *__restrict__ assignment,
+                    const float *__restrict__ boxes, int P, int mh, int mw, float *__restrict__ out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P * L * mh * mw;
+    if (idx >= total) return;
+    const int x = (int)(idx % mw);
+    const int y = (int)((idx / mw) % mh);
+    const int l = (int)((idx / ((long long)mw * mh)) % L);
+    const int p = (int)(idx / ((long long)mw * mh * L));
+    const int gidx = assignment[p];
+    float v = 0.f;                                                        // extrapolation value 0 (:339)
+    if (gidx >= 0 && gidx < G) {
+        const float y1 = boxes[4 * p + 0], x1 = boxes[4 * p + 1], y2 = boxes[4 * p + 2], x2 = boxes[4 * p + 3];
+        const Tap ty = axis_tap(y1, y2, axis_scale(y1, y2, H, mh), H, mh, y);
+        const Tap tx = axis_tap(x1, x2, axis_scale(x1, x2, W, mw), W, mw, x);
+        if (ty.lo != INVALID_TAP && tx.lo != INVALID_TAP) {
+            const unsigned char *pl = masks + ((size_t)l * G + gidx) * H * W;
+            const int yh = ty.lo + (ty.lerp != 0.f), xh = tx.lo + (tx.lerp != 0.f);
+            const float tl = (float)pl[(size_t)ty.lo * W + tx.lo], tr = (float)pl[(size_t)ty.lo * W + xh];
+            const float bl = (float)pl[(size_t)yh * W + tx.lo], br = (float)pl[(size_t)yh * W + xh];
+            v = lerp2(tl, tr, bl, br, tx.lerp, ty.lerp);
+        }
+    }
+    out[idx] = rintf(v);                                                  // torch.round (:346)
+}
+
+}  // namespace sln
+
+extern "C" int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, int W, const int *assignment,
+                                const float *boxes, int P, int mh, int mw, float *out, void *stream)
+{
+    SLN_REQUIRE(L >= 0 && G >= 0 && H >= 0 && W >= 0 && P >= 0 && mh >= 1 && mw >= 1, SLN_ERR_ARG, "bad size");
+    const long long total = (long long)P * L * mh * mw;
+    if (total == 0) return SLN_OK;
+    SLN_REQUIRE(gt_masks && assignment && boxes && out, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE(H > 0 && W > 0 && H <= 32767 && W <= 32767, SLN_ERR_ARG, "mask side outside [1, 32767]");
+    SLN_REQUIRE((total + 255) / 256 < (1ll << 31), SLN_ERR_ARG, "too many target samples");
+    sln::mask_targets_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gt_masks, L, G, H, W, assignment, boxes, P, mh, mw, out);
+    SLN_LAUNCH_OK("mask_targets_kernel");
+    return SLN_OK;
+}

@@ -24,7 +24,7 @@ def install(model_module=None, functions_module=None, modals_module=None, datase
     AmodalDataset (gets the device layer decoder as load_layer2).  channels_last_model: an
     nn.Module to convert to channels_last so FPN outputs feed the NHWC kernels natively.
     Returns the list of rebinding performed (for logging / tests)."""
-    from . import proposal, pyramid, semdist, detection
+    from . import proposal, pyramid, semdist, detection, targets
 
     model_module = model_module or sys.modules.get("model")
     functions_module = functions_module or sys.modules.get("modal.Functions")
@@ -39,6 +39,8 @@ def install(model_module=None, functions_module=None, modals_module=None, datase
     for mod in (model_module, functions_module):
         bind(mod, "proposal_layer", proposal.proposal_layer)
         bind(mod, "refine_detections", detection.refine_detections)
+        bind(mod, "detection_target_layer", targets.detection_target_layer)
+        bind(mod, "bbox_overlaps", targets.bbox_overlaps)
         bind(mod, "pyramid_roi_align_image", pyramid.pyramid_roi_align_image)
     for mod in (modals_module, model_module):
         bind(mod, "pyramid_roi_align", pyramid.pyramid_roi_align)

@@ -292,6 +292,61 @@ def refine_decode_device(rois, probs, deltas, std_dev, image_hw, window, min_con
     return dets, cls_nms, class_ids, n_excl
 
 
+def bbox_overlaps_device(boxes1, boxes2, matrix=True, reduce=False):
+    """IoU of boxes1 [N,4] against boxes2 [G,4] (include/sln_b200.h, sln_bbox_overlaps).
+    Returns the [N,G] matrix, or (matrix | None, iou_max [N], argmax int32 [N]) with reduce=True."""
+    _require_cuda(boxes1, "boxes1")
+    b1 = _f32c(boxes1).view(-1, 4)
+    b2 = _f32c(boxes2).view(-1, 4).to(b1.device)
+    N, G = b1.shape[0], b2.shape[0]
+    ov = torch.empty((N, G), dtype=torch.float32, device=b1.device) if matrix else None
+    mx = torch.empty(N, dtype=torch.float32, device=b1.device) if reduce else None
+    am = torch.empty(N, dtype=torch.int32, device=b1.device) if reduce else None
+    if N:
+        with torch.cuda.device(b1.device):
+            check(lib().sln_bbox_overlaps(ptr(b1), N, ptr(b2), G, ptr(ov), ptr(mx), ptr(am), stream_ptr()), "sln_bbox_overlaps")
+        _lib.count_launches(1)
+    return (ov, mx, am) if reduce else ov
+
+
+def box_refinement_device(box, gt_box, std_dev=None):
+    """utils.box_refinement for M box pairs, optionally divided by std_dev (sln_box_refinement)."""
+    _require_cuda(box, "box")
+    b = _f32c(box).view(-1, 4)
+    g = _f32c(gt_box).view(-1, 4)
+    if g.shape != b.shape:
+        raise _lib.SlnError("box and gt_box disagree")
+    out = torch.empty_like(b)
+    sd = (C.c_float * 4)(*[float(v) for v in std_dev]) if std_dev is not None else None
+    if b.shape[0]:
+        with torch.cuda.device(b.device):
+            check(lib().sln_box_refinement(ptr(b), ptr(g), b.shape[0], sd, ptr(out), stream_ptr()), "sln_box_refinement")
+        _lib.count_launches(1)
+    return out
+
+
+def mask_targets_device(gt_masks, assignment, boxes, mh, mw):
+    """round(crop_and_resize(gt_masks[l, assignment[p]], boxes[p])) for every layer l and positive ROI p, straight from
+    u8 / bool masks [L,G,H,W] (sln_mask_targets).  Returns f32 [P,L,mh,mw]."""
+    _require_cuda(gt_masks, "gt_masks")
+    if gt_masks.dtype == torch.bool:
+        gt_masks = gt_masks.view(torch.uint8)
+    if gt_masks.dtype != torch.uint8 or gt_masks.dim() != 4:
+        raise _lib.SlnError("gt_masks must be uint8 / bool [L,G,H,W]")
+    gt_masks = gt_masks.contiguous()
+    L, G, H, W = gt_masks.shape
+    boxes = _f32c(boxes).view(-1, 4)
+    assignment = _i32c(assignment).view(-1)
+    P = boxes.shape[0]
+    out = torch.empty((P, L, int(mh), int(mw)), dtype=torch.float32, device=gt_masks.device)
+    if out.numel():
+        with torch.cuda.device(gt_masks.device):
+            check(lib().sln_mask_targets(ptr(gt_masks), L, G, H, W, ptr(assignment), ptr(boxes), P, int(mh), int(mw), ptr(out),
+                                         stream_ptr()), "sln_mask_targets")
+        _lib.count_launches(1)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # proposal_layer
 # ---------------------------------------------------------------------------

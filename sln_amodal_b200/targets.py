@@ -1,0 +1,108 @@
+"""Drop-in for bbox_overlaps / detection_target_layer (reference modal/Functions.py:184-416) and
+utils.box_refinement (utils.py:96-117) -- SURVEY.md section 8(f), row 1.
+
+Same signatures and return conventions as the reference.  The IoU matching (two [N*G,4] repeat tensors and ~20
+elementwise kernels in the reference) and the box refinement are one launch each; the mask targets go through this
+repo's CropAndResizeFunction (A12).  Subsampling draws `torch.randperm` from the CPU generator at the same two places
+as the reference (:288, :361), so with the same seed the sampled ROIs are the same ones.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .crop_and_resize import CropAndResizeFunction
+
+
+def bbox_overlaps(boxes1, boxes2):
+    """IoU overlaps [N1,N2] between two sets of (y1,x1,y2,x2) boxes (Functions.py:184-218)."""
+    return ops.bbox_overlaps_device(boxes1, boxes2)
+
+
+def box_refinement(box, gt_box):
+    """Refinement (dy, dx, log dh, log dw) that maps box onto gt_box (utils.py:96-117)."""
+    return ops.box_refinement_device(box, gt_box)
+
+
+def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
+    """proposals [1,N,4] normalised, gt_class_ids [1,G], gt_boxes [1,G,4] normalised, gt_masks [1,L,G,H,W]
+    -> (rois [R,4], roi_gt_class_ids [R], deltas [R,4], masks [R,L,mh,mw]); empty tensors when nothing is sampled
+    (Functions.py:223-416, batch 1 like the reference)."""
+    dev = proposals.device
+    proposals = proposals.squeeze(0).float().contiguous()
+    gt_class_ids = gt_class_ids.squeeze(0).to(dev)
+    gt_boxes = gt_boxes.squeeze(0).float().to(dev)
+    gt_masks = gt_masks.squeeze(0)
+    n = proposals.shape[0]
+
+    if bool((gt_class_ids < 0).any()):                                        # COCO crowds, :253-267
+        crowd_ix = torch.nonzero(gt_class_ids < 0)[:, 0]
+        non_crowd_ix = torch.nonzero(gt_class_ids > 0)[:, 0]
+        crowd_boxes = gt_boxes[crowd_ix]
+        gt_class_ids = gt_class_ids[non_crowd_ix]
+        gt_boxes = gt_boxes[non_crowd_ix]
+        gt_masks = gt_masks[:, non_crowd_ix.to(gt_masks.device)]
+        _, crowd_iou_max, _ = ops.bbox_overlaps_device(proposals, crowd_boxes, matrix=False, reduce=True)
+        no_crowd_bool = crowd_iou_max < 0.001
+    else:
+        no_crowd_bool = torch.ones(n, dtype=torch.bool, device=dev)
+
+    # overlaps [proposals, gt_boxes] reduced on the fly: row maximum and its (first) index, :274-277, :297
+    _, roi_iou_max, roi_argmax = ops.bbox_overlaps_device(proposals, gt_boxes, matrix=False, reduce=True)
+    positive_roi_bool = roi_iou_max >= 0.5
+    L = gt_masks.shape[0]
+    mh, mw = int(config.MASK_SHAPE[0]), int(config.MASK_SHAPE[1])
+    positive_count = 0
+    if bool(positive_roi_bool.any()):
+        positive_indices = torch.nonzero(positive_roi_bool)[:, 0]
+        want = int(config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO)
+        rand_idx = torch.randperm(positive_indices.shape[0])[:want].to(dev)   # CPU generator, like the reference
+        positive_indices = positive_indices[rand_idx]
+        positive_count = positive_indices.shape[0]
+        positive_rois = proposals[positive_indices]
+        assignment = roi_argmax[positive_indices].long()
+        roi_gt_boxes = gt_boxes[assignment]
+        roi_gt_class_ids = gt_class_ids[assignment]
+        deltas = ops.box_refinement_device(positive_rois, roi_gt_boxes, np.reshape(config.BBOX_STD_DEV, [4]))
+        boxes = positive_rois
+        if config.USE_MINI_MASK:                                              # :316-325
+            y1, x1, y2, x2 = positive_rois.chunk(4, dim=1)
+            gt_y1, gt_x1, gt_y2, gt_x2 = roi_gt_boxes.chunk(4, dim=1)
+            gt_h, gt_w = gt_y2 - gt_y1, gt_x2 - gt_x1
+            boxes = torch.cat([(y1 - gt_y1) / gt_h, (x1 - gt_x1) / gt_w, (y2 - gt_y1) / gt_h, (x2 - gt_x1) / gt_w], dim=1)
+        if gt_masks.is_cuda and gt_masks.dtype in (torch.uint8, torch.bool):
+            # gather by assignment + crop + round in one launch, sampling the u8 planes directly (:327-346)
+            masks = ops.mask_targets_device(gt_masks, assignment, boxes, mh, mw)
+        else:
+            roi_masks = gt_masks[:, assignment.to(gt_masks.device)].to(dev)   # [L,P,H,W]
+            box_ids = torch.arange(positive_count, dtype=torch.int32, device=dev)
+            crop = CropAndResizeFunction(mh, mw, 0)
+            masks = torch.stack([crop(roi_masks[i].unsqueeze(1).float(), boxes, box_ids).detach() for i in range(L)], dim=1)
+            masks = torch.round(masks.squeeze(2))                             # :346
+
+    negative_roi_bool = (roi_iou_max < 0.5) & no_crowd_bool                   # :351-352
+    negative_count = 0
+    if positive_count > 0 and bool(negative_roi_bool.any()):
+        negative_indices = torch.nonzero(negative_roi_bool)[:, 0]
+        r = 1.0 / config.ROI_POSITIVE_RATIO
+        negative_count = int(r * positive_count - positive_count)
+        rand_idx = torch.randperm(negative_indices.shape[0])[:negative_count].to(dev)
+        negative_indices = negative_indices[rand_idx]
+        negative_count = negative_indices.shape[0]
+        negative_rois = proposals[negative_indices]
+
+    if positive_count > 0 and negative_count > 0:                             # :370-384
+        rois = torch.cat((positive_rois, negative_rois), dim=0)
+        roi_gt_class_ids = torch.cat([roi_gt_class_ids.int(), torch.zeros(negative_count, dtype=torch.int32, device=dev)], dim=0)
+        deltas = torch.cat([deltas, torch.zeros(negative_count, 4, device=dev)], dim=0)
+        masks = torch.cat([masks, torch.zeros(negative_count, L, mh, mw, device=dev)], dim=0)
+    elif positive_count > 0:
+        rois = positive_rois
+        roi_gt_class_ids = roi_gt_class_ids.int()
+    else:                                                                     # nothing sampled: empty tensors, :400-409
+        rois = torch.empty(0, device=dev)
+        roi_gt_class_ids = torch.empty(0, dtype=torch.int32, device=dev)
+        deltas = torch.empty(0, device=dev)
+        masks = torch.empty(0, device=dev)
+    return rois, roi_gt_class_ids, deltas, masks

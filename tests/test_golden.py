@@ -130,3 +130,70 @@ def test_gpu_layer_decode_matches_reference_python():
         got = planes[0, :n].permute(2, 3, 1, 0).cpu().numpy().astype(bool)
         assert np.array_equal(got, ref)
         assert not planes[0, n:].any()
+
+
+# --------------------------------------------------------------------------- detection targets
+def target_cases():
+    g = load("detection_targets")
+    for k in range(int(g["n_cases"])):
+        shp = tuple(int(v) for v in g["masks_shape%d" % k])
+        masks = np.unpackbits(g["masks%d" % k])[: int(np.prod(shp))].reshape(shp)
+        tshp = tuple(int(v) for v in g["tmasks_shape%d" % k])
+        n_t = int(np.prod(tshp)) if len(tshp) > 1 else 0
+        tmasks = np.unpackbits(g["tmasks%d" % k])[:n_t].reshape(tshp).astype(np.float32) if n_t else np.zeros(0, np.float32)
+        yield dict(props=g["props%d" % k], ids=g["ids%d" % k], gt=g["gt%d" % k], masks=masks, seed=int(g["seed%d" % k]),
+                   rois=g["rois%d" % k], cls=g["cls%d" % k], deltas=g["deltas%d" % k], tmasks=tmasks)
+
+
+class TCfg:
+    BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    TRAIN_ROIS_PER_IMAGE = 100
+    ROI_POSITIVE_RATIO = 0.7
+    MASK_SHAPE = [32, 32]
+    USE_MINI_MASK = False
+    GPU_COUNT = 1
+
+
+def test_oracle_detection_targets_match_reference_python():
+    g = load("detection_targets")
+    assert np.array_equal(oracle.bbox_overlaps(g["ov_b1"], g["ov_b2"]), g["ov_out"], equal_nan=True)
+    assert np.array_equal(oracle.box_refinement(g["ref_box"], g["ref_gt"]), g["ref_out"])
+    for c in target_cases():
+        torch.manual_seed(c["seed"])
+        rois, cls, deltas, tm = oracle.detection_target_layer(c["props"], c["ids"], c["gt"], c["masks"])
+        if c["rois"].size == 0:
+            assert rois.size == 0 and cls.size == 0 and tm.size == 0
+            continue
+        assert np.array_equal(rois, c["rois"]) and np.array_equal(cls, c["cls"]) and np.array_equal(deltas, c["deltas"])
+        assert np.array_equal(tm, c["tmasks"])
+
+
+@pytest.mark.gpu
+def test_gpu_detection_targets_match_reference_python():
+    from sln_amodal_b200 import bbox_overlaps, box_refinement, detection_target_layer, ops
+    g = load("detection_targets")
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ov = bbox_overlaps(t(g["ov_b1"]), t(g["ov_b2"])).cpu().numpy()
+    assert np.array_equal(ov, g["ov_out"], equal_nan=True)
+    _, mx, am = ops.bbox_overlaps_device(t(g["ov_b1"]), t(g["ov_b2"]), matrix=False, reduce=True)
+    want = torch.from_numpy(g["ov_out"])
+    assert np.array_equal(mx.cpu().numpy(), want.max(1)[0].numpy(), equal_nan=True)
+    rows = ~np.isnan(g["ov_out"]).any(1)
+    assert np.array_equal(am.cpu().numpy()[rows], g["ov_out"][rows].argmax(1))
+    np.testing.assert_allclose(box_refinement(t(g["ref_box"]), t(g["ref_gt"])).cpu().numpy(), g["ref_out"], rtol=3e-7, atol=1e-7)
+    for c in target_cases():
+        torch.manual_seed(c["seed"])
+        # GT masks on the host (generic crop path) and on the device as u8 (fused gather + crop + round kernel)
+        for gm in (torch.from_numpy(c["masks"]).unsqueeze(0), t(c["masks"]).unsqueeze(0)):
+            torch.manual_seed(c["seed"])
+            rois, cls, deltas, tm = detection_target_layer(t(c["props"]).unsqueeze(0), t(c["ids"]).unsqueeze(0),
+                                                           t(c["gt"]).unsqueeze(0), gm, TCfg())
+            if c["rois"].size:
+                assert np.array_equal(tm.cpu().numpy(), c["tmasks"]) and np.array_equal(rois.cpu().numpy(), c["rois"])
+        if c["rois"].size == 0:
+            assert rois.numel() == 0 and cls.numel() == 0 and deltas.numel() == 0 and tm.numel() == 0
+            continue
+        assert np.array_equal(rois.cpu().numpy(), c["rois"]) and np.array_equal(cls.cpu().numpy(), c["cls"])
+        np.testing.assert_allclose(deltas.cpu().numpy(), c["deltas"], rtol=3e-6, atol=1e-6)
+        assert np.array_equal(tm.cpu().numpy(), c["tmasks"])
