@@ -360,6 +360,7 @@ def run_ours(args):
         extra = side_metrics(dev, peak)
         extra["head_pipeline"] = head_pipeline(dev, cpu=(world == 1))
         extra["detection_targets"] = detection_targets_metric(dev, cpu=(world == 1))
+        extra["rpn_targets"] = rpn_targets_metric(dev, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -620,6 +621,43 @@ def detection_targets_metric(dev, cpu=True):
                                         "class_ids_identical": bool(np.array_equal(co, out[1].cpu().numpy())),
                                         "masks_identical": bool(np.array_equal(mo, out[3].cpu().numpy())),
                                         "deltas_max_abs_diff": float(np.abs(do - out[2].cpu().numpy()).max()) if do.size else 0.0}}
+    return res
+
+
+def rpn_targets_metric(dev, cpu=True):
+    """build_rpn_targets for one training image, 261 888 anchors x 12 GT boxes, numpy in / numpy out like
+    the reference (the float64 IoU reductions on the device, matching rules and sampling in numpy)."""
+    import torch
+    from sln_amodal_b200 import build_rpn_targets
+    anchors = synth.pyramid_anchors()
+    rng = np.random.default_rng(404)
+    c = rng.uniform(100, 924, (12, 2))
+    s_ = rng.uniform(40, 400, (12, 2))
+    gt = np.clip(np.concatenate([c - s_ / 2, c + s_ / 2], 1), 0, 1024).astype(np.int32)
+    ids = np.ones(12, np.int32)
+
+    class Cfg:
+        RPN_TRAIN_ANCHORS_PER_IMAGE = 256
+        RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+
+    np.random.seed(1)
+    out = build_rpn_targets((1024, 1024, 3), anchors, ids, gt, Cfg(), device=dev)
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        build_rpn_targets((1024, 1024, 3), anchors, ids, gt, Cfg(), device=dev)
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts)) * 1e3
+    res = {"what": "build_rpn_targets, %d anchors x 12 GT boxes, float64" % anchors.shape[0], "ms_per_image": round(ms, 3),
+           "positives": int((out[0] == 1).sum()), "negatives": int((out[0] == -1).sum())}
+    if cpu:
+        from oracle import oracle
+        np.random.seed(1)
+        t0 = time.perf_counter()
+        m, b = oracle.build_rpn_targets(anchors, ids, gt)
+        cpu_s = time.perf_counter() - t0
+        res["cpu_oracle"] = {"ms_per_image": round(cpu_s * 1e3, 1), "cores": os.cpu_count(),
+                             "identical": bool(np.array_equal(m, out[0]) and np.array_equal(b, out[1]))}
     return res
 
 

@@ -181,6 +181,13 @@ SLN_API int sln_box_refinement(const float *box, const float *gt_box, int M, con
 SLN_API int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, int W, const int *assignment,
                      const float *boxes, int P, int mh, int mw, float *out, void *stream);
 
+/* Overlap reductions of build_rpn_targets (modal/Functions.py:773-792) in float64, without the
+ * [A,G] matrix: anchor_iou_max f64 [A] and anchor_argmax i32 [A] = max / first argmax over the GT boxes of every anchor,
+ * gt_argmax i32 [G] = first argmax over the anchors of every GT box (numpy rules: NaN is the maximum).  Any output may
+ * be NULL (crowd boxes only need anchor_iou_max, :769-770).  anchors f64 [A,4], gt_boxes f64 [G,4], 32-byte aligned.  */
+SLN_API int sln_rpn_overlap_reductions(const double *anchors, int A, const double *gt_boxes, int G,
+                               double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *stream);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

@@ -453,6 +453,76 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, train_ro
 
 
 # ---------------------------------------------------------------------------
+# build_rpn_targets (modal/Functions.py:739-847, utils.compute_overlaps utils.py:54-93)
+# ---------------------------------------------------------------------------
+def compute_overlaps(boxes1, boxes2):
+    """utils.py:78-93 in float64 (what numpy computes for float anchors against int32 GT boxes): IoU f64[N1,N2]."""
+    b1 = np.asarray(boxes1, np.float64).reshape(-1, 4)
+    b2 = np.asarray(boxes2, np.float64).reshape(-1, 4)
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    y1 = np.maximum(b2[None, :, 0], b1[:, None, 0])
+    y2 = np.minimum(b2[None, :, 2], b1[:, None, 2])
+    x1 = np.maximum(b2[None, :, 1], b1[:, None, 1])
+    x2 = np.minimum(b2[None, :, 3], b1[:, None, 3])
+    inter = np.maximum(x2 - x1, 0) * np.maximum(y2 - y1, 0)
+    union = area2[None, :] + area1[:, None] - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return inter / union
+
+
+def build_rpn_targets(anchors, gt_class_ids, gt_boxes, anchors_per_image=256, std_dev=(0.1, 0.1, 0.2, 0.2), reductions=None):
+    """Functions.py:739-847.  Returns (rpn_match i32[A], rpn_bbox f64[anchors_per_image,4]).  Subsampling draws
+    np.random.choice from the global numpy generator exactly where the reference does (:806, :814).
+    `reductions` = (anchor_iou_max, anchor_iou_argmax, gt_iou_argmax, crowd_iou_max | None) lets a caller supply the
+    overlap reductions computed elsewhere (the CUDA kernels); the rest of the function is shared."""
+    anchors = np.asarray(anchors)
+    ids = np.asarray(gt_class_ids)
+    gtb = np.asarray(gt_boxes)
+    A = anchors.shape[0]
+    rpn_match = np.zeros([A], dtype=np.int32)
+    rpn_bbox = np.zeros((anchors_per_image, 4))
+    crowd_ix = np.where(ids < 0)[0]
+    crowd_boxes = None
+    if crowd_ix.shape[0] > 0:
+        non_crowd_ix = np.where(ids > 0)[0]
+        crowd_boxes = gtb[crowd_ix]
+        ids, gtb = ids[non_crowd_ix], gtb[non_crowd_ix]
+    if reductions is None:
+        ov = compute_overlaps(anchors, gtb)
+        a_arg = np.argmax(ov, axis=1)
+        a_max = ov[np.arange(A), a_arg]
+        g_arg = np.argmax(ov, axis=0)
+        c_max = np.amax(compute_overlaps(anchors, crowd_boxes), axis=1) if crowd_boxes is not None else None
+    else:
+        a_max, a_arg, g_arg, c_max = reductions
+    no_crowd = (c_max < 0.001) if c_max is not None else np.ones([A], dtype=bool)
+    rpn_match[(a_max < 0.3) & no_crowd] = -1
+    rpn_match[g_arg] = 1
+    rpn_match[a_max >= 0.7] = 1
+    pos = np.where(rpn_match == 1)[0]
+    extra = len(pos) - (anchors_per_image // 2)
+    if extra > 0:
+        rpn_match[np.random.choice(pos, extra, replace=False)] = 0
+    neg = np.where(rpn_match == -1)[0]
+    extra = len(neg) - (anchors_per_image - np.sum(rpn_match == 1))
+    if extra > 0:
+        rpn_match[np.random.choice(neg, extra, replace=False)] = 0
+    pos = np.where(rpn_match == 1)[0]
+    sd = np.asarray(std_dev, np.float64)
+    for ix, i in enumerate(pos):
+        a = anchors[i]
+        gt = gtb[a_arg[i]]
+        gt_h, gt_w = gt[2] - gt[0], gt[3] - gt[1]
+        gcy, gcx = gt[0] + 0.5 * gt_h, gt[1] + 0.5 * gt_w
+        a_h, a_w = a[2] - a[0], a[3] - a[1]
+        acy, acx = a[0] + 0.5 * a_h, a[1] + 0.5 * a_w
+        rpn_bbox[ix] = [(gcy - acy) / a_h, (gcx - acx) / a_w, np.log(gt_h / a_h), np.log(gt_w / a_w)]
+        rpn_bbox[ix] /= sd
+    return rpn_match, rpn_bbox
+
+
+# ---------------------------------------------------------------------------
 # the reference's own C, unmodified (oracle/_ref)
 # ---------------------------------------------------------------------------
 class _TH(C.Structure):

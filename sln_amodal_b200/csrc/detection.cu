@@ -230,3 +230,110 @@ extern "C" int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, in
     SLN_LAUNCH_OK("mask_targets_kernel");
     return SLN_OK;
 }
+
+// ---------------------------------------------------------------------------
+// the overlap reductions of build_rpn_targets (modal/Functions.py:773-792)
+// ---------------------------------------------------------------------------
+// The reference builds the [A, G] IoU matrix in float64 numpy (utils.compute_overlaps, 261 888 x G, one pass per GT
+// box) only to take three reductions of it: per anchor the maximum and its first index (:787-788), per GT box the first
+// index of its column maximum (:792) -- plus the per-anchor maximum against the crowd boxes (:769-770).  Here the
+// matrix is never materialised: kernel 1 walks the G boxes of an anchor, kernel 2 (one CTA per GT box) reduces a column
+// with (value, lowest index) pairs.  float64 throughout, the same operation order as compute_iou (utils.py:65-76);
+// numpy's argmax / amax treat NaN as the maximum, and so do these.
+namespace sln {
+
+__device__ __forceinline__ double iou_f64(const double4 a, double area_a, const double4 g, double area_g)
+{
+    const double y1 = fmax(g.x, a.x), y2 = fmin(g.z, a.z), x1 = fmax(g.y, a.y), x2 = fmin(g.w, a.w);
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1);
+    // np.maximum(v, 0) propagates NaN; fmax does not
+    const double inter = __dmul_rn(dx > 0.0 ? dx : (dx != dx ? dx : 0.0), dy > 0.0 ? dy : (dy != dy ? dy : 0.0));
+    const double uni = __dsub_rn(__dadd_rn(area_g, area_a), inter);
+    return __ddiv_rn(inter, uni);
+}
+
+__device__ __forceinline__ double box_area_f64(const double4 b) { return __dmul_rn(__dsub_rn(b.z, b.x), __dsub_rn(b.w, b.y)); }
+
+// "v beats best" under numpy's argmax rule: NaN is the maximum, the first one wins
+__device__ __forceinline__ bool beats(double v, int iv, double best, int ib)
+{
+    const bool vn = v != v, bn = best != best;
+    if (vn != bn) return vn;
+    if (!vn && v != best) return v > best;
+    return iv < ib;                                  // equal values (or both NaN): lowest index
+}
+
+__global__ void __launch_bounds__(256)
+rpn_anchor_reduce_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G,
+                         double *__restrict__ iou_max, int *__restrict__ argmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const double4 a = *reinterpret_cast<const double4 *>(anchors + 4 * (size_t)i);
+    const double area_a = box_area_f64(a);
+    double best = 0.0;
+    int arg = 0;
+    for (int j = 0; j < G; ++j) {
+        const double4 g = *reinterpret_cast<const double4 *>(gt + 4 * (size_t)j);
+        const double v = iou_f64(a, area_a, g, box_area_f64(g));
+        if (j == 0 || beats(v, j, best, arg)) { best = v; arg = j; }
+    }
+    if (iou_max) iou_max[i] = best;
+    if (argmax) argmax[i] = arg;
+}
+
+__global__ void __launch_bounds__(1024)
+rpn_gt_argmax_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G, int *__restrict__ gt_argmax)
+{
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
+    const int j = blockIdx.x;
+    const double4 g = *reinterpret_cast<const double4 *>(gt + 4 * (size_t)j);
+    const double area_g = box_area_f64(g);
+    double best = 0.0;
+    int arg = 0x7fffffff;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        const double4 a = *reinterpret_cast<const double4 *>(anchors + 4 * (size_t)i);
+        const double v = iou_f64(a, box_area_f64(a), g, area_g);
+        if (arg == 0x7fffffff || beats(v, i, best, arg)) { best = v; arg = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (oi != 0x7fffffff && (arg == 0x7fffffff || beats(ov, oi, best, arg))) { best = ov; arg = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = s_v[threadIdx.x]; arg = s_i[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (oi != 0x7fffffff && (arg == 0x7fffffff || beats(ov, oi, best, arg))) { best = ov; arg = oi; }
+        }
+        if (threadIdx.x == 0) gt_argmax[j] = arg == 0x7fffffff ? 0 : arg;
+    }
+}
+
+}  // namespace sln
+
+extern "C" int sln_rpn_overlap_reductions(const double *anchors, int A, const double *gt_boxes, int G,
+                                          double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *stream)
+{
+    SLN_REQUIRE(A >= 0 && G >= 0, SLN_ERR_ARG, "negative size");
+    if (A == 0 || G == 0) return SLN_OK;
+    SLN_REQUIRE(anchors && gt_boxes, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE(((reinterpret_cast<uintptr_t>(anchors) | reinterpret_cast<uintptr_t>(gt_boxes)) & 31u) == 0, SLN_ERR_LAYOUT,
+                "anchors / gt_boxes must be 32-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (anchor_iou_max || anchor_argmax) {
+        sln::rpn_anchor_reduce_kernel<<<sln::cdiv(A, 256), 256, 0, st>>>(anchors, A, gt_boxes, G, anchor_iou_max, anchor_argmax);
+        SLN_LAUNCH_OK("rpn_anchor_reduce_kernel");
+    }
+    if (gt_argmax) {
+        SLN_REQUIRE(G <= 65535 * 32, SLN_ERR_ARG, "too many GT boxes");
+        sln::rpn_gt_argmax_kernel<<<G, 1024, 0, st>>>(anchors, A, gt_boxes, G, gt_argmax);
+        SLN_LAUNCH_OK("rpn_gt_argmax_kernel");
+    }
+    return SLN_OK;
+}

@@ -347,6 +347,24 @@ def mask_targets_device(gt_masks, assignment, boxes, mh, mw):
     return out
 
 
+def rpn_overlap_reductions_device(anchors, gt_boxes, want_argmax=True):
+    """float64 IoU reductions of build_rpn_targets (sln_rpn_overlap_reductions).  anchors f64 [A,4], gt_boxes f64 [G,4]
+    on the device -> (anchor_iou_max f64 [A], anchor_argmax i32 [A] | None, gt_argmax i32 [G] | None)."""
+    _require_cuda(anchors, "anchors")
+    a = anchors.to(torch.float64).contiguous().view(-1, 4)
+    g = gt_boxes.to(device=a.device, dtype=torch.float64).contiguous().view(-1, 4)
+    A, G = a.shape[0], g.shape[0]
+    mx = torch.zeros(A, dtype=torch.float64, device=a.device)
+    am = torch.zeros(A, dtype=torch.int32, device=a.device) if want_argmax else None
+    ga = torch.zeros(G, dtype=torch.int32, device=a.device) if want_argmax else None
+    if A and G:
+        with torch.cuda.device(a.device):
+            check(lib().sln_rpn_overlap_reductions(ptr(a), A, ptr(g), G, ptr(mx), ptr(am), ptr(ga), stream_ptr()),
+                  "sln_rpn_overlap_reductions")
+        _lib.count_launches(2 if want_argmax else 1)
+    return mx, am, ga
+
+
 # ---------------------------------------------------------------------------
 # proposal_layer
 # ---------------------------------------------------------------------------

@@ -130,3 +130,18 @@ def label_map(H=1024, W=1024, n=20, seed=2024, min_piece=64):
     small[vals == 0] = False
     label = np.where(small[inv].reshape(H, W), np.uint64(0), label)
     return label
+
+
+def pyramid_anchors(image=1024, scales=(32, 64, 128, 256, 512), ratios=(0.5, 1.0, 2.0), strides=(4, 8, 16, 32, 64)):
+    """Anchor pyramid of the reference's configuration (config.py:58-73): for every FPN level a grid of centres at the
+    level's stride and one box per aspect ratio -- 261 888 anchors for a 1024^2 image.  f64 [A,4] (y1,x1,y2,x2) pixels."""
+    out = []
+    for scale, stride in zip(scales, strides):
+        n = image // stride
+        r = np.asarray(ratios, np.float64)
+        h, w = scale / np.sqrt(r), scale * np.sqrt(r)
+        cy, cx = np.meshgrid(np.arange(n) * stride, np.arange(n) * stride, indexing="ij")
+        cy, cx = cy.reshape(-1, 1).astype(np.float64), cx.reshape(-1, 1).astype(np.float64)
+        boxes = np.stack([cy - 0.5 * h, cx - 0.5 * w, cy + 0.5 * h, cx + 0.5 * w], axis=2).reshape(-1, 4)
+        out.append(boxes)
+    return np.concatenate(out, axis=0)

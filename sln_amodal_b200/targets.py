@@ -106,3 +106,77 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
         deltas = torch.empty(0, device=dev)
         masks = torch.empty(0, device=dev)
     return rois, roi_gt_class_ids, deltas, masks
+
+
+_ANCHOR_CACHE = {}
+
+
+def _device_anchors(anchors, dev):
+    """The anchor pyramid is a constant of the configuration: keep its float64 device copy between calls."""
+    key = (anchors.__array_interface__["data"][0], anchors.shape, str(anchors.dtype), str(dev))
+    hit = _ANCHOR_CACHE.get(key)
+    if hit is None or hit[0] is not anchors:
+        _ANCHOR_CACHE.clear()
+        hit = (anchors, torch.from_numpy(np.ascontiguousarray(anchors, dtype=np.float64)).to(dev))
+        _ANCHOR_CACHE[key] = hit
+    return hit[1]
+
+
+def build_rpn_targets(image_shape, anchors, gt_class_ids, gt_boxes, config, device=None):
+    """Drop-in for build_rpn_targets (modal/Functions.py:739-847): numpy in, numpy out --
+    (rpn_match int32 [A], rpn_bbox float64 [RPN_TRAIN_ANCHORS_PER_IMAGE, 4]).
+    The [A,G] float64 IoU matrix of the reference (utils.compute_overlaps) is never built: its three reductions come
+    from the device (ops.rpn_overlap_reductions_device); the matching rules, the two `np.random.choice` subsampling
+    draws (:806, :814 -- same global numpy generator, same order) and the <= 128 positive deltas stay in numpy exactly
+    as the reference has them."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    anchors = np.asarray(anchors)
+    gt_class_ids = np.asarray(gt_class_ids)
+    gt_boxes = np.asarray(gt_boxes)
+    A = anchors.shape[0]
+    rpn_match = np.zeros([A], dtype=np.int32)
+    rpn_bbox = np.zeros((config.RPN_TRAIN_ANCHORS_PER_IMAGE, 4))
+    d_anchors = _device_anchors(anchors, dev)
+    crowd_ix = np.where(gt_class_ids < 0)[0]
+    if crowd_ix.shape[0] > 0:                                                 # :759-770
+        non_crowd_ix = np.where(gt_class_ids > 0)[0]
+        crowd_boxes = gt_boxes[crowd_ix]
+        gt_class_ids = gt_class_ids[non_crowd_ix]
+        gt_boxes = gt_boxes[non_crowd_ix]
+        crowd_iou_max = ops.rpn_overlap_reductions_device(
+            d_anchors, torch.from_numpy(np.ascontiguousarray(crowd_boxes, dtype=np.float64)), want_argmax=False)[0].cpu().numpy()
+        no_crowd_bool = crowd_iou_max < 0.001
+    else:
+        no_crowd_bool = np.ones([A], dtype=bool)
+    mx, am, ga = ops.rpn_overlap_reductions_device(d_anchors, torch.from_numpy(np.ascontiguousarray(gt_boxes, dtype=np.float64)))
+    anchor_iou_max, anchor_iou_argmax, gt_iou_argmax = mx.cpu().numpy(), am.cpu().numpy(), ga.cpu().numpy()
+    rpn_match[(anchor_iou_max < 0.3) & no_crowd_bool] = -1                    # :789
+    rpn_match[gt_iou_argmax] = 1                                              # :792-793
+    rpn_match[anchor_iou_max >= 0.7] = 1                                      # :795
+    ids = np.where(rpn_match == 1)[0]                                         # :799-816
+    extra = len(ids) - (config.RPN_TRAIN_ANCHORS_PER_IMAGE // 2)
+    if extra > 0:
+        ids = np.random.choice(ids, extra, replace=False)
+        rpn_match[ids] = 0
+    ids = np.where(rpn_match == -1)[0]
+    extra = len(ids) - (config.RPN_TRAIN_ANCHORS_PER_IMAGE - np.sum(rpn_match == 1))
+    if extra > 0:
+        ids = np.random.choice(ids, extra, replace=False)
+        rpn_match[ids] = 0
+    ids = np.where(rpn_match == 1)[0]                                         # :820-845
+    ix = 0
+    for i, a in zip(ids, anchors[ids]):
+        gt = gt_boxes[anchor_iou_argmax[i]]
+        gt_h = gt[2] - gt[0]
+        gt_w = gt[3] - gt[1]
+        gt_center_y = gt[0] + 0.5 * gt_h
+        gt_center_x = gt[1] + 0.5 * gt_w
+        a_h = a[2] - a[0]
+        a_w = a[3] - a[1]
+        a_center_y = a[0] + 0.5 * a_h
+        a_center_x = a[1] + 0.5 * a_w
+        rpn_bbox[ix] = [(gt_center_y - a_center_y) / a_h, (gt_center_x - a_center_x) / a_w,
+                        np.log(gt_h / a_h), np.log(gt_w / a_w)]
+        rpn_bbox[ix] /= config.RPN_BBOX_STD_DEV
+        ix += 1
+    return rpn_match, rpn_bbox

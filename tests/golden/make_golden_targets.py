@@ -86,5 +86,37 @@ def main():
     print("written:", out, "overlaps", ov.shape, "refinement", ref.shape)
 
 
+def rpn_targets_main():
+    """build_rpn_targets (modal/Functions.py:739-847) on a reduced anchor pyramid: golden rpn_match / rpn_bbox."""
+    setup_reference_imports()
+    import modal.Functions as F
+    import utils as U
+
+    class RCfg(Cfg):
+        RPN_TRAIN_ANCHORS_PER_IMAGE = 256
+
+    anchors = U.generate_pyramid_anchors((32, 64, 128, 256, 512), [0.5, 1, 2], [[64, 64], [32, 32], [16, 16], [8, 8], [4, 4]],
+                                         [4, 8, 16, 32, 64], 1)          # 256^2 image: 16368 anchors
+    cases = {"anchors": anchors}
+    out = {}
+    for k, (seed, n_gt, crowds) in enumerate([(21, 6, 0), (22, 9, 2), (23, 1, 0)]):
+        rng = np.random.default_rng(seed)
+        c = rng.uniform(30, 226, (n_gt, 2))
+        s = rng.uniform(12, 110, (n_gt, 2))
+        gt = np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 256).astype(np.int32)
+        ids = rng.integers(1, 3, n_gt).astype(np.int32)
+        if crowds:
+            ids[:crowds] = -1
+        np.random.seed(500 + k)
+        match, bbox = F.build_rpn_targets((256, 256, 3), anchors, ids, gt, RCfg())
+        cases.update({"rgt%d" % k: gt, "rids%d" % k: ids, "rseed%d" % k: 500 + k, "rmatch%d" % k: match, "rbbox%d" % k: bbox})
+        out[k] = (int((match == 1).sum()), int((match == -1).sum()))
+    np.savez_compressed(os.path.join(HERE, "rpn_targets.npz"), n_cases=3, **cases)
+    print("rpn targets written:", out, anchors.shape, anchors.dtype)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "rpn":
+        rpn_targets_main()
+    else:
+        main()

@@ -197,3 +197,39 @@ def test_gpu_detection_targets_match_reference_python():
         assert np.array_equal(rois.cpu().numpy(), c["rois"]) and np.array_equal(cls.cpu().numpy(), c["cls"])
         np.testing.assert_allclose(deltas.cpu().numpy(), c["deltas"], rtol=3e-6, atol=1e-6)
         assert np.array_equal(tm.cpu().numpy(), c["tmasks"])
+
+
+# --------------------------------------------------------------------------- build_rpn_targets
+class RCfg:
+    RPN_TRAIN_ANCHORS_PER_IMAGE = 256
+    RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+
+
+def test_oracle_build_rpn_targets_matches_reference_python():
+    g = load("rpn_targets")
+    for k in range(int(g["n_cases"])):
+        np.random.seed(int(g["rseed%d" % k]))
+        m, b = oracle.build_rpn_targets(g["anchors"], g["rids%d" % k], g["rgt%d" % k])
+        assert np.array_equal(m, g["rmatch%d" % k]) and np.array_equal(b, g["rbbox%d" % k])
+
+
+@pytest.mark.gpu
+def test_gpu_build_rpn_targets_matches_reference_python():
+    from sln_amodal_b200 import build_rpn_targets, ops
+    g = load("rpn_targets")
+    for k in range(int(g["n_cases"])):
+        np.random.seed(int(g["rseed%d" % k]))
+        m, b = build_rpn_targets((256, 256, 3), g["anchors"], g["rids%d" % k], g["rgt%d" % k], RCfg())
+        assert m.dtype == np.int32 and np.array_equal(m, g["rmatch%d" % k])
+        assert b.dtype == np.float64 and np.array_equal(b, g["rbbox%d" % k])
+    # the reductions themselves against the float64 matrix, incl. a degenerate (zero-area, 0/0 -> NaN) pair
+    anchors = g["anchors"].copy()
+    anchors[100] = 0.0
+    gt = g["rgt1"].astype(np.float64)
+    gt[0] = 0.0
+    ov = oracle.compute_overlaps(anchors, gt)
+    dev = torch.device("cuda", 0)
+    mx, am, ga = ops.rpn_overlap_reductions_device(torch.from_numpy(anchors).to(dev), torch.from_numpy(gt))
+    assert np.array_equal(am.cpu().numpy(), np.argmax(ov, axis=1))
+    assert np.array_equal(mx.cpu().numpy(), ov[np.arange(ov.shape[0]), np.argmax(ov, axis=1)], equal_nan=True)
+    assert np.array_equal(ga.cpu().numpy(), np.argmax(ov, axis=0))
