@@ -188,6 +188,10 @@ SLN_API int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, int W
 SLN_API int sln_rpn_overlap_reductions(const double *anchors, int A, const double *gt_boxes, int G,
                                double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *stream);
 
+/* Tight bounding boxes of M binary u8 planes [M,H,W] (utils.extract_bboxes, utils.py:28-49, before its random jitter):
+ * boxes i32 [M,4] = (y1, x1, y2, x2) with y2 / x2 exclusive, zeros for an empty plane.                       */
+SLN_API int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int *boxes, void *stream);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

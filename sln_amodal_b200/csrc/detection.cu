@@ -337,3 +337,90 @@ extern "C" int sln_rpn_overlap_reductions(const double *anchors, int A, const do
     }
     return SLN_OK;
 }
+
+// ---------------------------------------------------------------------------
+// tight bounding boxes of binary planes (utils.extract_bboxes, utils.py:28-47, before its random jitter)
+// ---------------------------------------------------------------------------
+// One CTA per plane, 16-byte loads; per plane (y1, x1, y2, x2) with x2 / y2 exclusive like the reference (:44-45), or
+// zeros when the plane is empty (:49).  Meant for the planes sln_layer_decode leaves on the device, so that
+// load_image_gt's boxes (Functions.py:721) need no trip of the masks through the host.
+namespace sln {
+
+__global__ void __launch_bounds__(1024)
+plane_bbox_kernel(const unsigned char *__restrict__ planes, int H, int W, int *__restrict__ out)
+{
+    __shared__ int s_red[4][32];
+    const unsigned char *p = planes + (size_t)blockIdx.x * H * W;
+    int y1 = 0x7fffffff, x1 = 0x7fffffff, y2 = -1, x2 = -1;
+    const bool vec = (W % 16) == 0 && ((reinterpret_cast<uintptr_t>(planes) & 15u) == 0);
+    if (vec) {
+        const int wv = W / 16;
+        const long long n = (long long)H * wv;
+        for (long long k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + k);
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;
+            const int y = (int)(k / wv), xb = (int)(k - (long long)y * wv) * 16;
+            const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+            int first = -1, last = -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (w4[q]) {
+                    // lowest / highest non-zero byte of the word
+                    const unsigned nz = __vcmpne4(w4[q], 0u);              // 0xff per non-zero byte
+                    const int lo = (__ffs(nz) - 1) >> 3, hi = (31 - __clz(nz)) >> 3;
+                    if (first < 0) first = 4 * q + lo;
+                    last = 4 * q + hi;
+                }
+            }
+            y1 = min(y1, y); y2 = max(y2, y);
+            x1 = min(x1, xb + first); x2 = max(x2, xb + last);
+        }
+    } else {
+        const long long n = (long long)H * W;
+        for (long long k = threadIdx.x; k < n; k += blockDim.x) {
+            if (p[k]) {
+                const int y = (int)(k / W), x = (int)(k - (long long)y * W);
+                y1 = min(y1, y); y2 = max(y2, y); x1 = min(x1, x); x2 = max(x2, x);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        y1 = min(y1, __shfl_xor_sync(0xffffffffu, y1, o)); x1 = min(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y2 = max(y2, __shfl_xor_sync(0xffffffffu, y2, o)); x2 = max(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = y1; s_red[1][warp] = x1; s_red[2][warp] = y2; s_red[3][warp] = x2; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        y1 = lane < nw ? s_red[0][lane] : 0x7fffffff; x1 = lane < nw ? s_red[1][lane] : 0x7fffffff;
+        y2 = lane < nw ? s_red[2][lane] : -1; x2 = lane < nw ? s_red[3][lane] : -1;
+        for (int o = 16; o > 0; o >>= 1) {
+            y1 = min(y1, __shfl_xor_sync(0xffffffffu, y1, o)); x1 = min(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y2 = max(y2, __shfl_xor_sync(0xffffffffu, y2, o)); x2 = max(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+        }
+        if (lane == 0) {
+            int4 r = make_int4(0, 0, 0, 0);
+            if (y2 >= 0) r = make_int4(y1, x1, y2 + 1, x2 + 1);
+            *reinterpret_cast<int4 *>(out + 4 * (size_t)blockIdx.x) = r;
+        }
+    }
+}
+
+}  // namespace sln
+
+extern "C" int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int *boxes, void *stream)
+{
+    SLN_REQUIRE(M >= 0 && H >= 0 && W >= 0, SLN_ERR_ARG, "negative size");
+    if (M == 0) return SLN_OK;
+    SLN_REQUIRE(boxes != nullptr && (reinterpret_cast<uintptr_t>(boxes) & 15u) == 0, SLN_ERR_ARG, "boxes must be a 16-byte aligned pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((size_t)H * W == 0) {
+        SLN_CUDA_OK(cudaMemsetAsync(boxes, 0, sizeof(int) * 4 * (size_t)M, st));
+        return SLN_OK;
+    }
+    SLN_REQUIRE(planes != nullptr, SLN_ERR_ARG, "null planes");
+    sln::plane_bbox_kernel<<<M, 1024, 0, st>>>(planes, H, W, boxes);
+    SLN_LAUNCH_OK("plane_bbox_kernel");
+    return SLN_OK;
+}

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -363,6 +364,24 @@ def rpn_overlap_reductions_device(anchors, gt_boxes, want_argmax=True):
                   "sln_rpn_overlap_reductions")
         _lib.count_launches(2 if want_argmax else 1)
     return mx, am, ga
+
+
+def plane_bboxes_device(planes):
+    """Tight (y1, x1, y2, x2) of binary u8 / bool planes [..., H, W] on the device -> int32 [..., 4] (sln_plane_bboxes)."""
+    _require_cuda(planes, "planes")
+    if planes.dtype == torch.bool:
+        planes = planes.view(torch.uint8)
+    if planes.dtype != torch.uint8 or planes.dim() < 2:
+        raise _lib.SlnError("planes must be uint8 / bool [..., H, W]")
+    planes = planes.contiguous()
+    H, W = planes.shape[-2:]
+    M = planes.numel() // max(H * W, 1) if H * W else int(np.prod(planes.shape[:-2]))
+    out = torch.empty(tuple(planes.shape[:-2]) + (4,), dtype=torch.int32, device=planes.device)
+    if M:
+        with torch.cuda.device(planes.device):
+            check(lib().sln_plane_bboxes(ptr(planes), M, H, W, ptr(out), stream_ptr()), "sln_plane_bboxes")
+        _lib.count_launches(1)
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -180,3 +180,22 @@ def build_rpn_targets(image_shape, anchors, gt_class_ids, gt_boxes, config, devi
         rpn_bbox[ix] /= config.RPN_BBOX_STD_DEV
         ix += 1
     return rpn_match, rpn_bbox
+
+
+def extract_bboxes(mask):
+    """Drop-in for utils.extract_bboxes (utils.py:28-54).  mask [H,W,N] (numpy, like the reference) or a CUDA tensor of
+    planes [N,H,W] (what sem_dist_targets / decode_layers leave on the device: no trip of the masks through the host).
+    Returns int32 [N,4] = the tight box of every instance jittered by +-1/15 of its side with `np.random.rand(4)` drawn
+    per instance from the global numpy generator in the reference's order (:51), negatives clipped to 0 (:52)."""
+    if isinstance(mask, np.ndarray):
+        planes = torch.from_numpy(np.ascontiguousarray(np.moveaxis(mask, -1, 0)).astype(np.uint8)).cuda()
+    else:
+        planes = mask
+    tight = ops.plane_bboxes_device(planes).cpu().numpy().reshape(-1, 4)
+    boxes = np.zeros([tight.shape[0], 4], dtype=np.int32)
+    for i in range(tight.shape[0]):
+        y1, x1, y2, x2 = (int(v) for v in tight[i])
+        box = np.array([y1, x1, y2, x2]) + (np.random.rand(4) * 2 - 1) * (y2 - y1, x2 - x1, y2 - y1, x2 - x1) / 15
+        box[box < 0] = 0
+        boxes[i] = box
+    return boxes.astype(np.int32)

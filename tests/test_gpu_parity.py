@@ -636,3 +636,49 @@ def test_full_size_properties():
     d = ops.edt_sq_device(cuda(m)).cpu().numpy()
     assert np.array_equal(d == 0, m == 0)
     assert np.array_equal(d, oracle.edt_sq(m))
+
+
+# --------------------------------------------------------------------------- extract_bboxes
+def _extract_bboxes_reference(mask):
+    """utils.py:28-54 restated in numpy (same RNG draws)."""
+    boxes = np.zeros([mask.shape[-1], 4], dtype=np.int32)
+    for i in range(mask.shape[-1]):
+        m = mask[:, :, i]
+        hz = np.where(np.any(m, axis=0))[0]
+        vt = np.where(np.any(m, axis=1))[0]
+        if hz.shape[0]:
+            x1, x2 = hz[[0, -1]]
+            y1, y2 = vt[[0, -1]]
+            x2 += 1
+            y2 += 1
+        else:
+            x1, x2, y1, y2 = 0, 0, 0, 0
+        box = np.array([y1, x1, y2, x2]) + (np.random.rand(4) * 2 - 1) * (y2 - y1, x2 - x1, y2 - y1, x2 - x1) / 15
+        box[box < 0] = 0
+        boxes[i] = box
+    return boxes.astype(np.int32)
+
+
+@pytest.mark.parametrize("H,W", [(1024, 1024), (96, 130), (33, 17)])
+def test_extract_bboxes_matches_the_numpy_rule(H, W):
+    from sln_amodal_b200 import extract_bboxes, ops
+    rng = np.random.default_rng(H + W)
+    n = 9
+    mask = np.zeros((H, W, n), np.uint8)
+    for i in range(n - 2):
+        y1, x1 = rng.integers(0, H - 3), rng.integers(0, W - 3)
+        y2, x2 = rng.integers(y1 + 1, H + 1), rng.integers(x1 + 1, W + 1)
+        mask[y1:y2, x1:x2, i] = rng.random((y2 - y1, x2 - x1)) < 0.3
+    mask[H - 1, W - 1, n - 2] = 1                      # a single pixel in the last corner; plane n-1 stays empty
+    planes = cuda(np.ascontiguousarray(np.moveaxis(mask, -1, 0)))
+    tight = ops.plane_bboxes_device(planes).cpu().numpy()
+    for i in range(n):
+        ys, xs = np.nonzero(mask[:, :, i])
+        want = (ys.min(), xs.min(), ys.max() + 1, xs.max() + 1) if ys.size else (0, 0, 0, 0)
+        assert tuple(tight[i]) == want
+    np.random.seed(3)
+    want = _extract_bboxes_reference(mask)
+    np.random.seed(3)
+    assert np.array_equal(extract_bboxes(mask), want)
+    np.random.seed(3)
+    assert np.array_equal(extract_bboxes(planes), want)
