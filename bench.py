@@ -361,6 +361,7 @@ def run_ours(args):
         extra["head_pipeline"] = head_pipeline(dev, cpu=(world == 1))
         extra["detection_targets"] = detection_targets_metric(dev, cpu=(world == 1))
         extra["rpn_targets"] = rpn_targets_metric(dev, cpu=(world == 1))
+        extra["rle"] = rle_metric(dev, peak, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -658,6 +659,50 @@ def rpn_targets_metric(dev, cpu=True):
         cpu_s = time.perf_counter() - t0
         res["cpu_oracle"] = {"ms_per_image": round(cpu_s * 1e3, 1), "cores": os.cpu_count(),
                              "identical": bool(np.array_equal(m, out[0]) and np.array_equal(b, out[1]))}
+    return res
+
+
+def rle_metric(dev, peak, cpu=True):
+    """COCO RLE of 100 full-resolution (1024^2) detection masks (blobs), device run-length kernel + host
+    string coder, next to the reference's own maskApi.c (oracle/_ref) on the host."""
+    import torch
+    from sln_amodal_b200 import rle
+    n, h, w = 100, 1024, 1024
+    rng = np.random.default_rng(505)
+    yy, xx = np.mgrid[0:h, 0:w]
+    masks = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        cy, cx = rng.uniform(0.2, 0.8, 2) * h
+        ry, rx = rng.uniform(0.05, 0.2, 2) * h
+        masks[i] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
+    d = torch.from_numpy(masks).to(dev)
+    cols = d.transpose(1, 2).contiguous().view(n, h * w)
+    out = rle.encode(d)
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rle.rle_counts_device(cols)
+        b.record()
+        torch.cuda.synchronize()
+        ev.append(a.elapsed_time(b) * 1e3)
+    t0 = time.perf_counter()
+    rle.encode(d)
+    wall = time.perf_counter() - t0
+    us = float(np.median(ev))
+    res = {"what": "COCO RLE of 100 masks of 1024^2", "kernel_us": round(us, 1), "algorithmic_bytes": n * h * w,
+           "achieved_gbs": round(n * h * w / us / 1e3, 1), "frac": round(n * h * w / us / 1e3 / peak, 4),
+           "encode_ms_incl_transpose_d2h_and_strings": round(wall * 1e3, 2)}
+    if cpu:
+        from oracle import oracle
+        colh = np.ascontiguousarray(masks.transpose(0, 2, 1)).reshape(n, h * w)
+        t0 = time.perf_counter()
+        ref = oracle.ref_rle_encode(colh, h, w) if oracle.ref_mask_available() else [(oracle.rle_encode(c), None) for c in colh]
+        cpu_s = time.perf_counter() - t0
+        res["cpu_baseline"] = {"ms": round(cpu_s * 1e3, 1), "kind": "reference" if oracle.ref_mask_available() else "port", "cores": 1,
+                               "identical": bool(all(o["counts"] == (r[1] if r[1] is not None else oracle.rle_to_string(r[0]))
+                                                     for o, r in zip(out, ref)))}
     return res
 
 

@@ -192,6 +192,15 @@ SLN_API int sln_rpn_overlap_reductions(const double *anchors, int A, const doubl
  * boxes i32 [M,4] = (y1, x1, y2, x2) with y2 / x2 exclusive, zeros for an empty plane.                       */
 SLN_API int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int *boxes, void *stream);
 
+/* ---- COCO run-length codec ---------------------------------- *
+ * sln_rle_encode replaces rleEncode (cocoapi/common/maskApi.c:32-41): masks u8 [n][a] in the memory order to encode
+ * (pycocotools encodes column-major planes), counts u32 [n][cap], m_out i32 [n] = number of runs of mask i (the runs
+ * alternate, starting with the possibly empty run of zeros), or -m when m > cap (nothing is written for that mask).
+ * sln_rle_to_string is a HOST helper (no CUDA): rleToString (maskApi.c:204-216) of one count list into `out`; returns
+ * the string length, or -(needed capacity) when cap is too small.                                          */
+SLN_API int sln_rle_encode(const uint8_t *masks, int n, long long a, uint32_t *counts, int cap, int *m_out, void *stream);
+SLN_API long long sln_rle_to_string(const uint32_t *counts, long long m, char *out, long long cap);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

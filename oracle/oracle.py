@@ -29,6 +29,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORC_SO = os.path.join(_HERE, "_build", "libsln_oracle.so")
 _REF_CROP_SO = os.path.join(_HERE, "_ref", "libref_crop.so")
 _REF_NMS_SO = os.path.join(_HERE, "_ref", "libref_nms.so")
+_REF_MASK_SO = os.path.join(_HERE, "_ref", "libref_mask.so")
 
 
 def build(quiet: bool = True) -> None:
@@ -604,3 +605,72 @@ def ref_nms(dets, thresh):
     if dets.shape[0] == 0:
         return np.empty(0, np.int64)
     return ref_nms_given_order(dets, stable_order(dets[:, 4]), nms_areas(dets), thresh)
+
+
+# ---------------------------------------------------------------------------
+# COCO run-length codec (cocoapi/common/maskApi.c:32-47, 204-216)
+# ---------------------------------------------------------------------------
+def rle_encode(mask_flat):
+    """maskApi.c:32-41 for one mask given in the memory order to encode (pycocotools passes column-major planes):
+    u32 counts, alternating runs starting with the run of zeros (possibly empty)."""
+    t = np.asarray(mask_flat, np.uint8).reshape(-1)
+    prev = np.concatenate([np.zeros(1, np.uint8), t[:-1]])
+    pos = np.nonzero(t != prev)[0]
+    edges = np.concatenate([[0], pos, [t.size]])
+    return np.diff(edges).astype(np.uint32)
+
+
+def rle_to_string(counts):
+    """maskApi.c:204-216: LEB128-like, 6 bits per char, ascii 48-111, counts[i] delta-coded against counts[i-2] for i > 2."""
+    out = bytearray()
+    c = [int(v) for v in counts]
+    for i, v in enumerate(c):
+        x = v - c[i - 2] if i > 2 else v
+        more = True
+        while more:
+            ch = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(ch + 48)
+    return bytes(out)
+
+
+class _RLE(C.Structure):
+    _fields_ = [("h", C.c_ulong), ("w", C.c_ulong), ("m", C.c_ulong), ("cnts", C.POINTER(C.c_uint))]
+
+
+_ref_mask = None
+
+
+def _ref_mask_lib():
+    global _ref_mask
+    if _ref_mask is None:
+        lib = C.CDLL(_REF_MASK_SO)
+        lib.rleToString.restype = C.c_void_p
+        _ref_mask = lib
+    return _ref_mask
+
+
+def ref_mask_available() -> bool:
+    return os.path.exists(_REF_MASK_SO)
+
+
+def ref_rle_encode(masks, h, w):
+    """The reference's own rleEncode + rleToString on n masks [n, h*w] (memory order as given).
+    Returns [(counts u32[m], string bytes)]."""
+    lib = _ref_mask_lib()
+    m = np.ascontiguousarray(masks, np.uint8).reshape(-1, h * w)
+    n = m.shape[0]
+    R = (_RLE * n)()
+    lib.rleEncode(R, m.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_ulong(h), C.c_ulong(w), C.c_ulong(n))
+    out = []
+    libc = C.CDLL(None)
+    for i in range(n):
+        cnt = np.ctypeslib.as_array(R[i].cnts, shape=(R[i].m,)).copy()
+        sp = lib.rleToString(C.byref(R[i]))
+        out.append((cnt, C.string_at(sp)))
+        libc.free(C.c_void_p(sp))
+        lib.rleFree(C.byref(R[i]))
+    return out

@@ -14,6 +14,7 @@ from .pyramid import pyramid_roi_align, pyramid_roi_align_batched, pyramid_roi_a
 from .semdist import decode_layers, load_layer2, sem_dist_targets  # noqa: F401
 from .detection import refine_detections  # noqa: F401
 from .targets import bbox_overlaps, box_refinement, build_rpn_targets, detection_target_layer, extract_bboxes  # noqa: F401
+from .rle import encode as rle_encode  # noqa: F401
 from .install import install  # noqa: F401
 
 __version__ = "0.1.0"

@@ -682,3 +682,32 @@ def test_extract_bboxes_matches_the_numpy_rule(H, W):
     assert np.array_equal(extract_bboxes(mask), want)
     np.random.seed(3)
     assert np.array_equal(extract_bboxes(planes), want)
+
+
+# --------------------------------------------------------------------------- COCO RLE
+def test_rle_encode_matches_maskapi():
+    """Device run-length encoding against the reference's own rleEncode / rleToString (cocoapi/common/maskApi.c compiled
+    into oracle/_ref) where it is present, and against the oracle's restatement everywhere."""
+    from sln_amodal_b200 import rle
+    rng = np.random.default_rng(5)
+    for h, w in ((1024, 1024), (37, 53), (5, 3), (1, 1)):
+        n = 7
+        masks = np.zeros((n, h, w), np.uint8)
+        masks[0] = rng.random((h, w)) < 0.5                      # noise: ~a/2 runs (needs the capacity retry at 1024^2)
+        masks[2] = 1                                             # all ones: [0, a]
+        masks[3, : max(h // 3, 1)] = 1                           # starts with a one
+        yy, xx = np.mgrid[0:h, 0:w]
+        masks[4] = ((yy - h / 2) ** 2 + (xx - w / 2) ** 2) < (min(h, w) / 3) ** 2
+        masks[5] = masks[4] * 3                                  # non-binary values: a change is any difference
+        masks[6, h - 1, w - 1] = 1                               # last pixel only
+        got = rle.encode(cuda(masks))
+        cols = np.ascontiguousarray(masks.transpose(0, 2, 1)).reshape(n, h * w)
+        ref = oracle.ref_rle_encode(cols, h, w) if oracle.ref_mask_available() else None
+        for i in range(n):
+            want_c = oracle.rle_encode(cols[i])
+            assert got[i]["size"] == [h, w]
+            assert got[i]["counts"] == oracle.rle_to_string(want_c), (h, w, i)
+            if ref is not None:
+                assert np.array_equal(ref[i][0], want_c) and got[i]["counts"] == ref[i][1]
+        hwn = np.ascontiguousarray(masks.transpose(1, 2, 0))      # pycocotools' [h, w, n] convention
+        assert [r["counts"] for r in rle.encode(hwn)] == [r["counts"] for r in got]

@@ -137,3 +137,21 @@ def test_edt_matches_scipy():
         assert np.array_equal(got.astype(np.int64), want)
     full = np.ones((5, 7), np.uint8)
     assert np.all(oracle.edt_sq(full) == (5 + 7) ** 2)
+
+
+def test_rle_restatement_matches_reference_maskapi():
+    """oracle.rle_encode / rle_to_string against the reference's own maskApi.c (oracle/_ref/libref_mask.so)."""
+    import pytest
+    if not oracle.ref_mask_available():
+        pytest.skip("oracle/_ref/libref_mask.so not built (no /root/reference here)")
+    rng = np.random.default_rng(1)
+    h, w = 41, 29
+    masks = (rng.random((6, h * w)) < 0.35).astype(np.uint8)
+    masks[1] = 0
+    masks[2] = 1
+    masks[3, :7] = 1
+    masks[4, -1] = 1
+    ref = oracle.ref_rle_encode(masks, h, w)
+    for i in range(6):
+        c = oracle.rle_encode(masks[i])
+        assert np.array_equal(c, ref[i][0]) and oracle.rle_to_string(c) == ref[i][1]
