@@ -185,8 +185,10 @@ SLN_API int sln_mask_targets(const uint8_t *gt_masks, int L, int G, int H, int W
  * [A,G] matrix: anchor_iou_max f64 [A] and anchor_argmax i32 [A] = max / first argmax over the GT boxes of every anchor,
  * gt_argmax i32 [G] = first argmax over the anchors of every GT box (numpy rules: NaN is the maximum).  Any output may
  * be NULL (crowd boxes only need anchor_iou_max, :769-770).  anchors f64 [A,4], gt_boxes f64 [G,4], 32-byte aligned.  */
+SLN_API size_t sln_rpn_overlap_workspace_bytes(int G);     /* needed when gt_argmax is asked for */
 SLN_API int sln_rpn_overlap_reductions(const double *anchors, int A, const double *gt_boxes, int G,
-                               double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *stream);
+                               double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *workspace,
+                               size_t workspace_bytes, void *stream);
 
 /* Tight bounding boxes of M binary u8 planes [M,H,W] (utils.extract_bboxes, utils.py:28-49, before its random jitter):
  * boxes i32 [M,4] = (y1, x1, y2, x2) with y2 / x2 exclusive, zeros for an empty plane.                       */

@@ -41,7 +41,8 @@ PROTOTYPES = {
     "sln_bbox_overlaps": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "sln_box_refinement": (_i, [_vp, _vp, _i, C.POINTER(_f), _vp, _vp]),
     "sln_mask_targets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "sln_rpn_overlap_reductions": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "sln_rpn_overlap_workspace_bytes": (_sz, [_i]),
+    "sln_rpn_overlap_reductions": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sln_plane_bboxes": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sln_rle_encode": (_i, [_vp, _i, C.c_longlong, _vp, _i, _vp, _vp]),
     "sln_rle_to_string": (C.c_longlong, [_vp, C.c_longlong, C.c_char_p, C.c_longlong]),

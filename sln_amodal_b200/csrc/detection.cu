@@ -282,43 +282,78 @@ rpn_anchor_reduce_kernel(const double *__restrict__ anchors, int A, const double
     if (argmax) argmax[i] = arg;
 }
 
-__global__ void __launch_bounds__(1024)
-rpn_gt_argmax_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G, int *__restrict__ gt_argmax)
+// Column argmax in two stages: RPN_GT_SLICES CTAs per GT box each reduce a slice of the anchors to one (value, lowest
+// index) pair; a second, tiny launch reduces the slices.  (One CTA per GT box walked all 261 888 anchors in fp64: 237 us.)
+constexpr int RPN_GT_SLICES = 128;
+
+__device__ __forceinline__ void reduce_pair(double &best, int &arg)
 {
-    __shared__ double s_v[32];
-    __shared__ int s_i[32];
-    const int j = blockIdx.x;
-    const double4 g = *reinterpret_cast<const double4 *>(gt + 4 * (size_t)j);
-    const double area_g = box_area_f64(g);
-    double best = 0.0;
-    int arg = 0x7fffffff;
-    for (int i = threadIdx.x; i < A; i += blockDim.x) {
-        const double4 a = *reinterpret_cast<const double4 *>(anchors + 4 * (size_t)i);
-        const double v = iou_f64(a, box_area_f64(a), g, area_g);
-        if (arg == 0x7fffffff || beats(v, i, best, arg)) { best = v; arg = i; }
-    }
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
         if (oi != 0x7fffffff && (arg == 0x7fffffff || beats(ov, oi, best, arg))) { best = ov; arg = oi; }
     }
+}
+
+__global__ void __launch_bounds__(256)
+rpn_gt_argmax_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G,
+                     double *__restrict__ part_v, int *__restrict__ part_i)
+{
+    __shared__ double s_v[8];
+    __shared__ int s_i[8];
+    const int j = blockIdx.x, slice = blockIdx.y;
+    const double4 g = *reinterpret_cast<const double4 *>(gt + 4 * (size_t)j);
+    const double area_g = box_area_f64(g);
+    const int per = (A + RPN_GT_SLICES - 1) / RPN_GT_SLICES;
+    const int i0 = slice * per, i1 = min(A, i0 + per);
+    double best = 0.0;
+    int arg = 0x7fffffff;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double4 a = *reinterpret_cast<const double4 *>(anchors + 4 * (size_t)i);
+        const double v = iou_f64(a, box_area_f64(a), g, area_g);
+        if (arg == 0x7fffffff || beats(v, i, best, arg)) { best = v; arg = i; }
+    }
+    reduce_pair(best, arg);
     if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = arg; }
     __syncthreads();
     if (threadIdx.x < 32) {
-        best = s_v[threadIdx.x]; arg = s_i[threadIdx.x];
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
-            if (oi != 0x7fffffff && (arg == 0x7fffffff || beats(ov, oi, best, arg))) { best = ov; arg = oi; }
-        }
+        best = threadIdx.x < 8 ? s_v[threadIdx.x] : 0.0;
+        arg = threadIdx.x < 8 ? s_i[threadIdx.x] : 0x7fffffff;
+        reduce_pair(best, arg);
+        if (threadIdx.x == 0) { part_v[(size_t)j * RPN_GT_SLICES + slice] = best; part_i[(size_t)j * RPN_GT_SLICES + slice] = arg; }
+    }
+}
+
+__global__ void __launch_bounds__(RPN_GT_SLICES)
+rpn_gt_argmax_final_kernel(const double *__restrict__ part_v, const int *__restrict__ part_i, int *__restrict__ gt_argmax)
+{
+    __shared__ double s_v[RPN_GT_SLICES / 32];
+    __shared__ int s_i[RPN_GT_SLICES / 32];
+    const int j = blockIdx.x;
+    double best = part_v[(size_t)j * RPN_GT_SLICES + threadIdx.x];
+    int arg = part_i[(size_t)j * RPN_GT_SLICES + threadIdx.x];
+    reduce_pair(best, arg);
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < RPN_GT_SLICES / 32 ? s_v[threadIdx.x] : 0.0;
+        arg = threadIdx.x < RPN_GT_SLICES / 32 ? s_i[threadIdx.x] : 0x7fffffff;
+        reduce_pair(best, arg);
         if (threadIdx.x == 0) gt_argmax[j] = arg == 0x7fffffff ? 0 : arg;
     }
 }
 
 }  // namespace sln
 
+extern "C" size_t sln_rpn_overlap_workspace_bytes(int G)
+{
+    if (G <= 0) return 0;
+    return sln::align_up((sizeof(double) + sizeof(int)) * (size_t)G * sln::RPN_GT_SLICES, 256) + 256;
+}
+
 extern "C" int sln_rpn_overlap_reductions(const double *anchors, int A, const double *gt_boxes, int G,
-                                          double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *stream)
+                                          double *anchor_iou_max, int *anchor_argmax, int *gt_argmax, void *workspace,
+                                          size_t workspace_bytes, void *stream)
 {
     SLN_REQUIRE(A >= 0 && G >= 0, SLN_ERR_ARG, "negative size");
     if (A == 0 || G == 0) return SLN_OK;
@@ -331,8 +366,12 @@ extern "C" int sln_rpn_overlap_reductions(const double *anchors, int A, const do
         SLN_LAUNCH_OK("rpn_anchor_reduce_kernel");
     }
     if (gt_argmax) {
-        SLN_REQUIRE(G <= 65535 * 32, SLN_ERR_ARG, "too many GT boxes");
-        sln::rpn_gt_argmax_kernel<<<G, 1024, 0, st>>>(anchors, A, gt_boxes, G, gt_argmax);
+        SLN_REQUIRE(workspace && workspace_bytes >= sln_rpn_overlap_workspace_bytes(G), SLN_ERR_WORKSPACE,
+                    "rpn overlap workspace: need %zu bytes, got %zu", sln_rpn_overlap_workspace_bytes(G), workspace_bytes);
+        double *pv = static_cast<double *>(workspace);
+        int *pi = reinterpret_cast<int *>(pv + (size_t)G * sln::RPN_GT_SLICES);
+        sln::rpn_gt_argmax_kernel<<<dim3(G, sln::RPN_GT_SLICES), 256, 0, st>>>(anchors, A, gt_boxes, G, pv, pi);
+        sln::rpn_gt_argmax_final_kernel<<<G, sln::RPN_GT_SLICES, 0, st>>>(pv, pi, gt_argmax);
         SLN_LAUNCH_OK("rpn_gt_argmax_kernel");
     }
     return SLN_OK;

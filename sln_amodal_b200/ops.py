@@ -360,9 +360,11 @@ def rpn_overlap_reductions_device(anchors, gt_boxes, want_argmax=True):
     ga = torch.zeros(G, dtype=torch.int32, device=a.device) if want_argmax else None
     if A and G:
         with torch.cuda.device(a.device):
-            check(lib().sln_rpn_overlap_reductions(ptr(a), A, ptr(g), G, ptr(mx), ptr(am), ptr(ga), stream_ptr()),
+            ws = _workspace(lib().sln_rpn_overlap_workspace_bytes(G), a.device) if want_argmax else None
+            check(lib().sln_rpn_overlap_reductions(ptr(a), A, ptr(g), G, ptr(mx), ptr(am), ptr(ga), ptr(ws),
+                                                   ws.numel() if ws is not None else 0, stream_ptr()),
                   "sln_rpn_overlap_reductions")
-        _lib.count_launches(2 if want_argmax else 1)
+        _lib.count_launches(3 if want_argmax else 1)
     return mx, am, ga
 
 

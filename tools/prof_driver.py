@@ -1,5 +1,5 @@
 """Short driver for ncu captures: runs one family of kernels a few times on the bench workload.
-    python tools/prof_driver.py {crop|nms|proposal|semdist} [reps]
+    python tools/prof_driver.py {crop|nms|proposal|semdist|targets} [reps]
 """
 import os
 import sys
@@ -48,5 +48,13 @@ elif what == "semdist":
     for _ in range(reps):
         planes, n_obj = ops.layer_decode_device(labels, 1, 20)
         ops.edt_sq_device(planes)
+elif what == "targets":
+    # the section 8(f) rows: head pipeline pieces, detection / RPN targets, plane boxes, COCO RLE
+    dev0 = dev
+    for _ in range(reps):
+        bench.head_pipeline(dev0, cpu=False)
+        bench.detection_targets_metric(dev0, cpu=False)
+        bench.rpn_targets_metric(dev0, cpu=False)
+        bench.rle_metric(dev0, 6650.0, cpu=False)
 torch.cuda.synchronize()
 print("done", what)
