@@ -54,15 +54,20 @@ rle_encode_kernel(const unsigned char *__restrict__ masks, long long a, unsigned
         if (vec) {
             auto vec16 = [&](const uint4 v, long long jj) {
                 const unsigned w[4] = {v.x, v.y, v.z, v.w};
+                // byte-wise "differs from the byte before": four XORs; almost every 16-byte piece of a mask is constant,
+                // so the per-byte extraction only runs where something changes
+                const unsigned d[4] = {w[0] ^ ((w[0] << 8) | prev), w[1] ^ ((w[1] << 8) | (w[0] >> 24)),
+                                       w[2] ^ ((w[2] << 8) | (w[1] >> 24)), w[3] ^ ((w[3] << 8) | (w[2] >> 24))};
+                prev = w[3] >> 24;
+                if ((d[0] | d[1] | d[2] | d[3]) == 0u) return;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    unsigned ch = change_bits(w[q4], prev);
+                    unsigned ch = __vcmpne4(d[q4], 0u) & 0x01010101u;
                     while (ch) {
                         const int q = (__ffs(ch) - 1) >> 3;
                         ch &= ch - 1;
                         on_change(jj + 4 * q4 + q);
                     }
-                    prev = w[q4] >> 24;
                 }
             };
             for (; j + 16 <= j1; j += 16) vec16(__ldg(reinterpret_cast<const uint4 *>(T + j)), j);
