@@ -203,6 +203,12 @@ SLN_API int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int *bo
 SLN_API int sln_rle_encode(const uint8_t *masks, int n, long long a, uint32_t *counts, int cap, int *m_out, void *stream);
 SLN_API long long sln_rle_to_string(const uint32_t *counts, long long m, char *out, long long cap);
 
+/* Nearest-neighbour zoom / flip of n u8 planes as a gather (utils.resize_layer, utils.py:358-362; np.fliplr,
+ * Functions.py:712-715): dst[p][y][x] = src[p][iy[y]][ix[x]], 0 where an index is negative.  iy i32 [H2], ix i32 [W2] on
+ * the device, computed by the caller with scipy.ndimage.zoom's float64 rule (sln_amodal_b200/targets.py).          */
+SLN_API int sln_gather_planes(const uint8_t *src, int n, int H, int W, const int *iy, const int *ix, int H2, int W2,
+                      uint8_t *dst, void *stream);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

@@ -463,3 +463,59 @@ extern "C" int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int 
     SLN_LAUNCH_OK("plane_bbox_kernel");
     return SLN_OK;
 }
+
+// ---------------------------------------------------------------------------
+// nearest-neighbour zoom / flip of label planes (utils.resize_layer, utils.py:358-362: scipy.ndimage.zoom(order=0);
+// np.fliplr in load_image_gt, Functions.py:712-715) as one gather
+// ---------------------------------------------------------------------------
+// dst[p][y][x] = src[p][iy[y]][ix[x]], or 0 where iy[y] < 0 or ix[x] < 0.  The index maps are computed by the caller
+// (sln_amodal_b200/targets.py: scipy's own float64 rule, including its habit of zero-filling a last line whose sample
+// position overshoots the input by one rounding error; a flip is the reversed column map), so the kernel is a pure,
+// exact gather.  16 output bytes per thread.
+namespace sln {
+
+__global__ void __launch_bounds__(256)
+gather_planes_kernel(const unsigned char *__restrict__ src, int H, int W, const int *__restrict__ iy,
+                     const int *__restrict__ ix, int H2, int W2, unsigned char *__restrict__ dst)
+{
+    const int xs = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y;
+    if (xs >= W2) return;
+    const unsigned char *sp = src + (size_t)blockIdx.z * H * W;
+    unsigned char *dp = dst + ((size_t)blockIdx.z * H2 + y) * W2 + xs;
+    const int sy = iy[y];
+    unsigned char v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        v[k] = 0;
+        if (xs + k < W2) {
+            const int sx = ix[xs + k];
+            if (sy >= 0 && sx >= 0) v[k] = sp[(size_t)sy * W + sx];
+        }
+    }
+    if (xs + 16 <= W2 && ((reinterpret_cast<uintptr_t>(dp) & 15u) == 0)) {
+        uint4 o;
+        o.x = v[0] | (v[1] << 8) | (v[2] << 16) | ((unsigned)v[3] << 24);
+        o.y = v[4] | (v[5] << 8) | (v[6] << 16) | ((unsigned)v[7] << 24);
+        o.z = v[8] | (v[9] << 8) | (v[10] << 16) | ((unsigned)v[11] << 24);
+        o.w = v[12] | (v[13] << 8) | (v[14] << 16) | ((unsigned)v[15] << 24);
+        *reinterpret_cast<uint4 *>(dp) = o;
+    } else {
+        for (int k = 0; k < 16 && xs + k < W2; ++k) dp[k] = v[k];
+    }
+}
+
+}  // namespace sln
+
+extern "C" int sln_gather_planes(const uint8_t *src, int n, int H, int W, const int *iy, const int *ix, int H2, int W2,
+                                 uint8_t *dst, void *stream)
+{
+    SLN_REQUIRE(n >= 0 && H >= 0 && W >= 0 && H2 >= 0 && W2 >= 0, SLN_ERR_ARG, "negative size");
+    if ((size_t)n * H2 * W2 == 0) return SLN_OK;
+    SLN_REQUIRE(src && iy && ix && dst, SLN_ERR_ARG, "null pointer");
+    SLN_REQUIRE(H2 <= 65535 && n <= 65535, SLN_ERR_ARG, "output height / plane count above 65535");
+    dim3 grid(sln::cdiv(sln::cdiv(W2, 16), 256), H2, n);
+    sln::gather_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, H, W, iy, ix, H2, W2, dst);
+    SLN_LAUNCH_OK("gather_planes_kernel");
+    return SLN_OK;
+}

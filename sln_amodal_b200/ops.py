@@ -386,6 +386,30 @@ def plane_bboxes_device(planes):
     return out
 
 
+def gather_planes_device(planes, iy, ix):
+    """dst[..., y, x] = planes[..., iy[y], ix[x]] (0 where an index is negative); planes u8 / bool [..., H, W] on the
+    device, iy / ix int32 index maps (numpy or tensors) -> u8 [..., len(iy), len(ix)] (sln_gather_planes)."""
+    _require_cuda(planes, "planes")
+    was_bool = planes.dtype == torch.bool
+    if was_bool:
+        planes = planes.view(torch.uint8)
+    if planes.dtype != torch.uint8 or planes.dim() < 2:
+        raise _lib.SlnError("planes must be uint8 / bool [..., H, W]")
+    planes = planes.contiguous()
+    H, W = planes.shape[-2:]
+    n = planes.numel() // max(H * W, 1)
+    d_iy = torch.as_tensor(np.asarray(iy, dtype=np.int32)).to(planes.device) if not torch.is_tensor(iy) else _i32c(iy)
+    d_ix = torch.as_tensor(np.asarray(ix, dtype=np.int32)).to(planes.device) if not torch.is_tensor(ix) else _i32c(ix)
+    H2, W2 = d_iy.numel(), d_ix.numel()
+    out = torch.empty(tuple(planes.shape[:-2]) + (H2, W2), dtype=torch.uint8, device=planes.device)
+    if out.numel():
+        with torch.cuda.device(planes.device):
+            check(lib().sln_gather_planes(ptr(planes), n, H, W, ptr(d_iy), ptr(d_ix), H2, W2, ptr(out), stream_ptr()),
+                  "sln_gather_planes")
+        _lib.count_launches(1)
+    return out.view(torch.bool) if was_bool else out
+
+
 # ---------------------------------------------------------------------------
 # proposal_layer
 # ---------------------------------------------------------------------------

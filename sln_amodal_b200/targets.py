@@ -199,3 +199,36 @@ def extract_bboxes(mask):
         box[box < 0] = 0
         boxes[i] = box
     return boxes.astype(np.int32)
+
+
+def zoom_index_map(n_in, n_out):
+    """Source index of every output line of scipy.ndimage.zoom(order=0, mode='constant') along one axis, in scipy's own
+    float64 arithmetic: position = o * (n_in-1)/(n_out-1), index = floor(position + 0.5); a position outside
+    [0, n_in-1] -- the last line overshoots by one rounding error for some size pairs -- reads the constant 0 (index -1)."""
+    if n_out <= 1:
+        return np.zeros(max(n_out, 0), np.int32)
+    z = (n_in - 1) / (n_out - 1)
+    cc = np.arange(n_out, dtype=np.float64) * z
+    idx = np.floor(cc + 0.5).astype(np.int64)
+    idx[(cc < 0) | (cc > n_in - 1)] = -1
+    return idx.astype(np.int32)
+
+
+def resize_layer_device(planes, scale, flip=False):
+    """utils.resize_layer (utils.py:358-362: scipy.ndimage.zoom(mask, [sy, sx, 1, 1], order=0)) and the optional
+    np.fliplr of load_image_gt (Functions.py:712-715) for device-resident planes [..., H, W] in one gather launch."""
+    H, W = planes.shape[-2:]
+    H2, W2 = int(round(H * scale[0])), int(round(W * scale[1]))
+    iy, ix = zoom_index_map(H, H2), zoom_index_map(W, W2)
+    if flip:
+        ix = ix[::-1].copy()
+    return ops.gather_planes_device(planes, iy, ix)
+
+
+def resize_layer(mask, scale, padding=None):
+    """Drop-in for utils.resize_layer: numpy mask [H, W, ...] in, numpy out (the planes take one trip through the
+    device; use resize_layer_device on the output of decode_layers / sem_dist_targets to stay there)."""
+    m = np.asarray(mask)
+    planes = torch.from_numpy(np.ascontiguousarray(np.moveaxis(m, (0, 1), (-2, -1))).astype(np.uint8)).cuda()
+    out = resize_layer_device(planes, scale).cpu().numpy()
+    return np.moveaxis(out, (-2, -1), (0, 1)).astype(m.dtype)

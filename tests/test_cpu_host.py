@@ -184,3 +184,27 @@ def test_gloo_world_size_2(tmp_path):
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("OK") == 2
+
+
+def test_zoom_index_map_reproduces_scipy_nearest_zoom():
+    """targets.zoom_index_map is the host half of resize_layer: it must reproduce scipy.ndimage.zoom(order=0), the
+    function the reference calls (utils.py:360), including the zero-filled last line some size pairs produce."""
+    import scipy.ndimage as ndi
+    from sln_amodal_b200.targets import zoom_index_map
+    rng = np.random.default_rng(0)
+    quirks = 0
+    for _ in range(200):
+        h, w = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        sy = float(rng.choice([1024 / h, rng.uniform(0.3, 3.0)]))
+        sx = float(rng.choice([1024 / w, rng.uniform(0.3, 3.0)]))
+        oh, ow = int(round(h * sy)), int(round(w * sx))
+        if oh == 0 or ow == 0:
+            continue
+        a = rng.integers(1, 255, (h, w)).astype(np.uint8)
+        iy, ix = zoom_index_map(h, oh), zoom_index_map(w, ow)
+        got = a[np.maximum(iy, 0)][:, np.maximum(ix, 0)]
+        got[iy < 0, :] = 0
+        got[:, ix < 0] = 0
+        quirks += int((iy < 0).any() or (ix < 0).any())
+        assert np.array_equal(got, ndi.zoom(a, zoom=[sy, sx], order=0))
+    assert quirks > 0          # the sweep does contain overshooting last lines

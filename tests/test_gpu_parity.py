@@ -711,3 +711,19 @@ def test_rle_encode_matches_maskapi():
                 assert np.array_equal(ref[i][0], want_c) and got[i]["counts"] == ref[i][1]
         hwn = np.ascontiguousarray(masks.transpose(1, 2, 0))      # pycocotools' [h, w, n] convention
         assert [r["counts"] for r in rle.encode(hwn)] == [r["counts"] for r in got]
+
+
+def test_resize_layer_matches_scipy_zoom():
+    """utils.resize_layer = scipy.ndimage.zoom(mask, [sy, sx, 1, 1], order=0) (utils.py:358-362) and np.fliplr, on the
+    device, against scipy itself -- incl. a size pair whose last column scipy zero-fills."""
+    import scipy.ndimage as ndi
+    from sln_amodal_b200 import resize_layer, resize_layer_device
+    rng = np.random.default_rng(9)
+    for (h, w), scale in (((328, 414), (1.8358701484000286, 0.49965678675982783)), ((480, 640), (1024 / 480, 1024 / 640)),
+                          ((97, 61), (0.5, 2.25)), ((64, 64), (1.0, 1.0))):
+        mask = (rng.random((h, w, 3, 2)) < 0.4).astype(np.uint8)            # reference layout [H, W, n, L]
+        want = ndi.zoom(mask, zoom=[scale[0], scale[1], 1, 1], order=0)
+        assert np.array_equal(resize_layer(mask, scale, None), want)
+        planes = cuda(np.ascontiguousarray(np.moveaxis(mask, (0, 1), (-2, -1))))
+        got = resize_layer_device(planes, scale, flip=True).cpu().numpy()
+        assert np.array_equal(np.moveaxis(got, (-2, -1), (0, 1)), np.fliplr(want))
