@@ -509,17 +509,14 @@ def build_rpn_targets(anchors, gt_class_ids, gt_boxes, anchors_per_image=256, st
     extra = len(neg) - (anchors_per_image - np.sum(rpn_match == 1))
     if extra > 0:
         rpn_match[np.random.choice(neg, extra, replace=False)] = 0
-    pos = np.where(rpn_match == 1)[0]
-    sd = np.asarray(std_dev, np.float64)
-    for ix, i in enumerate(pos):
-        a = anchors[i]
-        gt = gtb[a_arg[i]]
-        gt_h, gt_w = gt[2] - gt[0], gt[3] - gt[1]
-        gcy, gcx = gt[0] + 0.5 * gt_h, gt[1] + 0.5 * gt_w
-        a_h, a_w = a[2] - a[0], a[3] - a[1]
-        acy, acx = a[0] + 0.5 * a_h, a[1] + 0.5 * a_w
-        rpn_bbox[ix] = [(gcy - acy) / a_h, (gcx - acx) / a_w, np.log(gt_h / a_h), np.log(gt_w / a_w)]
-        rpn_bbox[ix] /= sd
+    pos = np.where(rpn_match == 1)[0]                                     # :820-845, all positives at once
+    if pos.size:
+        a, g = anchors[pos], gtb[a_arg[pos]]
+        g_h, g_w = g[:, 2] - g[:, 0], g[:, 3] - g[:, 1]
+        a_h, a_w = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+        dy = ((g[:, 0] + 0.5 * g_h) - (a[:, 0] + 0.5 * a_h)) / a_h
+        dx = ((g[:, 1] + 0.5 * g_w) - (a[:, 1] + 0.5 * a_w)) / a_w
+        rpn_bbox[: pos.size] = np.stack([dy, dx, np.log(g_h / a_h), np.log(g_w / a_w)], 1) / np.asarray(std_dev, np.float64)
     return rpn_match, rpn_bbox
 
 

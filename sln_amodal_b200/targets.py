@@ -150,35 +150,30 @@ def build_rpn_targets(image_shape, anchors, gt_class_ids, gt_boxes, config, devi
         no_crowd_bool = np.ones([A], dtype=bool)
     mx, am, ga = ops.rpn_overlap_reductions_device(d_anchors, torch.from_numpy(np.ascontiguousarray(gt_boxes, dtype=np.float64)))
     anchor_iou_max, anchor_iou_argmax, gt_iou_argmax = mx.cpu().numpy(), am.cpu().numpy(), ga.cpu().numpy()
-    rpn_match[(anchor_iou_max < 0.3) & no_crowd_bool] = -1                    # :789
-    rpn_match[gt_iou_argmax] = 1                                              # :792-793
-    rpn_match[anchor_iou_max >= 0.7] = 1                                      # :795
-    ids = np.where(rpn_match == 1)[0]                                         # :799-816
-    extra = len(ids) - (config.RPN_TRAIN_ANCHORS_PER_IMAGE // 2)
-    if extra > 0:
-        ids = np.random.choice(ids, extra, replace=False)
-        rpn_match[ids] = 0
-    ids = np.where(rpn_match == -1)[0]
-    extra = len(ids) - (config.RPN_TRAIN_ANCHORS_PER_IMAGE - np.sum(rpn_match == 1))
-    if extra > 0:
-        ids = np.random.choice(ids, extra, replace=False)
-        rpn_match[ids] = 0
-    ids = np.where(rpn_match == 1)[0]                                         # :820-845
-    ix = 0
-    for i, a in zip(ids, anchors[ids]):
-        gt = gt_boxes[anchor_iou_argmax[i]]
-        gt_h = gt[2] - gt[0]
-        gt_w = gt[3] - gt[1]
-        gt_center_y = gt[0] + 0.5 * gt_h
-        gt_center_x = gt[1] + 0.5 * gt_w
-        a_h = a[2] - a[0]
-        a_w = a[3] - a[1]
-        a_center_y = a[0] + 0.5 * a_h
-        a_center_x = a[1] + 0.5 * a_w
-        rpn_bbox[ix] = [(gt_center_y - a_center_y) / a_h, (gt_center_x - a_center_x) / a_w,
-                        np.log(gt_h / a_h), np.log(gt_w / a_w)]
-        rpn_bbox[ix] /= config.RPN_BBOX_STD_DEV
-        ix += 1
+    # matching rules (:789-795): negatives first, then one anchor per GT box whatever its IoU, then every anchor >= 0.7
+    rpn_match[(anchor_iou_max < 0.3) & no_crowd_bool] = -1
+    rpn_match[gt_iou_argmax] = 1
+    rpn_match[anchor_iou_max >= 0.7] = 1
+    # balance (:799-816): at most half positives, the rest negatives; the surplus of either kind goes back to neutral.
+    # Same two draws from numpy's global generator, in the same order and with the same arguments, as the reference.
+    budget = config.RPN_TRAIN_ANCHORS_PER_IMAGE
+    for label, allowed in ((1, lambda: budget // 2), (-1, lambda: budget - np.sum(rpn_match == 1))):
+        members = np.where(rpn_match == label)[0]
+        surplus = len(members) - allowed()
+        if surplus > 0:
+            rpn_match[np.random.choice(members, surplus, replace=False)] = 0
+    # refinement targets of the surviving positives (:820-845), all at once: the same float64 operations element by
+    # element (GT boxes keep their integer dtype until the first float operand, as in the reference's scalar code)
+    pos = np.where(rpn_match == 1)[0]
+    if pos.size:
+        a = anchors[pos]
+        g = gt_boxes[anchor_iou_argmax[pos]]
+        g_h, g_w = g[:, 2] - g[:, 0], g[:, 3] - g[:, 1]
+        g_cy, g_cx = g[:, 0] + 0.5 * g_h, g[:, 1] + 0.5 * g_w
+        a_h, a_w = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+        a_cy, a_cx = a[:, 0] + 0.5 * a_h, a[:, 1] + 0.5 * a_w
+        t = np.stack([(g_cy - a_cy) / a_h, (g_cx - a_cx) / a_w, np.log(g_h / a_h), np.log(g_w / a_w)], axis=1)
+        rpn_bbox[: pos.size] = t / config.RPN_BBOX_STD_DEV
     return rpn_match, rpn_bbox
 
 
