@@ -46,7 +46,16 @@ def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(p))
+            # the driver's file names the copy bandwidth `hbm_gbs`; tolerate nesting / near-synonyms of that key
+            flat = dict(d)
+            for v in d.values():
+                if isinstance(v, dict):
+                    flat.update(v)
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs", "hbm_bandwidth_gbs", "hbm"):
+                if key in flat and float(flat[key]) > 0:
+                    v = float(flat[key])
+                    return (v * 1000.0 if v < 100.0 else v), "measured (MEASURED_PEAKS.json %s)" % key     # TB/s -> GB/s
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
