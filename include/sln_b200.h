@@ -203,6 +203,15 @@ SLN_API int sln_plane_bboxes(const uint8_t *planes, int M, int H, int W, int *bo
 SLN_API int sln_rle_encode(const uint8_t *masks, int n, long long a, uint32_t *counts, int cap, int *m_out, void *stream);
 SLN_API long long sln_rle_to_string(const uint32_t *counts, long long m, char *out, long long cap);
 
+/* Mask paste after the path: utils.unmold_mask (utils.py:447-465) for N detections in one launch.
+ * masks f32 [N,mh,mw] (the head's small masks), boxes i32 [N,4] = (y1,x1,y2,x2) in image pixels, y2 / x2 exclusive,
+ * out u8 [N,H,W].  Per detection: scipy.misc.bytescale (min/max stretch to u8, float32), Pillow's 8-bit bilinear
+ * resample to (y2-y1, x2-x1) -- what scipy.misc.imresize(interp='bilinear') runs, bit-identical --, v/255 >= 0.5, paste
+ * into a zero image.  A box that is empty or not inside [0,H]x[0,W] pastes nothing (the reference drops zero-area
+ * detections first, model.py:786-795, and its paste raises on a box outside the image).  mh, mw <= 256.          */
+SLN_API int sln_unmold_masks(const float *masks, int N, int mh, int mw, const int *boxes, int H, int W,
+                     uint8_t *out, void *stream);
+
 /* Nearest-neighbour zoom / flip of n u8 planes as a gather (utils.resize_layer, utils.py:358-362; np.fliplr,
  * Functions.py:712-715): dst[p][y][x] = src[p][iy[y]][ix[x]], 0 where an index is negative.  iy i32 [H2], ix i32 [W2] on
  * the device, computed by the caller with scipy.ndimage.zoom's float64 rule (sln_amodal_b200/targets.py).          */

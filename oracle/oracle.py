@@ -671,3 +671,121 @@ def ref_rle_encode(masks, h, w):
         libc.free(C.c_void_p(sp))
         lib.rleFree(C.byref(R[i]))
     return out
+
+
+# ---------------------------------------------------------------------------
+# unmold_mask (utils.py:447-465) -- SURVEY.md section 8(f), row 3: the step after the path.
+#
+# The reference calls scipy.misc.imresize(mask, (y2-y1, x2-x1), interp='bilinear'), i.e. two third-party pieces
+# that are NOT in /root/reference:
+#   * scipy.misc.pilutil.bytescale / toimage / imresize (scipy 1.0-1.2; removed in scipy 1.3, so absent here):
+#     restated below from its published source, with the float32 scalar promotion of the numpy 1.x it ran on;
+#   * PIL.Image.resize(size, resample=BILINEAR) = Pillow's libImaging/Resample.c (8-bit, 22-bit fixed-point
+#     coefficients, horizontal pass first, 8-bit intermediate).  Pillow IS installed here (12.2.0), so
+#     unmold_mask_pil() below runs the real library and pil_resize_bilinear_u8() -- the restatement the CUDA
+#     kernel follows -- is pinned to it bit for bit by tests/test_oracle_pin.py.
+# ---------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def bytescale_f32(data):
+    """scipy.misc.bytescale(data) with cmin / cmax = data.min() / data.max(), high=255, low=0, for float32 input
+    under numpy-1.x promotion: scale = f32(255.0 / f64(cmax - cmin)); ((data - cmin) * scale).clip(0, 255) + 0.5 in
+    float32, truncated to uint8."""
+    d = np.ascontiguousarray(data, dtype=np.float32)
+    cmin, cmax = d.min(), d.max()
+    cscale = np.float32(cmax - cmin)
+    if cscale == 0:
+        cscale = np.float32(1)
+    scale = np.float32(255.0 / float(cscale))
+    b = (d - cmin).astype(np.float32) * scale
+    b = np.clip(b, np.float32(0), np.float32(255)).astype(np.float32) + np.float32(0.5)
+    return b.astype(np.float32).astype(np.uint8)
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the triangle filter (support 1.0), box = whole axis.
+    -> (xmin i32 [out], count i32 [out], coeff i32 [out, ksize])."""
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    xmin_a = np.zeros(out_size, np.int32)
+    cnt_a = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)          # C cast: truncation towards zero
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = np.zeros(max(xmax, 0), np.float64)
+        ww = 0.0
+        for x in range(xmax):
+            v = (x + xmin - center + 0.5) * ss
+            v = -v if v < 0.0 else v
+            w[x] = 1.0 - v if v < 1.0 else 0.0
+            ww += w[x]
+        for x in range(xmax):
+            k = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(0.5 + k * float(1 << PIL_PRECISION_BITS))
+        xmin_a[xx], cnt_a[xx] = xmin, xmax
+    return xmin_a, cnt_a, kk
+
+
+def _pil_pass(src, xmin, cnt, kk):
+    """one 8bpc pass along the last axis: out[r, xx] = clip8((2^21 + sum_x src[r, xmin+x] * k[x]) >> 22)"""
+    out = np.zeros((src.shape[0], xmin.shape[0]), np.uint8)
+    s = src.astype(np.int64)
+    for xx in range(xmin.shape[0]):
+        acc = np.full(src.shape[0], 1 << (PIL_PRECISION_BITS - 1), np.int64)
+        for x in range(cnt[xx]):
+            acc += s[:, xmin[xx] + x] * int(kk[xx, x])
+        out[:, xx] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out
+
+
+def pil_resize_bilinear_u8(img, out_h, out_w):
+    """ImagingResample for an 'L' image: horizontal pass (all rows), then vertical pass on its 8-bit result."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    tmp = _pil_pass(img, *pil_bilinear_coeffs(img.shape[1], out_w))
+    return np.ascontiguousarray(_pil_pass(np.ascontiguousarray(tmp.T), *pil_bilinear_coeffs(img.shape[0], out_h)).T)
+
+
+def _paste(small, bbox, image_shape):
+    y1, x1, y2, x2 = (int(v) for v in bbox)
+    full = np.zeros(tuple(image_shape[:2]), np.uint8)
+    if y2 > y1 and x2 > x1:
+        full[y1:y2, x1:x2] = small
+    return full
+
+
+def unmold_mask(mask, bbox, image_shape):
+    """utils.py:447-465 on the restated resize: bytescale -> bilinear resize to the box -> v / 255 >= 0.5 (v >= 128)
+    -> paste.  An empty box pastes nothing (the reference drops zero-area detections first, model.py:786-795)."""
+    y1, x1, y2, x2 = (int(v) for v in bbox)
+    m = np.squeeze(np.asarray(mask, dtype=np.float32))
+    if y2 <= y1 or x2 <= x1:
+        return np.zeros(tuple(image_shape[:2]), np.uint8)
+    r = pil_resize_bilinear_u8(bytescale_f32(m), y2 - y1, x2 - x1)
+    small = np.where(r.astype(np.float32) / np.float32(255.0) >= 0.5, 1, 0).astype(np.uint8)
+    return _paste(small, bbox, image_shape)
+
+
+def unmold_mask_pil(mask, bbox, image_shape):
+    """The same function through the real Pillow (what scipy.misc.imresize calls): toimage -> Image.resize(BILINEAR)
+    -> fromimage.  Used to pin unmold_mask(); needs PIL."""
+    from PIL import Image
+    y1, x1, y2, x2 = (int(v) for v in bbox)
+    m = np.squeeze(np.asarray(mask, dtype=np.float32))
+    if y2 <= y1 or x2 <= x1:
+        return np.zeros(tuple(image_shape[:2]), np.uint8)
+    b = bytescale_f32(m)
+    im = Image.frombytes("L", (b.shape[1], b.shape[0]), b.tobytes())
+    r = np.asarray(im.resize((x2 - x1, y2 - y1), resample=Image.BILINEAR), dtype=np.uint8)
+    small = np.where(r.astype(np.float32) / np.float32(255.0) >= 0.5, 1, 0).astype(np.uint8)
+    return _paste(small, bbox, image_shape)

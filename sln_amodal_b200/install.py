@@ -46,6 +46,14 @@ def install(model_module=None, functions_module=None, modals_module=None, datase
     for mod in (modals_module, model_module):
         bind(mod, "pyramid_roi_align", pyramid.pyramid_roi_align)
         bind(mod, "pyramid_roi_align_image", pyramid.pyramid_roi_align_image)
+    if model_module is not None and hasattr(getattr(model_module, "MaskRCNN", None), "unmold_detections"):
+        from . import unmold
+
+        def _unmold_detections(self, detections, mrcnn_mask, image_shape, window):
+            return unmold.unmold_detections(detections, mrcnn_mask, image_shape, window)
+
+        model_module.MaskRCNN.unmold_detections = _unmold_detections       # model.py:747-806
+        done.append(f"{model_module.__name__}.MaskRCNN.unmold_detections")
     if dataset_class is not None:
         dataset_class.load_layer2 = semdist.load_layer2
         done.append(f"{dataset_class.__name__}.load_layer2")

@@ -727,3 +727,65 @@ def test_resize_layer_matches_scipy_zoom():
         planes = cuda(np.ascontiguousarray(np.moveaxis(mask, (0, 1), (-2, -1))))
         got = resize_layer_device(planes, scale, flip=True).cpu().numpy()
         assert np.array_equal(np.moveaxis(got, (-2, -1), (0, 1)), np.fliplr(want))
+
+
+# --------------------------------------------------------------------------- unmold_mask (8(f)-3)
+def _unmold_cases(rng, n, H, W, mh=28, mw=28):
+    masks = rng.random((n, mh, mw)).astype(np.float32) ** 2
+    masks[0] = 0.3                                                          # constant mask (cscale == 0)
+    boxes = np.zeros((n, 4), np.int32)
+    for i in range(n):
+        bh = int(rng.integers(1, H + 1)) if i % 4 else int(rng.integers(1, min(mh, H)))     # every 4th: downscale
+        bw = int(rng.integers(1, W + 1)) if i % 3 else int(rng.integers(1, min(mw, W)))
+        y1 = int(rng.integers(0, H - bh + 1))
+        x1 = int(rng.integers(0, W - bw + 1))
+        boxes[i] = (y1, x1, y1 + bh, x1 + bw)
+    boxes[1] = (0, 0, H, W)                                                 # whole image
+    boxes[2] = (5, 7, 5, 40)                                                # empty: pastes nothing
+    return masks, boxes
+
+
+@pytest.mark.parametrize("H,W,mh,mw", [(256, 320, 28, 28), (130, 131, 28, 28), (192, 160, 14, 33)])
+def test_unmold_masks_match_oracle(H, W, mh, mw):
+    """sln_unmold_masks against the oracle's restatement of scipy bytescale + Pillow's bilinear resample (pinned to
+    Pillow itself on the CPU): bit-identical planes, vector (W % 16 == 0) and byte paths."""
+    from sln_amodal_b200 import unmold
+    rng = np.random.default_rng(H + W)
+    masks, boxes = _unmold_cases(rng, 24, H, W, mh, mw)
+    got = unmold.unmold_masks(cuda(masks), cuda(boxes), (H, W, 3)).cpu().numpy()
+    for i in range(masks.shape[0]):
+        want = oracle.unmold_mask(masks[i], boxes[i], (H, W, 3))
+        assert np.array_equal(got[i], want), (i, boxes[i].tolist(), int((got[i] != want).sum()))
+    one = unmold.unmold_mask(masks[3][None], boxes[3], (H, W, 3)).cpu().numpy()
+    assert np.array_equal(one, got[3])
+
+
+def test_unmold_detections_full_size_and_rle():
+    """model.py:747-806 end to end at 1024^2: detections + class masks -> boxes / pasted planes -> COCO RLE strings,
+    against the oracle (same numpy box arithmetic, restated resize) and the restated maskApi coder."""
+    from sln_amodal_b200 import rle, unmold
+    rng = np.random.default_rng(11)
+    H = W = 1024
+    N, pad = 12, 4
+    det = np.zeros((N + pad, 6), np.float32)
+    yx = rng.uniform(0, 700, (N, 2)).astype(np.float32)
+    det[:N, 0:2] = yx
+    det[:N, 2:4] = yx + rng.uniform(2, 320, (N, 2)).astype(np.float32)
+    det[:N, 4] = rng.integers(1, 5, N)
+    det[:N, 5] = rng.random(N)
+    det[3, 2] = det[3, 0]                                                   # zero-area detection: filtered out
+    mm = rng.random((N + pad, 28, 28, 2)).astype(np.float32)
+    window = np.array([0, 0, 1024, 1024])
+    boxes, cls, scores, planes = unmold.unmold_detections(det, mm, (H, W, 3), window, return_device_planes=True)
+    assert boxes.shape == (N - 1, 4) and planes.shape == (N - 1, H, W) and np.all(cls == 1)
+    keep = [i for i in range(N) if i != 3]
+    got = planes.cpu().numpy()
+    for j, i in enumerate(keep):
+        want = oracle.unmold_mask(mm[i, :, :, 1], boxes[j], (H, W, 3))
+        assert np.array_equal(got[j], want), (i, boxes[j].tolist())
+    enc = rle.encode(planes)
+    for j in range(len(keep)):
+        col = np.ascontiguousarray(got[j].T).reshape(-1)
+        assert enc[j]["counts"] == oracle.rle_to_string(oracle.rle_encode(col))
+    b2, c2, s2, hwn = unmold.unmold_detections(det, mm, (H, W, 3), window)
+    assert hwn.shape == (H, W, N - 1) and np.array_equal(hwn[:, :, 0], got[0])

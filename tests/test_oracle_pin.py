@@ -155,3 +155,38 @@ def test_rle_restatement_matches_reference_maskapi():
     for i in range(6):
         c = oracle.rle_encode(masks[i])
         assert np.array_equal(c, ref[i][0]) and oracle.rle_to_string(c) == ref[i][1]
+
+
+def test_unmold_restatement_matches_pillow():
+    """oracle.pil_resize_bilinear_u8 / unmold_mask (the restatement the CUDA kernel follows) against the real Pillow --
+    the library scipy.misc.imresize(interp='bilinear'), called by utils.unmold_mask (utils.py:459-460), runs."""
+    import pytest
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    for t in range(120):
+        mh, mw = (28, 28) if t % 3 else (int(rng.integers(1, 40)), int(rng.integers(1, 40)))
+        img = rng.integers(0, 256, (mh, mw)).astype(np.uint8)
+        oh, ow = int(rng.integers(1, 160)), int(rng.integers(1, 160))
+        want = np.asarray(Image.frombytes("L", (mw, mh), img.tobytes()).resize((ow, oh), resample=Image.BILINEAR))
+        assert np.array_equal(oracle.pil_resize_bilinear_u8(img, oh, ow), want), (mh, mw, oh, ow)
+    for t in range(40):
+        m = rng.random((28, 28)).astype(np.float32) ** 2
+        if t == 0:
+            m[:] = 0.25                                                     # constant mask: cscale == 0 branch
+        y1, x1 = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        y2, x2 = y1 + int(rng.integers(0, 70)), x1 + int(rng.integers(0, 70))
+        a = oracle.unmold_mask(m, (y1, x1, y2, x2), (128, 130, 3))
+        b = oracle.unmold_mask_pil(m, (y1, x1, y2, x2), (128, 130, 3))
+        assert a.shape == (128, 130) and np.array_equal(a, b)
+
+
+def test_bytescale_restatement_is_float32():
+    """scipy.misc.bytescale under numpy-1.x promotion computes in float32 (the array's dtype); the restatement must not
+    depend on the numpy-2 promotion rules of the interpreter it runs on."""
+    m = np.linspace(0, 1, 784, dtype=np.float32).reshape(28, 28) ** 3
+    b = oracle.bytescale_f32(m)
+    assert b.dtype == np.uint8 and b.min() == 0 and b.max() == 255
+    lo, hi = m.min(), m.max()
+    scale = np.float32(255.0 / float(np.float32(hi - lo)))
+    want = (np.clip((m - lo) * scale, 0, 255).astype(np.float32) + np.float32(0.5)).astype(np.uint8)
+    assert np.array_equal(b, want)
