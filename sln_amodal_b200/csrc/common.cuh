@@ -45,6 +45,38 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 int sm_count();   // cached per process, current device
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_chain(pdl = true) may be scheduled while its
+// predecessor in the stream is still running; pdl_prologue() at the very top of BOTH kernels makes the predecessor
+// allow that as soon as all of its CTAs are resident and makes the successor block until the predecessor has
+// completed and flushed -- only the launch latency and CTA placement overlap, never the bodies.  Without the launch
+// attribute both instructions are no-ops.  SLN_PDL=0 in the environment turns the attribute off (A/B).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();   // lib.cu: getenv("SLN_PDL") != "0", cached
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // One axis of the crop sampling grid, bit-compatible with crop_and_resize.c:44-56
 // (scale and sample position, un-fused fp32; the single-sample case is evaluated in
 // double like the reference's `0.5 * (y1 + y2) * (image_height - 1)`), :58/:80 (range

@@ -1,5 +1,6 @@
 // lib.cu -- library-level entry points and shared host helpers of libsln_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -24,6 +25,13 @@ int sm_count()
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
     cached = n;
     return n;
+}
+
+// read on every launch (a getenv is ~100 ns) so that one process can A/B both settings
+bool pdl_enabled()
+{
+    const char *e = getenv("SLN_PDL");
+    return !(e && e[0] == '0');
 }
 
 }  // namespace sln

@@ -97,6 +97,7 @@ rank_kernel(const float *__restrict__ scores, int stride, const int *__restrict_
 {
     __shared__ __align__(16) unsigned s_key[RANK_COLS];
     __shared__ __align__(16) unsigned s_tie[RANK_COLS];     // ~tie id
+    pdl_prologue();
     const int i0 = blockIdx.x * RANK_ROWS, i = i0 + threadIdx.x;
     const int j0 = blockIdx.y * RANK_COLS;
     const int jn = min(RANK_COLS, n - j0);
@@ -839,6 +840,7 @@ nms_bin_kernel(const float4 *__restrict__ boxes, const float *__restrict__ areas
     __shared__ float s_part[5];                    // this CTA's bounds + bad flag (read by the whole cluster)
     __shared__ int s_warp[SP_BIN_THREADS / 32];
     __shared__ int s_slice_tot;
+    pdl_prologue();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crank = (int)cluster.block_rank();
     const int NC = CB * G * G;
@@ -994,6 +996,7 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
     __shared__ unsigned s_buf[SP_PAIR_WARPS][SP_WARP_BUF];
     __shared__ int s_rs[SP_PAIR_WARPS][64];        // first item of each window row
     __shared__ int s_ri[SP_PAIR_WARPS][64];        // inclusive running count of candidates
+    pdl_prologue();
     const SparseHdr h = *sb.hdr;
     if (h.bail) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1131,6 +1134,7 @@ nms_sparse_resolve_kernel(const int *__restrict__ order, int n, int max_keep, un
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_wsum[SP_RESOLVE_THREADS / 32];
     __shared__ unsigned s_used;
+    pdl_prologue();
     if (sb.hdr->bail) return;                      // uniform over the cluster: nobody is left at a barrier
     if (sb.hdr->edge_count > edge_cap) return;     // status stays 0: dense path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1320,20 +1324,20 @@ static int launch_sparse(const float4 *boxes, const float *areas, const int *cls
     const float t = thresh > 1.f ? 1.f : thresh;
     const float ct = (1.f - t) * (t < 0.5f ? 0.5f / t : 1.f) * 1.01f;
     const unsigned edge_cap = (unsigned)SP_EDGES_PER_BOX * (unsigned)n;
-    if (cls) nms_bin_kernel<true><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb, sparse_only ? num_keep : nullptr);
-    else nms_bin_kernel<false><<<SP_CLUSTER, SP_BIN_THREADS, 0, st>>>(boxes, areas, cls, n, G, CB, sb, sparse_only ? num_keep : nullptr);
-    SLN_LAUNCH_OK("nms_bin_kernel");
+    // rank -> bin -> pairs -> resolve is a chain of short kernels: programmatic dependent launches (common.cuh)
+    int *preset = sparse_only ? num_keep : nullptr;
+    SLN_CUDA_OK(launch_chain(cls ? nms_bin_kernel<true> : nms_bin_kernel<false>, dim3(SP_CLUSTER), dim3(SP_BIN_THREADS), 0, st,
+                             true, boxes, areas, cls, n, G, CB, sb, preset));
     int ctas = cdiv(n, SP_PAIR_WARPS);
     if (ctas > SLN_SP_PAIR_CTAS_PER_SM * sm_count()) ctas = SLN_SP_PAIR_CTAS_PER_SM * sm_count();
-    if (cls) nms_pairs_kernel<true><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
-    else nms_pairs_kernel<false><<<ctas, 32 * SP_PAIR_WARPS, 0, st>>>(boxes, areas, cls, n, thresh, ct, edge_cap, sb);
-    SLN_LAUNCH_OK("nms_pairs_kernel");
+    SLN_CUDA_OK(launch_chain(cls ? nms_pairs_kernel<true> : nms_pairs_kernel<false>, dim3(ctas), dim3(32 * SP_PAIR_WARPS), 0, st,
+                             true, boxes, areas, cls, n, thresh, ct, edge_cap, sb));
     int items = cdiv(cdiv(n, 32), SP_CLUSTER * 32);
     if (items > SP_CACHE_ITEMS) items = SP_CACHE_ITEMS;
     const size_t smem = sizeof(unsigned) * (2 * SP_WORDS + 32) + 2 * SP_OV_CACHE + (size_t)items * SP_RESOLVE_THREADS * sizeof(uint4) * SP_INL_V;
     SLN_CUDA_OK(cudaFuncSetAttribute(nms_sparse_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_sparse_resolve_kernel<<<SP_CLUSTER, SP_RESOLVE_THREADS, smem, st>>>(order, n, max_keep, edge_cap, sb, keep64, keep32, num_keep);
-    SLN_LAUNCH_OK("nms_sparse_resolve_kernel");
+    SLN_CUDA_OK(launch_chain(nms_sparse_resolve_kernel, dim3(SP_CLUSTER), dim3(SP_RESOLVE_THREADS), smem, st, true, order, n,
+                             max_keep, edge_cap, sb, keep64, keep32, num_keep));
     *skip_out = &sb.hdr->status;
     return SLN_OK;
 }

@@ -80,6 +80,7 @@ select_hist_kernel(const float *__restrict__ probs, int A, int K, SelectState *_
                    unsigned *__restrict__ hist)
 {
     __shared__ unsigned s_hist[SEL_BINS];
+    pdl_prologue();
     for (int t = threadIdx.x; t < SEL_BINS; t += SEL_THREADS) s_hist[t] = 0u;
     unsigned prefix = 0u;
     if (PASS > 0) {
@@ -118,6 +119,7 @@ select_count_eq_kernel(const float *__restrict__ probs, int A, int K, SelectStat
                        const unsigned *__restrict__ hist, int *__restrict__ blk_eq)
 {
     __shared__ int s_cnt;
+    pdl_prologue();
     if (threadIdx.x == 0) s_cnt = 0;
     // pick of pass 2: the exact k-th key T and how many keys equal to T are still wanted
     const Pick p = cta_pick<2>(hist + 2 * SEL_BINS, state[0].prefix, state[0].k_rem);
@@ -146,6 +148,7 @@ select_compact_kernel(const float *__restrict__ probs, int A, SelectState *__res
 {
     __shared__ int s_warp[SEL_THREADS / 32];
     __shared__ int s_base;
+    pdl_prologue();
     state += 1;                                     // final state, published by select_count_eq_kernel
     const unsigned T = state->prefix;
     const int count_gt = state->count_gt, need_eq = state->k_rem;
@@ -226,6 +229,7 @@ __global__ void proposal_decode_kernel(const float *__restrict__ anchors, const 
                                        Float4Std sd, float img_h, float img_w, float4 *__restrict__ boxes,
                                        float *__restrict__ areas)
 {
+    pdl_prologue();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= K) return;
     const int a = cand_idx[j];
@@ -354,19 +358,21 @@ extern "C" int sln_proposal_layer(const float *probs, const float *deltas, const
         if (nblk > cdiv(A, SEL_THREADS)) nblk = cdiv(A, SEL_THREADS);
         SLN_CUDA_OK(cudaMemsetAsync(b.hist, 0, sizeof(unsigned) * 3 * SEL_BINS, st));
         select_hist_kernel<0><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);
-        select_hist_kernel<1><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);      // picks pass 0 -> state[1]
-        select_hist_kernel<2><<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist);      // picks pass 1 -> state[0]
-        select_count_eq_kernel<<<nblk, SEL_THREADS, 0, st>>>(probs, A, K, b.state, b.hist, b.blk_eq);   // picks pass 2 -> state[1]
-        select_compact_kernel<<<nblk, SEL_THREADS, 0, st>>>(probs, A, b.state, b.blk_eq, b.cand_score, b.cand_idx);
-        SLN_LAUNCH_OK("select kernels");
+        SLN_LAUNCH_OK("select_hist_kernel");
+        // the rest of the select chain as programmatic dependent launches (common.cuh): every kernel starts with pdl_prologue()
+        SLN_CUDA_OK(launch_chain(select_hist_kernel<1>, dim3(nblk), dim3(SEL_THREADS), 0, st, true, probs, A, K, b.state, b.hist));   // picks pass 0 -> state[1]
+        SLN_CUDA_OK(launch_chain(select_hist_kernel<2>, dim3(nblk), dim3(SEL_THREADS), 0, st, true, probs, A, K, b.state, b.hist));   // picks pass 1 -> state[0]
+        SLN_CUDA_OK(launch_chain(select_count_eq_kernel, dim3(nblk), dim3(SEL_THREADS), 0, st, true, probs, A, K, b.state,
+                                 (const unsigned *)b.hist, b.blk_eq));                                                           // picks pass 2 -> state[1]
+        SLN_CUDA_OK(launch_chain(select_compact_kernel, dim3(nblk), dim3(SEL_THREADS), 0, st, true, probs, A, b.state,
+                                 (const int *)b.blk_eq, b.cand_score, b.cand_idx));
     }
     SLN_CUDA_OK(cudaMemsetAsync(nb.rank, 0, sizeof(int) * (size_t)K, st));
     int rc = rank_sort_launch(b.cand_score, 1, b.cand_idx, K, nb.rank, st);
     if (rc != SLN_OK) return rc;
     Float4Std sd{std_dev_host[0], std_dev_host[1], std_dev_host[2], std_dev_host[3]};
-    proposal_decode_kernel<<<cdiv(K, 128), 128, 0, st>>>(anchors, deltas, b.cand_idx, nb.rank, K, sd, img_h, img_w,
-                                                        nb.boxes, nb.areas);
-    SLN_LAUNCH_OK("proposal_decode_kernel");
+    SLN_CUDA_OK(launch_chain(proposal_decode_kernel, dim3(cdiv(K, 128)), dim3(128), 0, st, true, anchors, deltas,
+                             (const int *)b.cand_idx, (const int *)nb.rank, K, sd, img_h, img_w, nb.boxes, nb.areas));
     rc = nms_sorted_launch(nb.boxes, nb.areas, nullptr, nullptr, K, nms_thresh, proposal_count, nb.mask, nullptr,
                            b.keep, b.num_keep, st, nb.stage, nb.fix, nb.sparse);
     if (rc != SLN_OK) return rc;
