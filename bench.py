@@ -371,6 +371,8 @@ def run_ours(args):
         extra["detection_targets"] = detection_targets_metric(dev, cpu=(world == 1))
         extra["rpn_targets"] = rpn_targets_metric(dev, cpu=(world == 1))
         extra["rle"] = rle_metric(dev, peak, cpu=(world == 1))
+        extra["unmold"] = unmold_metric(dev, peak, cpu=(world == 1))
+        extra["rpn_pack"] = rpn_pack_metric(dev, peak, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -712,6 +714,98 @@ def rle_metric(dev, peak, cpu=True):
         res["cpu_baseline"] = {"ms": round(cpu_s * 1e3, 1), "kind": "reference" if oracle.ref_mask_available() else "port", "cores": 1,
                                "identical": bool(all(o["counts"] == (r[1] if r[1] is not None else oracle.rle_to_string(r[0]))
                                                      for o, r in zip(out, ref)))}
+    return res
+
+
+def _event_us(fn, reps=10, flush=None):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ev.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ev))
+
+
+def unmold_metric(dev, peak, cpu=True):
+    """utils.unmold_mask for the 100 detections of one 1024^2 image (28x28 masks -> resize to the box,
+    threshold, paste) as one launch, then the device RLE; next to the oracle (scipy bytescale restated + Pillow-exact
+    resample) on the host for a bounded sample of the same detections.  Algorithmic bytes: the N*H*W planes written."""
+    import torch
+    from sln_amodal_b200 import rle, unmold
+    rng = np.random.default_rng(3)
+    N, H, W = 100, 1024, 1024
+    masks_np = rng.random((N, 28, 28)).astype(np.float32)
+    hw = np.exp(rng.uniform(np.log(24), np.log(600), (N, 2)))
+    y1x1 = rng.uniform(0, 1, (N, 2)) * (1024 - hw)
+    boxes_np = np.concatenate([y1x1, y1x1 + hw], 1).astype(np.int32)
+    masks, boxes = torch.from_numpy(masks_np).to(dev), torch.from_numpy(boxes_np).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    us = _event_us(lambda: unmold.unmold_masks(masks, boxes, (H, W)), flush=flush)
+    planes = unmold.unmold_masks(masks, boxes, (H, W))
+    t0 = time.perf_counter()
+    enc = rle.encode(unmold.unmold_masks(masks, boxes, (H, W)))
+    wall = time.perf_counter() - t0
+    res = {"what": "unmold_mask of 100 detections (28x28 -> box, threshold, paste) into 1024^2 planes, one launch",
+           "kernel_us": round(us, 1), "algorithmic_bytes": N * H * W, "achieved_gbs": round(N * H * W / us / 1e3, 1),
+           "frac": round(N * H * W / us / 1e3 / peak, 4), "l2": "flushed between iterations",
+           "unmold_plus_rle_encode_ms": round(wall * 1e3, 2)}
+    if cpu:
+        from oracle import oracle
+        k = 20
+        t0 = time.perf_counter()
+        want = [oracle.unmold_mask(masks_np[i], boxes_np[i], (H, W)) for i in range(k)]
+        cpu_s = time.perf_counter() - t0
+        got = planes[:k].cpu().numpy()
+        res["cpu_baseline"] = {"ms_per_100_detections": round(cpu_s * 1e3 * N / k, 1), "kind": "port", "cores": 1,
+                               "sample": "first %d of the 100 detections" % k,
+                               "identical": bool(all(np.array_equal(got[i], want[i]) for i in range(k)))}
+        del enc
+    return res
+
+
+def rpn_pack_metric(dev, peak, cpu=True):
+    """RPN output re-layout for one 1024^2 image (five levels, 261 888 anchors): one launch against the
+    reference's expression (10 permute copies + 5 softmax + 3 cat) in torch on the same device and on the host."""
+    import torch
+    from sln_amodal_b200 import rpn
+    torch.manual_seed(5)
+    sizes = (256, 128, 64, 32, 16)
+    cls_maps = [torch.randn(1, 6, s, s, device=dev) * 4 for s in sizes]
+    box_maps = [torch.randn(1, 12, s, s, device=dev) for s in sizes]
+
+    def ref_expr(cm, bm):
+        lg = [c.permute(0, 2, 3, 1).contiguous().view(c.size(0), -1, 2) for c in cm]
+        pr = [torch.softmax(x, dim=2) for x in lg]
+        bx = [b.permute(0, 2, 3, 1).contiguous().view(b.size(0), -1, 4) for b in bm]
+        return torch.cat(lg, 1), torch.cat(pr, 1), torch.cat(bx, 1)
+
+    us = _event_us(lambda: rpn.rpn_pack(cls_maps, box_maps), reps=20)
+    us_t = _event_us(lambda: ref_expr(cls_maps, box_maps), reps=20)
+    ours, ref = rpn.rpn_pack(cls_maps, box_maps), ref_expr(cls_maps, box_maps)
+    A = ours[0].shape[1]
+    nbytes = A * (2 + 4) * 4 * 2 + A * 2 * 4                                  # read 6 floats, write 8 per anchor
+    res = {"what": "RPN re-layout + softmax + concat, 5 levels, %d anchors, one launch" % A, "us": round(us, 1),
+           "torch_expression_same_device_us": round(us_t, 1), "algorithmic_bytes": nbytes,
+           "achieved_gbs": round(nbytes / us / 1e3, 1), "bound": "launch latency (6.3 MB per image)",
+           "copies_identical": bool(torch.equal(ours[0], ref[0]) and torch.equal(ours[2], ref[2])),
+           "softmax_bit_identical_to_torch_cuda": bool(torch.equal(ours[1], ref[1])),
+           "softmax_max_rel_err_vs_torch_cuda": float(((ours[1] - ref[1]).abs() / ref[1].abs().clamp_min(1e-30)).max().item())}
+    if cpu:
+        cm, bm = [c.cpu() for c in cls_maps], [b.cpu() for b in box_maps]
+        ref_expr(cm, bm)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ref_expr(cm, bm)
+        res["cpu_baseline"] = {"ms": round((time.perf_counter() - t0) / 5 * 1e3, 2), "kind": "port",
+                               "cores": torch.get_num_threads(), "sample": "the same image, torch-CPU expression of modals.py:394-410 + model.py:553-563"}
     return res
 
 

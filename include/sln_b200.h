@@ -218,6 +218,22 @@ SLN_API int sln_unmold_masks(const float *masks, int N, int mh, int mw, const in
 SLN_API int sln_gather_planes(const uint8_t *src, int n, int H, int W, const int *iy, const int *ix, int H2, int W2,
                       uint8_t *dst, void *stream);
 
+/* ---- RPN output re-layout ------------------------------------- *
+ * Replaces, for all pyramid levels at once, the per-level permute(0,2,3,1).contiguous().view + Softmax(dim=2) of
+ * RPN.forward (modal/modals.py:388-412) and the concatenation over levels of MaskRCNN.predict (model.py:553-563).
+ * logits[l] f32 [B,2a,H_l,W_l], bbox[l] f32 [B,4a,H_l,W_l] (host arrays of n_levels device pointers; layout =
+ * SLN_LAYOUT_NCHW, or SLN_LAYOUT_NHWC for channels_last conv outputs); a = anchors per location.  With
+ * A = a * sum_l H_l*W_l:  out_logits f32 [B,A,2], out_probs f32 [B,A,2] = softmax over the last axis, out_bbox f32
+ * [B,A,4]; row (y*W_l + x)*a + k of level l, value j <- channel 2k+j (4k+j).  Any output (and either input list) may
+ * be NULL.  sln_rpn_unpack_grads is the backward of the two copies: it writes every element of d_logits[l] / d_bbox[l]
+ * (same shapes and layout as the inputs) from g_logits [B,A,2] / g_bbox [B,A,4] (a NULL gradient writes zeros).     */
+SLN_API int sln_rpn_pack(const float *const *logits, const float *const *bbox, const int *heights, const int *widths,
+                 int n_levels, int B, int a, int layout, float *out_logits, float *out_probs, float *out_bbox,
+                 void *stream);
+SLN_API int sln_rpn_unpack_grads(const float *g_logits, const float *g_bbox, const int *heights, const int *widths,
+                         int n_levels, int B, int a, int layout, float *const *d_logits, float *const *d_bbox,
+                         void *stream);
+
 /* ---- proposal_layer ----------------------------------------------------- *
  * Replaces proposal_layer (modal/Functions.py:114-178) for one image:
  * fg score = probs[:,1]; deltas *= std_dev; top `pre_nms_limit` anchors by score

@@ -789,3 +789,24 @@ def unmold_mask_pil(mask, bbox, image_shape):
     r = np.asarray(im.resize((x2 - x1, y2 - y1), resample=Image.BILINEAR), dtype=np.uint8)
     small = np.where(r.astype(np.float32) / np.float32(255.0) >= 0.5, 1, 0).astype(np.uint8)
     return _paste(small, bbox, image_shape)
+
+
+# ---------------------------------------------------------------------------
+# RPN output re-layout: RPN.forward's permute / view / softmax (modal/modals.py:
+# 394-410) and the concatenation over levels (model.py:553-563), restated with numpy index arithmetic.
+# ---------------------------------------------------------------------------
+def rpn_pack(class_maps, bbox_maps):
+    """class_maps[l] f32 [B,2a,H,W], bbox_maps[l] f32 [B,4a,H,W] -> (logits [B,A,2], probs [B,A,2], bbox [B,A,4])."""
+    lg, bx = [], []
+    for c, b in zip(class_maps, bbox_maps):
+        c = np.asarray(c, np.float32)
+        b = np.asarray(b, np.float32)
+        B = c.shape[0]
+        lg.append(np.ascontiguousarray(c.transpose(0, 2, 3, 1)).reshape(B, -1, 2))        # modals.py:394-397
+        bx.append(np.ascontiguousarray(b.transpose(0, 2, 3, 1)).reshape(B, -1, 4))        # modals.py:407-410
+    logits = np.concatenate(lg, axis=1)                                                   # model.py:560
+    bbox = np.concatenate(bx, axis=1)
+    m = logits.max(axis=2, keepdims=True)
+    e = np.exp((logits - m).astype(np.float32)).astype(np.float32)                        # Softmax(dim=2), modals.py:400
+    probs = (e / (e[..., :1] + e[..., 1:]).astype(np.float32)).astype(np.float32)
+    return logits, probs, bbox

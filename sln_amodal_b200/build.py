@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsln_b200.so")
-SOURCES = ["lib.cu", "crop.cu", "nms.cu", "proposal.cu", "semdist.cu", "detection.cu", "rle.cu", "unmold.cu"]
+SOURCES = ["lib.cu", "crop.cu", "nms.cu", "proposal.cu", "semdist.cu", "detection.cu", "rle.cu", "unmold.cu", "rpn.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "nms_core.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sln_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

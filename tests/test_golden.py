@@ -233,3 +233,13 @@ def test_gpu_build_rpn_targets_matches_reference_python():
     assert np.array_equal(am.cpu().numpy(), np.argmax(ov, axis=1))
     assert np.array_equal(mx.cpu().numpy(), ov[np.arange(ov.shape[0]), np.argmax(ov, axis=1)], equal_nan=True)
     assert np.array_equal(ga.cpu().numpy(), np.argmax(ov, axis=0))
+
+
+def test_rpn_pack_oracle_matches_reference_module():
+    """oracle.rpn_pack against the reference's own RPN module + MaskRCNN.predict concatenation (fixture made by
+    tests/golden/make_golden_rpn.py): copies bit for bit, softmax within 2 ulp of torch's CPU kernel (numpy's exp)."""
+    g = np.load(os.path.join(G, "rpn_pack.npz"))
+    logits, probs, bbox = oracle.rpn_pack([g["cls_%d" % l] for l in range(3)], [g["box_%d" % l] for l in range(3)])
+    assert np.array_equal(logits, g["rpn_class_logits"])
+    assert np.array_equal(bbox, g["rpn_bbox"])
+    assert np.allclose(probs, g["rpn_class"], rtol=3e-7, atol=0)

@@ -789,3 +789,61 @@ def test_unmold_detections_full_size_and_rle():
         assert enc[j]["counts"] == oracle.rle_to_string(oracle.rle_encode(col))
     b2, c2, s2, hwn = unmold.unmold_detections(det, mm, (H, W, 3), window)
     assert hwn.shape == (H, W, N - 1) and np.array_equal(hwn[:, :, 0], got[0])
+
+
+# --------------------------------------------------------------------------- RPN re-layout (8(f)-4)
+def _ref_rpn_expr(cls_maps, box_maps):
+    """RPN.forward's re-layout (modal/modals.py:394-410) + the concatenation of model.py:553-563, as torch ops."""
+    lg = [c.permute(0, 2, 3, 1).contiguous().view(c.size(0), -1, 2) for c in cls_maps]
+    bx = [b.permute(0, 2, 3, 1).contiguous().view(b.size(0), -1, 4) for b in box_maps]
+    return torch.cat(lg, 1), torch.cat([torch.softmax(x, dim=2) for x in lg], 1), torch.cat(bx, 1)
+
+
+def test_rpn_pack_matches_reference_module_fixture():
+    """sln_rpn_pack on the conv outputs captured from the reference's RPN module against what the module + the
+    concatenation of MaskRCNN.predict returned (tests/golden/rpn_pack.npz): logits and deltas bit for bit; softmax within
+    1e-6 relative of the reference's CPU kernel (the only floating-point step; tolerance per BASELINE north_star 1e-5)."""
+    import os
+    from sln_amodal_b200 import rpn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rpn_pack.npz"))
+    cls_maps = [cuda(g["cls_%d" % l]) for l in range(3)]
+    box_maps = [cuda(g["box_%d" % l]) for l in range(3)]
+    logits, probs, bbox = rpn.rpn_pack(cls_maps, box_maps)
+    assert np.array_equal(logits.cpu().numpy(), g["rpn_class_logits"])
+    assert np.array_equal(bbox.cpu().numpy(), g["rpn_bbox"])
+    assert np.allclose(probs.cpu().numpy(), g["rpn_class"], rtol=1e-6, atol=0)
+    # channels_last conv outputs take the NHWC branch: same result
+    cl = [t.contiguous(memory_format=torch.channels_last) for t in cls_maps]
+    bl = [t.contiguous(memory_format=torch.channels_last) for t in box_maps]
+    l2, p2, b2 = rpn.rpn_pack(cl, bl)
+    assert torch.equal(l2, logits) and torch.equal(p2, probs) and torch.equal(b2, bbox)
+
+
+@pytest.mark.parametrize("a", [3, 2])
+def test_rpn_pack_full_size_and_backward(a):
+    """BASELINE shape (five levels of a 1024^2 image, 261 888 anchors at a = 3): forward against the torch expression of
+    the reference on the same device (copies bit-exact, softmax <= 1e-6 relative), oracle on one level, and the backward
+    launch against autograd through that expression."""
+    from sln_amodal_b200 import rpn
+    torch.manual_seed(5)
+    sizes = (256, 128, 64, 32, 16)
+    cls_maps = [torch.randn(1, 2 * a, s, s, device=dev()) * 4 for s in sizes]
+    box_maps = [torch.randn(1, 4 * a, s, s, device=dev()) for s in sizes]
+    c1 = [t.clone().requires_grad_(True) for t in cls_maps]
+    b1 = [t.clone().requires_grad_(True) for t in box_maps]
+    c2 = [t.clone().requires_grad_(True) for t in cls_maps]
+    b2 = [t.clone().requires_grad_(True) for t in box_maps]
+    logits, probs, bbox = rpn.rpn_pack(c1, b1)
+    rl, rp, rb = _ref_rpn_expr(c2, b2)
+    assert logits.shape == (1, a * 87296, 2) and torch.equal(logits, rl) and torch.equal(bbox, rb)
+    assert torch.allclose(probs, rp, rtol=1e-6, atol=0)
+    ol, op, ob = oracle.rpn_pack([cls_maps[4].cpu().numpy()], [box_maps[4].cpu().numpy()])
+    n4 = a * 256
+    assert np.array_equal(logits[:, -n4:].cpu().numpy(), ol) and np.array_equal(bbox[:, -n4:].cpu().numpy(), ob)
+    assert np.allclose(probs[:, -n4:].cpu().numpy(), op, rtol=1e-6, atol=0)
+    wl, wb = torch.randn_like(rl), torch.randn_like(rb)
+    ((logits * wl).sum() + (bbox * wb).sum()).backward()
+    ((rl * wl).sum() + (rb * wb).sum()).backward()
+    for x, y in zip(c1 + b1, c2 + b2):
+        assert torch.equal(x.grad, y.grad)
+    assert not probs.requires_grad
