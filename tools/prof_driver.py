@@ -1,5 +1,5 @@
 """Short driver for ncu captures: runs one family of kernels a few times on the bench workload.
-    python tools/prof_driver.py {crop|nms|proposal|semdist|targets} [reps]
+    python tools/prof_driver.py {crop|nms|proposal|semdist|targets|after} [reps]
 """
 import os
 import sys
@@ -56,5 +56,10 @@ elif what == "targets":
         bench.detection_targets_metric(dev0, cpu=False)
         bench.rpn_targets_metric(dev0, cpu=False)
         bench.rle_metric(dev0, 6650.0, cpu=False)
+elif what == "after":
+    # the steps either side of the path added last: mask paste (unmold) and the RPN re-layout
+    for _ in range(reps):
+        bench.unmold_metric(dev, 6650.0, cpu=False)
+        bench.rpn_pack_metric(dev, 6650.0, cpu=False)
 torch.cuda.synchronize()
 print("done", what)
