@@ -839,8 +839,8 @@ def test_rpn_pack_full_size_and_backward(a):
     assert torch.allclose(probs, rp, rtol=1e-6, atol=0)
     ol, op, ob = oracle.rpn_pack([cls_maps[4].cpu().numpy()], [box_maps[4].cpu().numpy()])
     n4 = a * 256
-    assert np.array_equal(logits[:, -n4:].cpu().numpy(), ol) and np.array_equal(bbox[:, -n4:].cpu().numpy(), ob)
-    assert np.allclose(probs[:, -n4:].cpu().numpy(), op, rtol=1e-6, atol=0)
+    assert np.array_equal(logits.detach()[:, -n4:].cpu().numpy(), ol) and np.array_equal(bbox.detach()[:, -n4:].cpu().numpy(), ob)
+    assert np.allclose(probs.detach()[:, -n4:].cpu().numpy(), op, rtol=1e-6, atol=0)
     wl, wb = torch.randn_like(rl), torch.randn_like(rb)
     ((logits * wl).sum() + (bbox * wb).sum()).backward()
     ((rl * wl).sum() + (rb * wb).sum()).backward()
