@@ -212,6 +212,14 @@ SLN_API long long sln_rle_to_string(const uint32_t *counts, long long m, char *o
 SLN_API int sln_unmold_masks(const float *masks, int N, int mh, int mw, const int *boxes, int H, int W,
                      uint8_t *out, void *stream);
 
+/* Image resize in front of the path: utils.resize_image (utils.py:301-356) squashes the uint8 image to
+ * (max_dim, max_dim) with scipy.misc.imresize = Pillow's 8-bit bilinear resample per band (triangle filter of support
+ * max(1, in/out), 22-bit fixed-point coefficients, horizontal pass first with an 8-bit intermediate) -- reproduced bit
+ * for bit.  src u8 [h,w,C] (interleaved channels), out u8 [H2,W2,C]; three launches, workspace from the query below. */
+SLN_API size_t sln_resize_image_workspace_bytes(int h, int w, int C, int H2, int W2);
+SLN_API int sln_resize_image_u8(const uint8_t *src, int h, int w, int C, int H2, int W2, uint8_t *out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* Nearest-neighbour zoom / flip of n u8 planes as a gather (utils.resize_layer, utils.py:358-362; np.fliplr,
  * Functions.py:712-715): dst[p][y][x] = src[p][iy[y]][ix[x]], 0 where an index is negative.  iy i32 [H2], ix i32 [W2] on
  * the device, computed by the caller with scipy.ndimage.zoom's float64 rule (sln_amodal_b200/targets.py).          */

@@ -14,6 +14,8 @@
 // box columns, runs the horizontal pass only for the mask rows its vertical taps reach, and writes its slab once:
 // 16 pixels per thread from one 16-byte shared-memory read per tap (the intermediate is stored at column offset
 // x1 & 15, so image-aligned 16-pixel units are aligned in shared memory too).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace sln {
@@ -221,9 +223,119 @@ unmold_kernel(const float *__restrict__ masks, int mh, int mw, const int *__rest
     }
 }
 
+// ---------------------------------------------------------------------------
+// utils.resize_image (utils.py:301-356): scipy.misc.imresize(image, (max_dim, max_dim)) of the uint8 RGB image =
+// Pillow's 8-bit bilinear resample per band (no bytescale for uint8 input).  Same coefficient code as above:
+// a table launch, a horizontal pass into an 8-bit intermediate [h, W2, C], a vertical pass.
+// ---------------------------------------------------------------------------
+struct ResizeTabs {
+    int *hx, *hk, *vy, *vk;      // xmin | count << 16 and coefficient rows of the two axes
+    int tH, tV;
+};
+
+__global__ void __launch_bounds__(256)
+resize_coeffs_kernel(int h, int w, int H2, int W2, ResizeTabs t)
+{
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W2) t.hx[i] = pil_axis(w, W2, i, t.hk + (size_t)i * t.tH);
+    else if (i < W2 + H2) t.vy[i - W2] = pil_axis(h, H2, i - W2, t.vk + (size_t)(i - W2) * t.tV);
+}
+
+// tmp[r][xx][c] = clip8((2^21 + sum_t src[r][xmin+t][c] * k[t]) >> 22)
+__global__ void __launch_bounds__(256)
+resize_h_kernel(const uint8_t *__restrict__ src, int h, int w, int C, int W2, ResizeTabs t, uint8_t *__restrict__ tmp)
+{
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)h * W2) return;
+    const int r = (int)(i / W2), xx = (int)(i - (long long)r * W2);
+    const int pk = t.hx[xx], xmin = pk & 0xffff, cnt = pk >> 16;
+    const int *k = t.hk + (size_t)xx * t.tH;
+    const uint8_t *s = src + ((size_t)r * w + xmin) * C;
+    for (int c = 0; c < C; ++c) {
+        int acc = 1 << (PIL_BITS - 1);
+        for (int q = 0; q < cnt; ++q) acc += (int)s[(size_t)q * C + c] * __ldg(k + q);
+        acc >>= PIL_BITS;
+        tmp[((size_t)r * W2 + xx) * C + c] = (uint8_t)min(max(acc, 0), 255);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+resize_v_kernel(const uint8_t *__restrict__ tmp, int C, int H2, int W2, ResizeTabs t, uint8_t *__restrict__ out)
+{
+    pdl_prologue();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per output byte (x, c fastest)
+    const long long rowb = (long long)W2 * C;
+    if (i >= (long long)H2 * rowb) return;
+    const int yy = (int)(i / rowb);
+    const long long xc = i - (long long)yy * rowb;
+    const int pk = t.vy[yy], ymin = pk & 0xffff, cnt = pk >> 16;
+    const int *k = t.vk + (size_t)yy * t.tV;
+    int acc = 1 << (PIL_BITS - 1);
+    for (int q = 0; q < cnt; ++q) acc += (int)tmp[(size_t)(ymin + q) * rowb + xc] * __ldg(k + q);
+    acc >>= PIL_BITS;
+    out[i] = (uint8_t)min(max(acc, 0), 255);
+}
+
+static int resize_taps_host(int in_size, int out_size)
+{
+    const double scale = (double)in_size / (double)out_size;
+    const double fs = scale < 1.0 ? 1.0 : scale;
+    const int ksize = (int)ceil(fs) * 2 + 1;
+    return ksize < in_size ? ksize : in_size;
+}
+
+static size_t resize_ws_layout(int h, int w, int C, int H2, int W2, size_t off[5])
+{
+    const int tH = resize_taps_host(w, W2), tV = resize_taps_host(h, H2);
+    size_t o = 0;
+    off[0] = o; o += align_up(sizeof(int) * (size_t)W2, 256);
+    off[1] = o; o += align_up(sizeof(int) * (size_t)W2 * tH, 256);
+    off[2] = o; o += align_up(sizeof(int) * (size_t)H2, 256);
+    off[3] = o; o += align_up(sizeof(int) * (size_t)H2 * tV, 256);
+    off[4] = o; o += align_up((size_t)h * W2 * C, 256);
+    return o;
+}
+
 }  // namespace sln
 
 using namespace sln;
+
+extern "C" size_t sln_resize_image_workspace_bytes(int h, int w, int C, int H2, int W2)
+{
+    if (h <= 0 || w <= 0 || C <= 0 || H2 <= 0 || W2 <= 0) return 0;
+    size_t off[5];
+    return resize_ws_layout(h, w, C, H2, W2, off);
+}
+
+extern "C" int sln_resize_image_u8(const uint8_t *src, int h, int w, int C, int H2, int W2, uint8_t *out, void *workspace,
+                                   size_t workspace_bytes, void *stream)
+{
+    SLN_REQUIRE(h > 0 && w > 0 && C > 0 && H2 > 0 && W2 > 0, SLN_ERR_ARG, "bad resize shape");
+    SLN_REQUIRE(h < 65536 && w < 65536 && H2 < 65536 && W2 < 65536 && C <= 16, SLN_ERR_ARG, "resize: sides < 65536, C <= 16");
+    SLN_REQUIRE(src && out, SLN_ERR_ARG, "null pointer");
+    size_t off[5];
+    const size_t need = resize_ws_layout(h, w, C, H2, W2, off);
+    SLN_REQUIRE(workspace && workspace_bytes >= need, SLN_ERR_WORKSPACE, "resize workspace: need %zu bytes, got %zu", need, workspace_bytes);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    ResizeTabs t;
+    t.hx = reinterpret_cast<int *>(ws + off[0]);
+    t.hk = reinterpret_cast<int *>(ws + off[1]);
+    t.vy = reinterpret_cast<int *>(ws + off[2]);
+    t.vk = reinterpret_cast<int *>(ws + off[3]);
+    t.tH = resize_taps_host(w, W2);
+    t.tV = resize_taps_host(h, H2);
+    uint8_t *tmp = ws + off[4];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    resize_coeffs_kernel<<<cdiv(W2 + H2, 256), 256, 0, st>>>(h, w, H2, W2, t);
+    SLN_LAUNCH_OK("resize_coeffs_kernel");
+    const long long nh = (long long)h * W2, nv = (long long)H2 * W2 * C;
+    SLN_REQUIRE((nh + 255) / 256 < (1ll << 31) && (nv + 255) / 256 < (1ll << 31), SLN_ERR_ARG, "resize: image too large");
+    SLN_CUDA_OK(launch_chain(resize_h_kernel, dim3((unsigned)((nh + 255) / 256)), dim3(256), 0, st, true, src, h, w, C, W2, t, tmp));
+    SLN_CUDA_OK(launch_chain(resize_v_kernel, dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, st, true, (const uint8_t *)tmp, C, H2, W2, t, out));
+    return SLN_OK;
+}
 
 extern "C" int sln_unmold_masks(const float *masks, int N, int mh, int mw, const int *boxes, int H, int W,
                                 uint8_t *out, void *stream)
