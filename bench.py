@@ -373,6 +373,7 @@ def run_ours(args):
         extra["rle"] = rle_metric(dev, peak, cpu=(world == 1))
         extra["unmold"] = unmold_metric(dev, peak, cpu=(world == 1))
         extra["rpn_pack"] = rpn_pack_metric(dev, peak, cpu=(world == 1))
+        extra["resize_image"] = resize_image_metric(dev, cpu=(world == 1))
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -806,6 +807,35 @@ def rpn_pack_metric(dev, peak, cpu=True):
             ref_expr(cm, bm)
         res["cpu_baseline"] = {"ms": round((time.perf_counter() - t0) / 5 * 1e3, 2), "kind": "port",
                                "cores": torch.get_num_threads(), "sample": "the same image, torch-CPU expression of modals.py:394-410 + model.py:553-563"}
+    return res
+
+
+def resize_image_metric(dev, cpu=True):
+    """utils.resize_image of one D2SA-sized RGB image (1440 x 1920 -> 1024^2, Pillow-exact bilinear) in
+    three launches, image already on the device; next to Pillow itself on one host core (what the reference calls)."""
+    import torch
+    from sln_amodal_b200 import targets
+    rng = np.random.default_rng(12)
+    img_np = rng.integers(0, 256, (1440, 1920, 3)).astype(np.uint8)
+    img = torch.from_numpy(img_np).to(dev)
+    us = _event_us(lambda: targets.resize_image_device(img, (1024, 1024)), reps=20)
+    nbytes = img_np.size + 1024 * 1024 * 3
+    res = {"what": "resize_image 1440x1920x3 u8 -> 1024x1024x3 (Pillow-exact bilinear), 3 launches", "us": round(us, 1),
+           "algorithmic_bytes": nbytes, "achieved_gbs": round(nbytes / us / 1e3, 1), "bound": "launch latency (11.4 MB per image)"}
+    if cpu:
+        from oracle import oracle
+        got = targets.resize_image_device(img, (1024, 1024)).cpu().numpy()
+        try:
+            oracle.resize_image_pil(img_np, (1024, 1024))
+            t0 = time.perf_counter()
+            want = oracle.resize_image_pil(img_np, (1024, 1024))
+            kind, cpu_s = "reference library (Pillow)", time.perf_counter() - t0
+        except ImportError:
+            t0 = time.perf_counter()
+            want = oracle.resize_image(img_np, (1024, 1024))
+            kind, cpu_s = "port", time.perf_counter() - t0
+        res["cpu_baseline"] = {"ms": round(cpu_s * 1e3, 2), "kind": kind, "cores": 1, "sample": "the same image",
+                               "identical": bool(np.array_equal(got, want))}
     return res
 
 

@@ -810,3 +810,23 @@ def rpn_pack(class_maps, bbox_maps):
     e = np.exp((logits - m).astype(np.float32)).astype(np.float32)                        # Softmax(dim=2), modals.py:400
     probs = (e / (e[..., :1] + e[..., 1:]).astype(np.float32)).astype(np.float32)
     return logits, probs, bbox
+
+
+def resize_image(image, out_hw):
+    """utils.resize_image's scipy.misc.imresize(image, (max_dim, max_dim)) (utils.py:352) for a uint8 image [h, w] or
+    [h, w, C]: no bytescale for uint8 input, Pillow's 8-bit bilinear resample per band (pil_resize_bilinear_u8)."""
+    a = np.asarray(image)
+    assert a.dtype == np.uint8
+    if a.ndim == 2:
+        return pil_resize_bilinear_u8(a, int(out_hw[0]), int(out_hw[1]))
+    return np.stack([pil_resize_bilinear_u8(np.ascontiguousarray(a[:, :, c]), int(out_hw[0]), int(out_hw[1]))
+                     for c in range(a.shape[2])], axis=2)
+
+
+def resize_image_pil(image, out_hw):
+    """The same through the real Pillow (toimage of a uint8 [h, w, 3] array is mode 'RGB'); pins resize_image()."""
+    from PIL import Image
+    a = np.ascontiguousarray(image)
+    mode = "L" if a.ndim == 2 else {3: "RGB", 4: "RGBA"}[a.shape[2]]
+    im = Image.frombytes(mode, (a.shape[1], a.shape[0]), a.tobytes())
+    return np.asarray(im.resize((int(out_hw[1]), int(out_hw[0])), resample=Image.BILINEAR), dtype=np.uint8)

@@ -36,36 +36,42 @@ def _is_nhwc(t):
 
 def _uniform_layout(maps):
     """-> (tensors, nhwc flag): all levels dense in one layout (channels_last kept as it is, anything else -> NCHW)"""
-    nhwc = all(_is_nhwc(m) and m.is_contiguous(memory_format=torch.channels_last) for m in maps)
-    if nhwc:
+    if all(m.is_contiguous() for m in maps):
+        return list(maps), False
+    if all(_is_nhwc(m) and m.is_contiguous(memory_format=torch.channels_last) for m in maps):
         return list(maps), True
     return [m.contiguous() for m in maps], False
+
+
+def _pack_forward(a, want_probs, n_levels, maps):
+    """-> (logits, probs or None, bbox, nhwc flag, dense tensors): the one launch"""
+    B = maps[0].shape[0]
+    for l in range(n_levels):
+        c, b = maps[l], maps[n_levels + l]
+        if not (c.is_cuda and b.is_cuda) or c.dtype != torch.float32 or b.dtype != torch.float32 or c.dim() != 4 or b.dim() != 4:
+            raise _lib.SlnError("rpn_pack: float32 CUDA tensors [B, C, H, W] expected (there is no CPU fallback)")
+        if c.shape[1] != 2 * a or b.shape[1] != 4 * a or c.shape[2:] != b.shape[2:] or c.shape[0] != B or b.shape[0] != B:
+            raise _lib.SlnError("rpn_pack: level shapes must be [B, 2a, H, W] / [B, 4a, H, W]")
+    tens, nhwc = _uniform_layout(maps)
+    nl, hs, ws = _level_args(tens[:n_levels])
+    A = a * sum(int(m.shape[2]) * int(m.shape[3]) for m in tens[:n_levels])
+    dev = tens[0].device
+    logits = torch.empty((B, A, 2), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, A, 2), dtype=torch.float32, device=dev) if want_probs else None
+    bbox = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    if B and A:
+        with torch.cuda.device(dev):
+            check(lib().sln_rpn_pack(_ptrs(tens[:n_levels]), _ptrs(tens[n_levels:]), hs, ws, nl, B, a,
+                                     _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW, ptr(logits), ptr(probs), ptr(bbox), stream_ptr()),
+                  "sln_rpn_pack")
+        _lib.count_launches(1)
+    return logits, probs, bbox, nhwc, tens
 
 
 class _RpnPack(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, want_probs, n_levels, *maps):
-        cls_maps, box_maps = maps[:n_levels], maps[n_levels:]
-        for m in maps:
-            if not m.is_cuda or m.dtype != torch.float32 or m.dim() != 4:
-                raise _lib.SlnError("rpn_pack: float32 CUDA tensors [B, C, H, W] expected (there is no CPU fallback)")
-        B = cls_maps[0].shape[0]
-        for c, b in zip(cls_maps, box_maps):
-            if c.shape[1] != 2 * a or b.shape[1] != 4 * a or c.shape[2:] != b.shape[2:] or c.shape[0] != B or b.shape[0] != B:
-                raise _lib.SlnError("rpn_pack: level shapes must be [B, 2a, H, W] / [B, 4a, H, W]")
-        tens, nhwc = _uniform_layout(list(cls_maps) + list(box_maps))
-        cls_t, box_t = tens[:n_levels], tens[n_levels:]
-        nl, hs, ws = _level_args(cls_t)
-        A = a * sum(int(m.shape[2]) * int(m.shape[3]) for m in cls_t)
-        dev = cls_t[0].device
-        logits = torch.empty((B, A, 2), dtype=torch.float32, device=dev)
-        probs = torch.empty((B, A, 2), dtype=torch.float32, device=dev) if want_probs else None
-        bbox = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
-        if B and A:
-            with torch.cuda.device(dev):
-                check(lib().sln_rpn_pack(_ptrs(cls_t), _ptrs(box_t), hs, ws, nl, B, a, _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW,
-                                         ptr(logits), ptr(probs), ptr(bbox), stream_ptr()), "sln_rpn_pack")
-            _lib.count_launches(1)
+        logits, probs, bbox, nhwc, tens = _pack_forward(a, want_probs, n_levels, list(maps))
         ctx.a, ctx.n_levels, ctx.nhwc = a, n_levels, nhwc
         ctx.shapes = [tuple(m.shape) for m in tens]
         if probs is None:
@@ -98,7 +104,11 @@ def rpn_pack(class_maps, bbox_maps, anchors_per_location=None, want_probs=True):
     if len(class_maps) != len(bbox_maps) or not class_maps:
         raise _lib.SlnError("rpn_pack: one class map and one bbox map per level")
     a = int(anchors_per_location) if anchors_per_location else int(class_maps[0].shape[1]) // 2
-    logits, probs, bbox = _RpnPack.apply(a, bool(want_probs), len(class_maps), *class_maps, *bbox_maps)
+    maps = list(class_maps) + list(bbox_maps)
+    if not (torch.is_grad_enabled() and any(m.requires_grad for m in maps)):        # inference: no autograd node
+        logits, probs, bbox = _pack_forward(a, bool(want_probs), len(class_maps), maps)[:3]
+        return [logits, probs, bbox]
+    logits, probs, bbox = _RpnPack.apply(a, bool(want_probs), len(class_maps), *maps)
     return [logits, probs if want_probs else None, bbox]
 
 

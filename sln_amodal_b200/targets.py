@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .crop_and_resize import CropAndResizeFunction
 
 
@@ -227,3 +227,37 @@ def resize_layer(mask, scale, padding=None):
     planes = torch.from_numpy(np.ascontiguousarray(np.moveaxis(m, (0, 1), (-2, -1))).astype(np.uint8)).cuda()
     out = resize_layer_device(planes, scale).cpu().numpy()
     return np.moveaxis(out, (-2, -1), (0, 1)).astype(m.dtype)
+
+
+def resize_image_device(image, out_hw):
+    """scipy.misc.imresize(image, out_hw) (interp='bilinear') of a uint8 image [h, w] or [h, w, C] on the device:
+    Pillow's 8-bit bilinear resample per band, bit for bit (sln_resize_image_u8).  numpy or tensor in, CUDA u8 out."""
+    if not torch.cuda.is_available():
+        raise _lib.SlnError("resize_image_device needs a CUDA device (there is no CPU fallback)")
+    t = torch.as_tensor(image)
+    if t.dtype != torch.uint8 or t.dim() not in (2, 3):
+        raise _lib.SlnError("resize_image_device: uint8 [h, w] or [h, w, C] expected")
+    if not t.is_cuda:
+        t = t.cuda()
+    t = t.contiguous()
+    h, w = int(t.shape[0]), int(t.shape[1])
+    C = int(t.shape[2]) if t.dim() == 3 else 1
+    H2, W2 = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((H2, W2, C) if t.dim() == 3 else (H2, W2), dtype=torch.uint8, device=t.device)
+    need = int(_lib.lib().sln_resize_image_workspace_bytes(h, w, C, H2, W2))
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().sln_resize_image_u8(_lib.ptr(t), h, w, C, H2, W2, _lib.ptr(out), _lib.ptr(ws), need, _lib.stream_ptr()),
+                   "sln_resize_image_u8")
+    _lib.count_launches(3)
+    return out
+
+
+def resize_image(image, min_dim=None, max_dim=None, padding=False):
+    """Drop-in for utils.resize_image (utils.py:301-356): the reference squashes every image to (max_dim, max_dim) with
+    scipy.misc.imresize and returns (image, window, scale, padding).  The image comes back as a CUDA u8 tensor."""
+    h, w = image.shape[:2]
+    out = resize_image_device(image, (max_dim, max_dim))
+    window = (0, 0, max_dim, max_dim)
+    scale = (max_dim / h, max_dim / w)
+    return out, window, scale, [(0, 0), (0, 0), (0, 0)]

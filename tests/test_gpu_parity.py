@@ -847,3 +847,25 @@ def test_rpn_pack_full_size_and_backward(a):
     for x, y in zip(c1 + b1, c2 + b2):
         assert torch.equal(x.grad, y.grad)
     assert not probs.requires_grad
+
+
+# --------------------------------------------------------------------------- resize_image (8(f)-2)
+@pytest.mark.parametrize("h,w,H2,W2", [(480, 640, 1024, 1024), (1440, 1920, 1024, 1024), (37, 53, 64, 80), (300, 20, 7, 33)])
+def test_resize_image_matches_oracle(h, w, H2, W2):
+    """sln_resize_image_u8 against the oracle's per-band restatement of Pillow's bilinear resample (pinned to Pillow on
+    the CPU): COCOA- and D2SA-sized RGB images squashed to 1024^2 like utils.resize_image does, plus odd shapes."""
+    from sln_amodal_b200 import targets
+    rng = np.random.default_rng(h + w)
+    img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    got = targets.resize_image_device(img, (H2, W2)).cpu().numpy()
+    want = oracle.resize_image(img, (H2, W2))
+    try:
+        assert np.array_equal(want, oracle.resize_image_pil(img, (H2, W2)))       # the real library, when it is installed
+    except ImportError:
+        pass
+    assert got.shape == (H2, W2, 3) and np.array_equal(got, want)
+    if h == 480:
+        out, window, scale, padding = targets.resize_image(img, max_dim=1024)
+        assert window == (0, 0, 1024, 1024) and scale == (1024 / 480, 1024 / 640) and np.array_equal(out.cpu().numpy(), want)
+        gray = targets.resize_image_device(img[:, :, 0].copy(), (H2, W2)).cpu().numpy()
+        assert np.array_equal(gray, want[:, :, 0])

@@ -190,3 +190,16 @@ def test_bytescale_restatement_is_float32():
     scale = np.float32(255.0 / float(np.float32(hi - lo)))
     want = (np.clip((m - lo) * scale, 0, 255).astype(np.float32) + np.float32(0.5)).astype(np.uint8)
     assert np.array_equal(b, want)
+
+
+def test_resize_image_restatement_matches_pillow_rgb():
+    """oracle.resize_image (per-band restatement) against the real Pillow on RGB images -- what utils.resize_image's
+    scipy.misc.imresize(image, (max_dim, max_dim)) runs (utils.py:352): up- and down-scaling, odd sizes."""
+    import pytest
+    pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(9)
+    for (h, w, H2, W2) in ((37, 53, 64, 64), (120, 90, 64, 64), (64, 64, 64, 64), (200, 31, 48, 80), (5, 7, 33, 2)):
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(oracle.resize_image(img, (H2, W2)), oracle.resize_image_pil(img, (H2, W2))), (h, w, H2, W2)
+    g = rng.integers(0, 256, (40, 50)).astype(np.uint8)
+    assert np.array_equal(oracle.resize_image(g, (64, 64)), oracle.resize_image_pil(g, (64, 64)))

@@ -61,5 +61,6 @@ elif what == "after":
     for _ in range(reps):
         bench.unmold_metric(dev, 6650.0, cpu=False)
         bench.rpn_pack_metric(dev, 6650.0, cpu=False)
+        bench.resize_image_metric(dev, cpu=False)
 torch.cuda.synchronize()
 print("done", what)
