@@ -17,6 +17,8 @@
 // The search cost of a pixel equals its true distance, so background pixels cost
 // nothing and the whole pass is coalesced along x.  The intermediate g is u16 and is
 // produced/consumed map-chunk by map-chunk so that it lives in L2, not HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sln {
@@ -644,6 +646,59 @@ __device__ __forceinline__ void pk_insert(PCol &c, unsigned *sc, int W, int u, i
 #define SLN_EDT_COLS_BLOCK 128
 #endif
 
+// Zero fill of the background tiles of one map: warp `wid` of `nw` takes tile rows wid, wid + nw, ..
+// warp = tile rows (32 output rows each), walked along x: one store instruction covers four adjacent
+// segments = 512 contiguous bytes of one row, so runs of background are written as long bursts
+// (A/B on 320 maps: 704 -> 676 us against column-wise 128-byte pieces at a 4 KB stride).
+// (a segment cut by the right border is flagged on every row, so only full-width tiles get here)
+__device__ __forceinline__ void edt_fill_rows(const unsigned *__restrict__ flm, int *__restrict__ om, int tiles_y, int tiles_x,
+                                              int H, int W, int wid, int nw, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    for (int ty = wid; ty < tiles_y; ty += nw) {
+        const int yb = ty << 5, rows = min(H, yb + 32) - yb;
+        for (int s0 = 0; s0 < tiles_x; s0 += 32) {
+            const unsigned f = s0 + lane < tiles_x ? __ldg(flm + (size_t)ty * tiles_x + s0 + lane) : 1u;
+            const unsigned emp = __ballot_sync(FULL, f == 0u);          // empty segments s0 .. s0+31
+            if (!emp) continue;
+#pragma unroll
+            for (int grp = 0; grp < 8; ++grp) {                         // 4 segments = 128 columns
+                if (!((emp >> (4 * grp)) & 0xfu)) continue;
+                const bool mine = (emp >> (4 * grp + (lane >> 3))) & 1u;
+                int *p = om + (size_t)yb * W + (size_t)(s0 + 4 * grp) * 32 + 4 * lane;
+                if (mine) {
+#pragma unroll 8
+                    for (int y = 0; y < rows; ++y)
+                        asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p + (size_t)y * W) : "memory");
+                }
+            }
+        }
+    }
+}
+
+// Split form of the packed column pass: the zero fill as its own launch of a few fat CTAs.  Each takes 227 KB of
+// dynamic shared memory it never touches, so it owns its SM: the envelope kernel (launched right behind it as a
+// programmatic dependent with a 4-KB request per CTA) cannot be placed beside it, and its latency-bound chains run on
+// the other SMs without queueing behind the fill's stores in the LSU (lg-throttle was 3.1 stall cycles per issue when
+// both roles shared every SM, and the two roles' times simply added up).
+constexpr int EDT_FILL_THREADS = 1024;
+constexpr int EDT_FILL_SMEM = 227 * 1024;
+constexpr int EDT_ENV_SPLIT_SMEM = 4 * 1024;
+
+__global__ void __launch_bounds__(EDT_FILL_THREADS, 1)
+edt_fill_kernel(const unsigned *__restrict__ flags, int tiles_y, int tiles_x, int H, int W, int mc, int *__restrict__ out)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int lane = threadIdx.x & 31;
+    const int wpc = EDT_FILL_THREADS >> 5;
+    // item = (map, tile row); consecutive warps take consecutive tile rows of one map
+    const long long items = (long long)mc * tiles_y;
+    for (long long it = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); it < items; it += (long long)gridDim.x * wpc) {
+        const int m = (int)(it / tiles_y), ty = (int)(it - (long long)m * tiles_y);
+        edt_fill_rows(flags + (size_t)m * tiles_y * tiles_x, out + (size_t)m * H * W, ty + 1, tiles_x, H, W, ty, 1 << 30, lane);
+    }
+}
+
 
 // The warp's 32 columns are one flag segment.  All tile flags of the segment (<= 64 words) are fetched once
 // into two registers per lane and broadcast by shuffle, so the sweeps visit only the non-empty 32-row tiles
@@ -657,7 +712,12 @@ edt_cols_envelope_packed_kernel(unsigned *__restrict__ g, const unsigned *__rest
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int x0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);             // warp-uniform
-    if (x0 >= W) return;
+    if (x0 >= W) {
+        // split form (sln_edt_sq): one CTA past the right border keeps this grid from completing before the fill
+        // kernel it was launched behind -- the next operation in the stream is ordered after this grid only
+        if (blockIdx.x * blockDim.x >= W && blockIdx.y == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
     const int x = x0 + lane;
     const bool valid = x < W;
     const int m = blockIdx.y;
@@ -669,32 +729,8 @@ edt_cols_envelope_packed_kernel(unsigned *__restrict__ g, const unsigned *__rest
     int *__restrict__ oc = out + (size_t)m * H * W + x;
 
     if (blockIdx.z == 1) {                          // ---- fill role: zero the background tiles
-        // warp = tile rows (32 output rows each), walked along x: one store instruction covers four adjacent
-        // segments = 512 contiguous bytes of one row, so runs of background are written as long bursts
-        // (A/B on 320 maps: 704 -> 676 us against column-wise 128-byte pieces at a 4 KB stride).
-        // (a segment cut by the right border is flagged on every row, so only full-width tiles get here)
-        const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-        const unsigned *__restrict__ flm = flags + (size_t)m * tiles_y * tiles_x;
-        int *__restrict__ om = out + (size_t)m * H * W;
-        for (int ty = wid; ty < tiles_y; ty += nw) {
-            const int yb = ty << 5, rows = min(H, yb + 32) - yb;
-            for (int s0 = 0; s0 < tiles_x; s0 += 32) {
-                const unsigned f = s0 + lane < tiles_x ? __ldg(flm + (size_t)ty * tiles_x + s0 + lane) : 1u;
-                const unsigned emp = __ballot_sync(FULL, f == 0u);          // empty segments s0 .. s0+31
-                if (!emp) continue;
-#pragma unroll
-                for (int grp = 0; grp < 8; ++grp) {                         // 4 segments = 128 columns
-                    if (!((emp >> (4 * grp)) & 0xfu)) continue;
-                    const bool mine = (emp >> (4 * grp + (lane >> 3))) & 1u;
-                    int *p = om + (size_t)yb * W + (size_t)(s0 + 4 * grp) * 32 + 4 * lane;
-                    if (mine) {
-#pragma unroll 8
-                        for (int y = 0; y < rows; ++y)
-                            asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p + (size_t)y * W) : "memory");
-                    }
-                }
-            }
-        }
+        edt_fill_rows(flags + (size_t)m * tiles_y * tiles_x, out + (size_t)m * H * W, tiles_y, tiles_x, H, W,
+                      blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), lane);
         return;
     }
 #ifdef SLN_EDT_PROBE_NOENV
@@ -809,10 +845,22 @@ edt_cols_envelope_packed_kernel(unsigned *__restrict__ g, const unsigned *__rest
 // (one column per thread was measured fastest: 1476 / 1926 / 3205 us for 1 / 2 / 4 columns per thread on 320
 // 1024^2 maps -- the scan is latency bound, warps in flight matter more than instruction count)
 
+#ifndef SLN_EDT_FILL_CTAS_DEFAULT
+#define SLN_EDT_FILL_CTAS_DEFAULT 0
+#endif
 constexpr size_t EDT_CHUNK_BYTES = 2048ull << 20;   // the column pass needs thousands of columns in flight: big chunks
 
 // shapes the packed envelope kernel takes (entry fields s:11 | t:11 | g:10, two flag words per segment)
 static bool edt_packed_shape(int H, int W) { return W >= 128 && W % 4 == 0 && H <= 2048 && W <= 1024; }
+
+// number of fat fill CTAs of the split form (0: fill role inside the envelope launch); SLN_EDT_FILL_CTAS overrides (A/B)
+static int edt_fill_ctas()
+{
+    const char *e = getenv("SLN_EDT_FILL_CTAS");
+    int f = e ? atoi(e) : SLN_EDT_FILL_CTAS_DEFAULT;
+    const int cap = sm_count() / 2;
+    return f < 0 ? 0 : (f > cap ? cap : f);
+}
 
 static int edt_chunk_maps(int M, int H, int W)
 {
@@ -912,7 +960,15 @@ extern "C" int sln_edt_sq(const uint8_t *maps, int M, int H, int W, int32_t *out
                                                                                 tiles_y, tiles_x, false);
         SLN_LAUNCH_OK("edt_rows_kernel");
         const dim3 cgrid(cdiv(W, 128), cdiv(H, 8), mc);
-        if (packed) {
+        if (packed && edt_fill_ctas() > 0) {
+            // split form: fat fill CTAs that own their SMs, the envelope kernel as a programmatic dependent beside them
+            SLN_CUDA_OK(cudaFuncSetAttribute(edt_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDT_FILL_SMEM));
+            edt_fill_kernel<<<edt_fill_ctas(), EDT_FILL_THREADS, EDT_FILL_SMEM, st>>>(flags, tiles_y, tiles_x, H, W, mc, out + (size_t)m0 * H * W);
+            SLN_LAUNCH_OK("edt_fill_kernel");
+            SLN_CUDA_OK(launch_chain(edt_cols_envelope_packed_kernel, dim3(cdiv(W, SLN_EDT_COLS_BLOCK) + 1, mc, 1), dim3(SLN_EDT_COLS_BLOCK),
+                                     (size_t)EDT_ENV_SPLIT_SMEM, st, true, reinterpret_cast<unsigned *>(g), (const unsigned *)flags, fgcol,
+                                     tiles_y, tiles_x, H, W, cap, out + (size_t)m0 * H * W));
+        } else if (packed) {
             edt_cols_envelope_packed_kernel<<<dim3(cdiv(W, SLN_EDT_COLS_BLOCK), mc, 2), SLN_EDT_COLS_BLOCK, 0, st>>>(
                 reinterpret_cast<unsigned *>(g), flags, fgcol, tiles_y, tiles_x, H, W, cap, out + (size_t)m0 * H * W);
         } else if (vec && W >= 128) {
