@@ -208,3 +208,39 @@ def test_zoom_index_map_reproduces_scipy_nearest_zoom():
         quirks += int((iy < 0).any() or (ix < 0).any())
         assert np.array_equal(got, ndi.zoom(a, zoom=[sy, sx], order=0))
     assert quirks > 0          # the sweep does contain overshooting last lines
+
+
+def test_after_the_path_entry_points_validate_and_refuse_cpu(built_lib):
+    """Mask paste, RPN re-layout and image resize: argument validation before any CUDA call, workspace
+    query, no CPU fallback, and install() rebinding MaskRCNN.unmold_detections."""
+    import ctypes as C
+    import types
+    import sln_amodal_b200 as s
+    from sln_amodal_b200 import _lib
+    L = _lib.lib()
+    assert L.sln_unmold_masks(None, 1, 0, 28, None, 64, 64, None, None) == -1 and b"unmold" in L.sln_last_error_string()
+    assert L.sln_unmold_masks(None, 1, 300, 300, None, 64, 64, None, None) == -1
+    assert L.sln_unmold_masks(None, 0, 28, 28, None, 64, 64, None, None) == 0              # nothing to do
+    hs, ws = (C.c_int * 2)(4, 2), (C.c_int * 2)(4, 2)
+    assert L.sln_rpn_pack(None, None, hs, ws, 9, 1, 3, 0, None, None, None, None) == -1 and b"levels" in L.sln_last_error_string()
+    assert L.sln_rpn_pack(None, None, hs, ws, 2, 1, 9, 0, None, None, None, None) == -1 and b"anchors per location" in L.sln_last_error_string()
+    assert L.sln_rpn_pack(None, None, hs, ws, 2, 0, 3, 0, None, None, None, None) == 0    # empty batch
+    need = L.sln_resize_image_workspace_bytes(1440, 1920, 3, 1024, 1024)
+    assert 1440 * 1024 * 3 <= need <= 1440 * 1024 * 3 + (1 << 20)                          # the 8-bit intermediate + tables
+    assert L.sln_resize_image_u8(None, 4, 4, 3, 8, 8, None, None, 0, None) == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SlnError):
+            s.unmold_masks(np.zeros((1, 28, 28), np.float32), np.array([[0, 0, 4, 4]]), (8, 8))
+        with pytest.raises(_lib.SlnError):
+            s.resize_image_device(np.zeros((4, 4, 3), np.uint8), (8, 8))
+    with pytest.raises(_lib.SlnError):
+        s.rpn_pack([torch.zeros(1, 6, 4, 4)], [torch.zeros(1, 12, 4, 4)])
+
+    model = types.ModuleType("model")
+
+    class MaskRCNN:
+        def unmold_detections(self, detections, mrcnn_mask, image_shape, window):
+            return "reference"
+    model.MaskRCNN = MaskRCNN
+    done = s.install(model, None, None)
+    assert "model.MaskRCNN.unmold_detections" in done and MaskRCNN.unmold_detections.__name__ == "_unmold_detections"
