@@ -253,29 +253,60 @@ resize_h_kernel(const uint8_t *__restrict__ src, int h, int w, int C, int W2, Re
     const int pk = t.hx[xx], xmin = pk & 0xffff, cnt = pk >> 16;
     const int *k = t.hk + (size_t)xx * t.tH;
     const uint8_t *s = src + ((size_t)r * w + xmin) * C;
+    uint8_t *d = tmp + ((size_t)r * W2 + xx) * C;
+    if (C <= 4) {                                   // grey / RGB / RGBA: one pass over the taps for all bands
+        int acc[4] = {1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1)};
+        for (int q = 0; q < cnt; ++q) {
+            const int kq = __ldg(k + q);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < C) acc[c] += (int)s[(size_t)q * C + c] * kq;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < C) d[c] = (uint8_t)min(max(acc[c] >> PIL_BITS, 0), 255);
+        return;
+    }
     for (int c = 0; c < C; ++c) {
         int acc = 1 << (PIL_BITS - 1);
         for (int q = 0; q < cnt; ++q) acc += (int)s[(size_t)q * C + c] * __ldg(k + q);
         acc >>= PIL_BITS;
-        tmp[((size_t)r * W2 + xx) * C + c] = (uint8_t)min(max(acc, 0), 255);
+        d[c] = (uint8_t)min(max(acc, 0), 255);
     }
 }
 
+// VEC4: four output bytes per thread (the row length in bytes is a multiple of 4: one 32-bit load per tap)
+template <bool VEC4>
 __global__ void __launch_bounds__(256)
 resize_v_kernel(const uint8_t *__restrict__ tmp, int C, int H2, int W2, ResizeTabs t, uint8_t *__restrict__ out)
 {
     pdl_prologue();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per output byte (x, c fastest)
-    const long long rowb = (long long)W2 * C;
-    if (i >= (long long)H2 * rowb) return;
-    const int yy = (int)(i / rowb);
-    const long long xc = i - (long long)yy * rowb;
+    constexpr int V = VEC4 ? 4 : 1;
+    const long long rowb = (long long)W2 * C, rowu = rowb / V;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per V output bytes (x, c fastest)
+    if (i >= (long long)H2 * rowu) return;
+    const int yy = (int)(i / rowu);
+    const long long xc = (i - (long long)yy * rowu) * V;
     const int pk = t.vy[yy], ymin = pk & 0xffff, cnt = pk >> 16;
     const int *k = t.vk + (size_t)yy * t.tV;
-    int acc = 1 << (PIL_BITS - 1);
-    for (int q = 0; q < cnt; ++q) acc += (int)tmp[(size_t)(ymin + q) * rowb + xc] * __ldg(k + q);
-    acc >>= PIL_BITS;
-    out[i] = (uint8_t)min(max(acc, 0), 255);
+    if (VEC4) {
+        int acc[4] = {1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1), 1 << (PIL_BITS - 1)};
+        for (int q = 0; q < cnt; ++q) {
+            const unsigned w = *reinterpret_cast<const unsigned *>(tmp + (size_t)(ymin + q) * rowb + xc);
+            const int kq = __ldg(k + q);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[b] += (int)((w >> (8 * b)) & 0xffu) * kq;
+        }
+        unsigned r = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r |= (unsigned)min(max(acc[b] >> PIL_BITS, 0), 255) << (8 * b);
+        *reinterpret_cast<unsigned *>(out + (size_t)yy * rowb + xc) = r;
+    } else {
+        int acc = 1 << (PIL_BITS - 1);
+        for (int q = 0; q < cnt; ++q) acc += (int)tmp[(size_t)(ymin + q) * rowb + xc] * __ldg(k + q);
+        acc >>= PIL_BITS;
+        out[(size_t)yy * rowb + xc] = (uint8_t)min(max(acc, 0), 255);
+    }
 }
 
 static int resize_taps_host(int in_size, int out_size)
@@ -330,10 +361,12 @@ extern "C" int sln_resize_image_u8(const uint8_t *src, int h, int w, int C, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     resize_coeffs_kernel<<<cdiv(W2 + H2, 256), 256, 0, st>>>(h, w, H2, W2, t);
     SLN_LAUNCH_OK("resize_coeffs_kernel");
-    const long long nh = (long long)h * W2, nv = (long long)H2 * W2 * C;
+    const bool vec4 = ((long long)W2 * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 3u) == 0;
+    const long long nh = (long long)h * W2, nv = (long long)H2 * W2 * C / (vec4 ? 4 : 1);
     SLN_REQUIRE((nh + 255) / 256 < (1ll << 31) && (nv + 255) / 256 < (1ll << 31), SLN_ERR_ARG, "resize: image too large");
     SLN_CUDA_OK(launch_chain(resize_h_kernel, dim3((unsigned)((nh + 255) / 256)), dim3(256), 0, st, true, src, h, w, C, W2, t, tmp));
-    SLN_CUDA_OK(launch_chain(resize_v_kernel, dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, st, true, (const uint8_t *)tmp, C, H2, W2, t, out));
+    SLN_CUDA_OK(launch_chain(vec4 ? resize_v_kernel<true> : resize_v_kernel<false>, dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, st, true,
+                             (const uint8_t *)tmp, C, H2, W2, t, out));
     return SLN_OK;
 }
 
