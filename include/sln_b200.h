@@ -8,7 +8,9 @@
  *     roialign/roi_align/src/crop_and_resize_gpu.h:1-16   (crop_and_resize_gpu_forward/backward)
  *     nms/src/nms.h / nms/src/nms_cuda.h                  (cpu_nms / gpu_nms)
  * and adds entry points for the Python-level functions of the same path
- * (proposal_layer, pyramid_roi_align, the layer codec, the EDT).
+ * (proposal_layer, pyramid_roi_align, the layer codec, the EDT) and of the steps either side
+ * of it (detection / RPN targets, image and layer resize, RPN output
+ * re-layout, mask paste, COCO run-length encoding).
  *
  * Conventions (all entry points):
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
