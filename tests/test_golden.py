@@ -243,3 +243,20 @@ def test_rpn_pack_oracle_matches_reference_module():
     assert np.array_equal(logits, g["rpn_class_logits"])
     assert np.array_equal(bbox, g["rpn_bbox"])
     assert np.allclose(probs, g["rpn_class"], rtol=3e-7, atol=0)
+
+
+def test_rpn_pack_oracle_matches_torch_expression_random_shapes():
+    """oracle.rpn_pack against the reference's expression (modal/modals.py:394-410 + model.py:553-563) evaluated with
+    torch on the CPU, over random level counts, sizes, batch sizes and anchors per location."""
+    rng = np.random.default_rng(17)
+    for _ in range(12):
+        a, B, nl = int(rng.integers(1, 5)), int(rng.integers(1, 4)), int(rng.integers(1, 6))
+        shapes = [(int(rng.integers(1, 9)), int(rng.integers(1, 9))) for _ in range(nl)]
+        cm = [rng.standard_normal((B, 2 * a, h, w)).astype(np.float32) * 5 for h, w in shapes]
+        bm = [rng.standard_normal((B, 4 * a, h, w)).astype(np.float32) for h, w in shapes]
+        lg = [torch.from_numpy(c).permute(0, 2, 3, 1).contiguous().view(B, -1, 2) for c in cm]
+        bx = [torch.from_numpy(b).permute(0, 2, 3, 1).contiguous().view(B, -1, 4) for b in bm]
+        want = (torch.cat(lg, 1).numpy(), torch.cat([torch.softmax(x, dim=2) for x in lg], 1).numpy(), torch.cat(bx, 1).numpy())
+        got = oracle.rpn_pack(cm, bm)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+        assert np.allclose(got[1], want[1], rtol=3e-7, atol=0)
