@@ -260,3 +260,40 @@ def test_rpn_pack_oracle_matches_torch_expression_random_shapes():
         got = oracle.rpn_pack(cm, bm)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
         assert np.allclose(got[1], want[1], rtol=3e-7, atol=0)
+
+
+def test_unmold_oracle_matches_reference_unmold_detections():
+    """oracle.unmold_mask against the masks the reference's own MaskRCNN.unmold_detections / utils.unmold_mask produced
+    (tests/golden/make_golden_unmold.py: reference Python unmodified, scipy.misc.imresize supplied around the real Pillow)."""
+    g = np.load(os.path.join(G, "unmold_detections.npz"))
+    boxes, masks = g["boxes"], g["masks"]
+    kept = [i for i in range(7) if i != 2]                          # detection 2 has zero area and is dropped
+    assert masks.shape == (96, 128, 6) and boxes.shape == (6, 4)
+    for j, i in enumerate(kept):
+        want = masks[:, :, j]
+        got = oracle.unmold_mask(g["mrcnn_mask"][i, :, :, 1], boxes[j], tuple(g["image_shape"]))
+        assert np.array_equal(got, want), (i, boxes[j].tolist())
+
+
+def test_unmold_detections_host_logic_matches_reference(monkeypatch):
+    """The host half of sln_amodal_b200.unmold.unmold_detections (padding cut, class collapse, window scale / shift,
+    int32 cast, zero-area filter, output layout) against the reference's own function, with the device launch replaced by
+    the oracle so that the test runs without a GPU."""
+    from sln_amodal_b200 import unmold
+    g = np.load(os.path.join(G, "unmold_detections.npz"))
+
+    def fake_unmold_masks(masks, boxes, image_shape):
+        m = masks.numpy() if isinstance(masks, torch.Tensor) else np.asarray(masks)
+        return torch.from_numpy(np.stack([oracle.unmold_mask(m[i], boxes[i], image_shape) for i in range(m.shape[0])]))
+    monkeypatch.setattr(unmold, "unmold_masks", fake_unmold_masks)
+    boxes, class_ids, scores, masks = unmold.unmold_detections(g["detections"], g["mrcnn_mask"], tuple(g["image_shape"]), g["window"])
+    assert boxes.dtype == g["boxes"].dtype and np.array_equal(boxes, g["boxes"])
+    assert np.array_equal(class_ids, g["class_ids"]) and np.array_equal(scores, g["scores"])
+    assert masks.shape == g["masks"].shape and np.array_equal(masks, g["masks"])
+
+
+def test_resize_image_oracle_matches_reference_resize_image():
+    """oracle.resize_image against the reference's own utils.resize_image output (same generator)."""
+    g = np.load(os.path.join(G, "resize_image.npz"))
+    assert np.array_equal(oracle.resize_image(g["image"], (64, 64)), g["resized"])
+    assert tuple(g["window"]) == (0, 0, 64, 64) and np.allclose(g["scale"], (64 / 75, 64 / 50))

@@ -869,3 +869,19 @@ def test_resize_image_matches_oracle(h, w, H2, W2):
         assert window == (0, 0, 1024, 1024) and scale == (1024 / 480, 1024 / 640) and np.array_equal(out.cpu().numpy(), want)
         gray = targets.resize_image_device(img[:, :, 0].copy(), (H2, W2)).cpu().numpy()
         assert np.array_equal(gray, want[:, :, 0])
+
+
+def test_unmold_and_resize_match_reference_fixtures():
+    """The device path against what the reference's own MaskRCNN.unmold_detections and utils.resize_image returned
+    (tests/golden/unmold_detections.npz, resize_image.npz; see make_golden_unmold.py)."""
+    import os
+    from sln_amodal_b200 import targets, unmold
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gd, "unmold_detections.npz"))
+    boxes, class_ids, scores, masks = unmold.unmold_detections(g["detections"], g["mrcnn_mask"], tuple(int(v) for v in g["image_shape"]),
+                                                               g["window"])
+    assert np.array_equal(boxes, g["boxes"]) and np.array_equal(class_ids, g["class_ids"]) and np.array_equal(scores, g["scores"])
+    assert masks.shape == g["masks"].shape and np.array_equal(masks.astype(np.uint8), g["masks"])
+    r = np.load(os.path.join(gd, "resize_image.npz"))
+    out, window, scale, padding = targets.resize_image(r["image"], max_dim=64)
+    assert np.array_equal(out.cpu().numpy(), r["resized"]) and window == tuple(r["window"]) and np.allclose(scale, r["scale"])
