@@ -64,6 +64,7 @@ def _lib():
         lib.orc_nms.restype = C.c_int
         lib.orc_layer_decode.restype = C.c_int
         lib.orc_edt_sq.restype = None
+        lib.orc_edt_sq_banded.restype = None
         _orc = lib
     return _orc
 
@@ -206,6 +207,18 @@ def edt_sq(mask):
     out = np.empty((H, W), np.int32)
     _lib().orc_edt_sq(mask.ctypes.data_as(C.POINTER(C.c_ubyte)), H, W,
                       out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out
+
+
+def edt_sq_banded(mask, band=32):
+    """Second, independent restatement of the same transform: row pass + one lower envelope per band of `band` rows,
+    every pixel the minimum over the bands in reach (oracle/sln_oracle.c: orc_edt_sq_banded) -- the executable form of
+    the banded column pass planned for the CUDA kernel.  Must equal edt_sq() for every band height."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    H, W = mask.shape
+    out = np.empty((H, W), np.int32)
+    _lib().orc_edt_sq_banded(mask.ctypes.data_as(C.POINTER(C.c_ubyte)), H, W, int(band),
+                             out.ctypes.data_as(C.POINTER(C.c_int32)))
     return out
 
 

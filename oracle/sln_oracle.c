@@ -214,6 +214,95 @@ void orc_edt_sq(const unsigned char *map, int H, int W, int32_t *out)
     free(g);
 }
 
+/* Second, independent EDT restatement -- and the executable form of the banded column pass planned for the CUDA
+ * kernel: row pass first (g = distance to the nearest zero along x), then per column one lower
+ * envelope PER BAND of `band` rows over the band's rows plus the row just above and just below it (site s has height
+ * g(s)^2; rows without a zero are no sites), and every pixel takes the minimum over the envelopes of the bands in
+ * reach: its own, then outwards while the row gap squared is below the best value so far.  Any superset of bands is
+ * exact (every candidate is the true squared distance to some zero pixel), so the pruning only saves work.
+ * tests/test_oracle_pin.py holds it to orc_edt_sq and scipy for band heights 1 .. H. */
+static int64_t ceil_div64(int64_t a, int64_t b)      /* b > 0 */
+{
+    int64_t q = a / b;
+    if ((a % b != 0) && (a > 0)) ++q;
+    return q;
+}
+
+void orc_edt_sq_banded(const unsigned char *map, int H, int W, int band, int32_t *out)
+{
+    const int32_t inf = H + W;
+    const int64_t cap = (int64_t)inf * inf;
+    if (band < 1) band = 1;
+    const int nb = (H + band - 1) / band;
+    int32_t *g = (int32_t *)malloc(sizeof(int32_t) * (size_t)H * W);
+    for (int y = 0; y < H; ++y) {                     /* row pass */
+        const unsigned char *m = map + (size_t)y * W;
+        int32_t *gr = g + (size_t)y * W;
+        int32_t d = inf;
+        for (int x = 0; x < W; ++x) { d = m[x] ? (d < inf ? d + 1 : inf) : 0; gr[x] = d; }
+        d = inf;
+        for (int x = W - 1; x >= 0; --x) { d = m[x] ? (d < inf ? d + 1 : inf) : 0; if (d < gr[x]) gr[x] = d; }
+    }
+    /* per band: site rows v[], first winning row z[] (z[0] = -inf), count */
+    int *v = (int *)malloc(sizeof(int) * (size_t)nb * (band + 2));
+    int64_t *z = (int64_t *)malloc(sizeof(int64_t) * (size_t)nb * (band + 2));
+    int *cnt = (int *)malloc(sizeof(int) * (size_t)nb);
+    for (int x = 0; x < W; ++x) {
+        for (int b = 0; b < nb; ++b) {                /* phase A: band-local envelopes */
+            int *vb = v + (size_t)b * (band + 2);
+            int64_t *zb = z + (size_t)b * (band + 2);
+            int k = -1;
+            const int s0 = b * band - 1 < 0 ? 0 : b * band - 1;
+            const int s1 = (b + 1) * band > H - 1 ? H - 1 : (b + 1) * band;      /* inclusive */
+            for (int s = s0; s <= s1; ++s) {
+                const int64_t gs = g[(size_t)s * W + x];
+                if (gs >= inf) continue;
+                const int64_t fs = gs * gs + (int64_t)s * s;
+                int64_t start = INT64_MIN;
+                while (k >= 0) {
+                    const int64_t gv = g[(size_t)vb[k] * W + x];
+                    const int64_t fv = gv * gv + (int64_t)vb[k] * vb[k];
+                    start = ceil_div64(fs - fv, 2 * (int64_t)(s - vb[k]));       /* first row where s is at least as good */
+                    if (start <= zb[k]) --k; else break;
+                }
+                if (k < 0) start = INT64_MIN;
+                ++k;
+                vb[k] = s;
+                zb[k] = start;
+            }
+            cnt[b] = k + 1;
+        }
+        for (int y = 0; y < H; ++y) {                 /* phase B: minimum over the bands in reach */
+            const int b = y / band;
+            int64_t best = INT64_MAX;
+            for (int d = 0; d < nb; ++d) {
+                int any = 0;
+                for (int side = 0; side < (d ? 2 : 1); ++side) {
+                    const int bb = side ? b + d : b - d;
+                    if (bb < 0 || bb >= nb) continue;
+                    int64_t gap = 0;                  /* rows between y and the nearest site row of band bb */
+                    if (bb < b) { const int last = (bb + 1) * band > H - 1 ? H - 1 : (bb + 1) * band; gap = y > last ? y - last : 0; }
+                    if (bb > b) { const int first = bb * band - 1; gap = first > y ? first - y : 0; }
+                    if (best != INT64_MAX && gap * gap >= best) continue;
+                    any = 1;
+                    const int n = cnt[bb];
+                    if (n == 0) continue;
+                    const int *vb = v + (size_t)bb * (band + 2);
+                    const int64_t *zb = z + (size_t)bb * (band + 2);
+                    int lo = 0, hi = n - 1;           /* largest k with z[k] <= y */
+                    while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (zb[mid] <= y) lo = mid; else hi = mid - 1; }
+                    const int64_t gv = g[(size_t)vb[lo] * W + x];
+                    const int64_t val = gv * gv + (int64_t)(y - vb[lo]) * (y - vb[lo]);
+                    if (val < best) best = val;
+                }
+                if (!any && d > 0) break;
+            }
+            out[(size_t)y * W + x] = (int32_t)(best < cap ? best : cap);
+        }
+    }
+    free(cnt); free(z); free(v); free(g);
+}
+
 /* Layer ("sem-dist") target decode in closed form.
  * Reference: amodal_train.py:236-271 (load_layer2) driving
  * modal/Functions.py:1012-1095 (get_image_labals, objectID_to_masks,

@@ -203,3 +203,26 @@ def test_resize_image_restatement_matches_pillow_rgb():
         assert np.array_equal(oracle.resize_image(img, (H2, W2)), oracle.resize_image_pil(img, (H2, W2))), (h, w, H2, W2)
     g = rng.integers(0, 256, (40, 50)).astype(np.uint8)
     assert np.array_equal(oracle.resize_image(g, (64, 64)), oracle.resize_image_pil(g, (64, 64)))
+
+
+def test_banded_edt_restatement_equals_the_first_one_and_scipy():
+    """orc_edt_sq_banded (row pass + per-band lower envelopes + minimum over the bands in reach: the column algorithm
+    planned for the CUDA kernel) against orc_edt_sq (column pass + bounded search) and scipy, for band heights from 1 to
+    more than H, on blobs, noise, single zeros and maps without a zero."""
+    from scipy import ndimage as ndi
+    from sln_amodal_b200 import synth
+    rng = np.random.default_rng(41)
+    lab = synth.label_map(96, 112, n=5, seed=9, min_piece=16)
+    cases = [((lab & np.uint64(1)) != 0).astype(np.uint8), ((lab >> np.uint64(33)) & np.uint64(1)).astype(np.uint8),
+             (rng.random((70, 45)) < 0.93).astype(np.uint8), (rng.random((33, 64)) < 0.5).astype(np.uint8)]
+    one = np.ones((50, 37), np.uint8)
+    one[17, 30] = 0
+    cases.append(one)
+    cases.append(np.ones((9, 13), np.uint8))                       # no zero pixel: (H + W)^2 everywhere
+    cases.append(np.zeros((8, 8), np.uint8))
+    for m in cases:
+        want = oracle.edt_sq(m)
+        if not m.all():
+            assert np.array_equal(want.astype(np.int64), np.rint(ndi.distance_transform_edt(m) ** 2).astype(np.int64))
+        for band in (1, 2, 5, 16, 32, 64, 1000):
+            assert np.array_equal(oracle.edt_sq_banded(m, band), want), (m.shape, band)
