@@ -164,6 +164,16 @@ SLN_API int sln_refine_decode(const float *rois, const float *probs, const float
                       float min_confidence, float *dets, int *cls_nms, int *class_ids, int *n_excluded,
                       void *stream);
 
+/* ---- refine_detections, selection without NMS ------------------------------- *
+ * The reference's shipped default (config.py:78 `USE_NMS = False`; modal/Functions.py:526-546): of the ROIs whose
+ * argmax class is not background keep the `max_keep` (100, hard-coded at :530-532) best by score, in descending score
+ * order; score ties go to the lower ROI index.  dets / class_ids are sln_refine_decode's outputs (run with
+ * min_confidence = 0: this branch has no score filter).  Writes rows [0, min(max_keep, N - *n_excluded)) of
+ * result f32 [max_keep,6] = (y1,x1,y2,x2,class_id,score) and keep i64 [max_keep] (ROI indices); later rows are not
+ * touched.  One launch, no host sync.                                                                      */
+SLN_API int sln_refine_topk(const float *dets, const int *class_ids, int N, int max_keep, float *result,
+                    int64_t *keep, void *stream);
+
 /* ---- detection targets -------------------------------------- *
  * sln_bbox_overlaps replaces bbox_overlaps (modal/Functions.py:184-218): IoU of boxes1 [N,4] against boxes2 [G,4]
  * (y1,x1,y2,x2; no "+1"; every operation rounded separately; 0/0 -> NaN).  Any of the three outputs may be NULL:

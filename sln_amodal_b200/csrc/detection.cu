@@ -90,6 +90,78 @@ extern "C" int sln_refine_decode(const float *rois, const float *probs, const fl
 }
 
 // ---------------------------------------------------------------------------
+// refine_detections without NMS (the reference's shipped default, config.py:78 USE_NMS = False): of the ROIs whose
+// argmax class is not background keep the `max_keep` best by score (Functions.py:528-532) and emit them in descending
+// score order (:538-546).  Ties are broken by the lower ROI index (torch's sort leaves them unspecified; same rule as
+// the NMS front).  Every thread ranks one ROI against all others (scores staged through shared memory, 4 keys per
+// 16-byte load); ROIs ranked below max_keep write their output row directly, so select + sort + the three gathers +
+// cat of the torch expression are this one launch.  dets / class_ids are sln_refine_decode's outputs (score = -inf for
+// filtered ROIs, which therefore never take part).
+namespace sln {
+
+constexpr int TOPK_THREADS = 256;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+refine_topk_kernel(const float *__restrict__ dets, const int *__restrict__ class_ids, int N, int max_keep,
+                   float *__restrict__ result, long long *__restrict__ keep)
+{
+    __shared__ __align__(16) float s_score[TOPK_THREADS];
+    const int i = blockIdx.x * TOPK_THREADS + threadIdx.x;
+    float si = -INFINITY;
+    bool valid = false;
+    if (i < N) {
+        si = __ldg(dets + 5 * (size_t)i + 4);
+        valid = __ldg(class_ids + i) > 0 && si > -INFINITY;
+    }
+    int rank = 0;
+    for (int j0 = 0; j0 < N; j0 += TOPK_THREADS) {
+        const int j = j0 + threadIdx.x;
+        float sj = -INFINITY;                                  // filtered and out-of-range ROIs never precede anyone
+        if (j < N && __ldg(class_ids + j) > 0) sj = __ldg(dets + 5 * (size_t)j + 4);
+        __syncthreads();
+        s_score[threadIdx.x] = sj;
+        __syncthreads();
+        const int lim = min(TOPK_THREADS, N - j0);
+        // entries before i in index order win ties, entries after it do not
+        const int split = min(max(i - j0, 0), lim);            // j0 + k < i  <=>  k < split
+        int k = 0;
+        for (; k + 4 <= split; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(s_score + k);
+            rank += (v.x >= si) + (v.y >= si) + (v.z >= si) + (v.w >= si);
+        }
+        for (; k < split; ++k) rank += s_score[k] >= si;
+        k = split + ((i >= j0 && i < j0 + lim) ? 1 : 0);       // skip i itself
+        for (; k < lim && (k & 3); ++k) rank += s_score[k] > si;
+        for (; k + 4 <= lim; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(s_score + k);
+            rank += (v.x > si) + (v.y > si) + (v.z > si) + (v.w > si);
+        }
+        for (; k < lim; ++k) rank += s_score[k] > si;
+    }
+    if (!valid || rank >= max_keep) return;
+    const float *d = dets + 5 * (size_t)i;
+    float *o = result + 6 * (size_t)rank;
+    o[0] = d[0]; o[1] = d[1]; o[2] = d[2]; o[3] = d[3];
+    o[4] = (float)__ldg(class_ids + i);
+    o[5] = si;
+    keep[rank] = i;
+}
+
+}  // namespace sln
+
+extern "C" int sln_refine_topk(const float *dets, const int *class_ids, int N, int max_keep, float *result,
+                               int64_t *keep, void *stream)
+{
+    SLN_REQUIRE(N >= 0 && max_keep >= 0, SLN_ERR_ARG, "negative size");
+    if (N == 0 || max_keep == 0) return SLN_OK;
+    SLN_REQUIRE(dets && class_ids && result && keep, SLN_ERR_ARG, "null pointer");
+    sln::refine_topk_kernel<<<sln::cdiv(N, sln::TOPK_THREADS), sln::TOPK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        dets, class_ids, N, max_keep, result, reinterpret_cast<long long *>(keep));
+    SLN_LAUNCH_OK("refine_topk_kernel");
+    return SLN_OK;
+}
+
+// ---------------------------------------------------------------------------
 // detection targets -- IoU matching and box refinement
 // ---------------------------------------------------------------------------
 // bbox_overlaps (modal/Functions.py:184-218): IoU of every box of set 1 against every box of set 2, no "+1"

@@ -293,6 +293,21 @@ def refine_decode_device(rois, probs, deltas, std_dev, image_hw, window, min_con
     return dets, cls_nms, class_ids, n_excl
 
 
+def refine_topk_device(dets, class_ids, max_keep=100):
+    """Top `max_keep` non-background ROIs by score, in descending score order (include/sln_b200.h, sln_refine_topk).
+    Returns (result f32 [max_keep,6], keep int64 [max_keep]); only the first min(max_keep, #kept) rows are written."""
+    _require_cuda(dets, "dets")
+    N = dets.shape[0]
+    result = torch.empty((int(max_keep), 6), dtype=torch.float32, device=dets.device)
+    keep = torch.empty(int(max_keep), dtype=torch.int64, device=dets.device)
+    if N and max_keep:
+        with torch.cuda.device(dets.device):
+            check(lib().sln_refine_topk(ptr(dets), ptr(class_ids), N, int(max_keep), ptr(result), ptr(keep), stream_ptr()),
+                  "sln_refine_topk")
+        _lib.count_launches(1)
+    return result, keep
+
+
 def bbox_overlaps_device(boxes1, boxes2, matrix=True, reduce=False):
     """IoU of boxes1 [N,4] against boxes2 [G,4] (include/sln_b200.h, sln_bbox_overlaps).
     Returns the [N,G] matrix, or (matrix | None, iou_max [N], argmax int32 [N]) with reduce=True."""

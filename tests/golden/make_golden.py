@@ -160,6 +160,20 @@ def main():
                         detections=det.numpy(), keep=keep.numpy())
     out["refine_detections"] = tuple(det.shape)
 
+    # ---- refine_detections on the reference's DEFAULT branch, USE_NMS = False (config.py:78; Functions.py:526-546):
+    # top-100 by score.  Case a: more than 100 non-background ROIs (truncation); case b: fewer (no truncation).
+    cfg = Cfg()
+    cfg.USE_NMS = False
+    nn = {}
+    for tag, n_use in (("a", N), ("b", 90)):
+        det, keep = F.refine_detections(torch.from_numpy(rois[:n_use]), torch.from_numpy(p[:n_use]),
+                                        torch.from_numpy(d[:n_use]), window, cfg)
+        nn["n_" + tag] = n_use
+        nn["detections_" + tag] = det.numpy()
+        nn["keep_" + tag] = keep.numpy()
+    np.savez_compressed(os.path.join(HERE, "refine_detections_nonms.npz"), rois=rois, probs=p, deltas=d, window=window, **nn)
+    out["refine_detections_nonms"] = (tuple(nn["detections_a"].shape), tuple(nn["detections_b"].shape))
+
     # ---- layer codec through AmodalDataset.load_layer2 (amodal_train.py:236-271)
     import amodal_train as AT
     tmp = tempfile.mkdtemp(prefix="sln_layers_")

@@ -244,3 +244,15 @@ def test_after_the_path_entry_points_validate_and_refuse_cpu(built_lib):
     model.MaskRCNN = MaskRCNN
     done = s.install(model, None, None)
     assert "model.MaskRCNN.unmold_detections" in done and MaskRCNN.unmold_detections.__name__ == "_unmold_detections"
+
+
+def test_refine_detections_has_no_cpu_path():
+    from sln_amodal_b200 import refine_detections
+
+    class Cfg:
+        RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+        IMAGE_SHAPE = np.array([1024, 1024, 3])
+        USE_NMS = False
+
+    with pytest.raises(RuntimeError):
+        refine_detections(torch.zeros(3, 4), torch.zeros(3, 2), torch.zeros(3, 2, 4), (0, 0, 1, 1), Cfg())

@@ -73,6 +73,17 @@ def test_oracle_refine_detections_matches_reference_python():
     assert det.tobytes() == g["detections"].tobytes()
 
 
+def test_oracle_refine_detections_default_branch_matches_reference_python():
+    """USE_NMS = False, the reference's shipped default (config.py:78): top-100 by score (Functions.py:526-546)."""
+    g = load("refine_detections_nonms")
+    for tag in ("a", "b"):
+        n = int(g["n_" + tag])
+        det, keep = oracle.refine_detections(g["rois"][:n], g["probs"][:n], g["deltas"][:n], g["window"], use_nms=False)
+        assert np.array_equal(keep, g["keep_" + tag])
+        assert det.tobytes() == g["detections_" + tag].tobytes()
+    assert g["detections_a"].shape[0] == 100 and g["detections_b"].shape[0] < 90      # truncated / not truncated
+
+
 def test_oracle_layer_codec_matches_reference_python():
     for label, nc, ref, class_ids in layer_cases():
         loops = oracle.layer_decode_loops(label, nc)
@@ -118,6 +129,21 @@ def test_gpu_refine_detections_matches_reference_python():
     det, keep = refine_detections(cuda(g["rois"]), cuda(g["probs"]), cuda(g["deltas"]), g["window"], Cfg())
     assert np.array_equal(keep.cpu().numpy(), g["keep"])
     np.testing.assert_allclose(det.cpu().numpy(), g["detections"], rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_refine_detections_default_branch_matches_reference_python():
+    """The device path of the USE_NMS = False branch (sln_refine_decode + sln_refine_topk) against the reference's own
+    refine_detections run with its default config."""
+    from sln_amodal_b200 import refine_detections
+    g = load("refine_detections_nonms")
+    cfg = Cfg()
+    cfg.USE_NMS = False
+    for tag in ("a", "b"):
+        n = int(g["n_" + tag])
+        det, keep = refine_detections(cuda(g["rois"][:n]), cuda(g["probs"][:n]), cuda(g["deltas"][:n]), g["window"], cfg)
+        assert np.array_equal(keep.cpu().numpy(), g["keep_" + tag])
+        assert det.cpu().numpy().tobytes() == g["detections_" + tag].tobytes()
 
 
 @pytest.mark.gpu

@@ -512,6 +512,41 @@ def test_refine_detections_fused_matches_oracle(n, K, min_conf):
     assert np.array_equal(det.cpu().numpy(), want_det)
 
 
+@pytest.mark.parametrize("n,K,bg_frac", [(1000, 81, 0.0), (1000, 2, 0.5), (5000, 61, 0.0), (257, 3, 0.3), (60, 2, 0.0), (40, 4, 1.0)])
+def test_refine_detections_without_nms_matches_oracle(n, K, bg_frac):
+    """USE_NMS = False -- the reference's shipped default (config.py:78; Functions.py:526-546): decode + device top-100
+    (sln_refine_decode + sln_refine_topk) against the oracle: same rows, same order, same keep indices; score ties
+    (rows 0-4 and a block of quantised scores) go to the lower ROI index; DETECTION_MIN_CONFIDENCE is ignored here."""
+    from sln_amodal_b200 import refine_detections
+    rng = np.random.default_rng(7 * n + K)
+    rois = synth.roi_boxes(n, seed=n + 1)
+    logits = rng.standard_normal((n, K)).astype(np.float32) * 3.0
+    bg = rng.random(n) < bg_frac
+    logits[bg, 0] = 50.0                                   # background wins: filtered
+    probs = (np.exp(logits - logits.max(1, keepdims=True)) / np.exp(logits - logits.max(1, keepdims=True)).sum(1, keepdims=True)).astype(np.float32)
+    probs[:5] = probs[0]                                   # exact ties across rows
+    q = slice(n // 2, n // 2 + 40)
+    probs[q] = np.round(probs[q] * 8) / 8                  # many equal winning scores around the cut
+    deltas = (rng.standard_normal((n, K, 4)) * 0.3).astype(np.float32)
+    window = (0.0, 0.0, 1024.0, 1024.0)
+
+    class Cfg:
+        RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+        IMAGE_SHAPE = np.array([1024, 1024, 3])
+        USE_NMS = False
+        DETECTION_MIN_CONFIDENCE = 0.7                     # must NOT filter on this branch (:492-495)
+        DETECTION_NMS_THRESHOLD = 0.3
+
+    want_det, want_keep = oracle.refine_detections(rois, probs, deltas, window, use_nms=False)
+    det, keep = refine_detections(cuda(rois), cuda(probs), cuda(deltas), window, Cfg())
+    if want_keep.size == 0:
+        assert len(det) == 0 and len(keep) == 0
+        return
+    assert want_keep.size <= 100
+    assert np.array_equal(keep.cpu().numpy(), want_keep)
+    assert det.cpu().numpy().tobytes() == want_det.tobytes()
+
+
 # --------------------------------------------------------------------------- proposal layer
 class _Cfg:
     RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
