@@ -15,8 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsln_b200.so")
 SOURCES = ["lib.cu", "crop.cu", "nms.cu", "proposal.cu", "semdist.cu", "detection.cu", "rle.cu", "unmold.cu", "rpn.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "nms_core.cuh"),
-           os.path.join(os.path.dirname(HERE), "include", "sln_b200.h")]
+# every translation unit is rebuilt when any header changes (crop.cu includes crop_bwd_tma.cuh, ...)
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + \
+          [os.path.join(os.path.dirname(HERE), "include", "sln_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

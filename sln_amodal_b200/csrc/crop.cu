@@ -20,6 +20,8 @@
 //                   the reference's serial order (box, y, x, tap) in registers and
 //                   writes the pixel exactly once.  Result is bit-identical to the
 //                   reference's CPU backward and independent of scheduling.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sln {
@@ -895,6 +897,8 @@ crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ ta
     }
 }
 
+#include "crop_bwd_tma.cuh"
+
 // ===========================================================================
 // layout converters: per image, [C][HW] <-> [HW][C]
 // ===========================================================================
@@ -1009,17 +1013,47 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
 // A tile visit pays shared-memory read-modify-writes the strip form keeps in registers, which costs more than the
 // cheaper search saves once a tile sees ~9+ samples of a ROI (14x14 crops), so: tile form for crops of at most
 // BWD_TILE_MAX_SAMPLES samples, strip form above.  SLN_BWD_IMPL forces one of them (0 strip, 1 tile) for A/B runs.
-#ifndef SLN_BWD_IMPL
-#define SLN_BWD_IMPL 2
-#endif
+// Since round 2 both are the fallback for shapes the bulk-async kernel (crop_bwd_tma.cuh) does not take: channel counts
+// that are not a multiple of 4, unaligned pointers, crops larger than 32 samples per side.  SLN_BWD_IMPL in the
+// environment forces one form for A/B runs: 0 strip, 1 tile, 2 strip / tile by crop size, 3 (default) bulk-async.
 constexpr int BWD_TILE_MAX_SAMPLES = 64;
+static int bwd_impl_env()
+{
+    const char *e = getenv("SLN_BWD_IMPL");
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+}
+static bool bwd_use_tma(int ph, int pw, bool vec4)
+{
+    return bwd_impl_env() == 3 && vec4 && ph <= bwdtma::MAX_POOL && pw <= bwdtma::MAX_POOL;
+}
 static bool bwd_use_tile(int ph, int pw)
 {
-#if SLN_BWD_IMPL == 2
+    const int impl = bwd_impl_env();
+    if (impl == 0) return false;
+    if (impl == 1) return true;
     return ph * pw <= BWD_TILE_MAX_SAMPLES;
-#else
-    return SLN_BWD_IMPL == 1;
-#endif
+}
+
+template <bool EXACT>
+static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
+                          cudaStream_t st)
+{
+    const int chunks = cdiv(C, bwdtma::CH_MAX);
+    SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
+    if (tiles == 0) return SLN_OK;
+    BwdTileBases TB{};
+    TB.n_levels = P.n_levels;
+    for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
+    dim3 grid((unsigned)tiles, chunks);
+    const size_t smem = bwdtma::smem_bytes();
+    auto kern = C % 256 == 0  ? bwdtma::crop_bwd_tma_kernel<2, EXACT, true>
+                : C == 128    ? bwdtma::crop_bwd_tma_kernel<1, EXACT, true>
+                : C > 128     ? bwdtma::crop_bwd_tma_kernel<2, EXACT, false>
+                              : bwdtma::crop_bwd_tma_kernel<1, EXACT, false>;
+    SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, ws.taps, ws.entries, ws.st_off, ws.st_count, ws.lv_table, TB, C, ph, pw);
+    SLN_LAUNCH_OK("crop_bwd_tma_kernel");
+    return SLN_OK;
 }
 
 template <int VEC, int NV, bool EXACT>
@@ -1088,6 +1122,8 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     int n_st = 0;
     long long tiles = 0;
     bool vec4 = (C % 4 == 0) && aligned16(grads);
+    for (int l = 0; l < n_levels; ++l) vec4 = vec4 && aligned16(maps[l]);
+    const bool use_tma = bwd_use_tma(ph, pw, vec4);
     for (int l = 0; l < n_levels; ++l) {
         BwdLevel &L = P.lv[l];
         L.out = maps[l];
@@ -1098,7 +1134,10 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         while ((1 << L.sg_shift) < L.sg.side) ++L.sg_shift;
         L.st_base = n_st;
         n_st += B * L.sg.nx * L.sg.ny;
-        if (bwd_use_tile(ph, pw)) {
+        if (use_tma) {
+            L.tiles_x = cdiv(L.W, bwdtma::TW);
+            L.tiles_y = cdiv(L.H, bwdtma::TH);
+        } else if (bwd_use_tile(ph, pw)) {
             L.tiles_x = cdiv(L.W, BWD_TILE_WARPS * BWD_TILE);
             L.tiles_y = cdiv(L.H, BWD_TILE);
         } else {
@@ -1146,6 +1185,10 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
         crop_bwd_fill_kernel<<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, N, P, ws.st_count, ws.st_off,
                                                             ws.entries);
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
+    }
+    if (use_tma) {
+        if (exact) return launch_bwd_tma<true>(grads, ws, P, tiles, C, ph, pw, st);
+        return launch_bwd_tma<false>(grads, ws, P, tiles, C, ph, pw, st);
     }
     if (vec4) {
         if (exact) return dispatch_bwd<4, true>(grads, ws, P, tiles, C, ph, pw, st);
