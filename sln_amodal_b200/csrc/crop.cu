@@ -268,6 +268,15 @@ struct RoiAxes {
     float by, sy, bx, sx;
 };
 
+// list entry of the bulk-async kernel: the ROI's sampling grid rides along, so that the planner needs no second,
+// dependent load per ROI
+struct __align__(16) ListEntryA {
+    RoiWin win;
+    int roi;
+    int pad;
+    RoiAxes ax;
+};
+
 __device__ __forceinline__ void axis_base_scale(float a1, float a2, int extent, int crop, float &base, float &scale)
 {
     if (crop > 1) {
@@ -318,7 +327,8 @@ __device__ __forceinline__ BwdLevel pick_level(const BwdParams &P, int l)
 __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const int *__restrict__ box_ind,
                                         const int *__restrict__ level, int N, int B, int ph, int pw,
                                         BwdParams P, RoiWin *__restrict__ win, Tap *__restrict__ taps,
-                                        int *__restrict__ st_count, BwdLevel *__restrict__ lv_table)
+                                        RoiAxes *__restrict__ axes, int *__restrict__ st_count,
+                                        BwdLevel *__restrict__ lv_table)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
@@ -332,8 +342,16 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
         const BwdLevel L = pick_level(P, l);
         const float y1 = boxes[4 * r + 0], x1 = boxes[4 * r + 1], y2 = boxes[4 * r + 2], x2 = boxes[4 * r + 3];
         const float sc_y = axis_scale(y1, y2, L.H, ph), sc_x = axis_scale(x1, x2, L.W, pw);
-        for (int k = 0; k < ph; ++k) tp[k] = axis_tap(y1, y2, sc_y, L.H, ph, k);
-        for (int k = 0; k < pw; ++k) tp[ph + k] = axis_tap(x1, x2, sc_x, L.W, pw, k);
+        if (taps) {
+            for (int k = 0; k < ph; ++k) tp[k] = axis_tap(y1, y2, sc_y, L.H, ph, k);
+            for (int k = 0; k < pw; ++k) tp[ph + k] = axis_tap(x1, x2, sc_x, L.W, pw, k);
+        }
+        if (axes) {
+            RoiAxes a;
+            axis_base_scale(y1, y2, L.H, ph, a.by, a.sy);
+            axis_base_scale(x1, x2, L.W, pw, a.bx, a.sx);
+            axes[r] = a;
+        }
         int a0, a1, c0, c1;
         axis_window(y1, y2, L.H, ph, a0, a1);
         axis_window(x1, x2, L.W, pw, c0, c1);
@@ -354,11 +372,14 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
 constexpr int FILL_THREADS = 1024;
 constexpr int FILL_PER_THREAD = 8;
 
+template <bool WITH_AXES>
 __global__ void __launch_bounds__(FILL_THREADS)
 crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ level,
-                     const RoiWin *__restrict__ win, int N, BwdParams P, const int *__restrict__ st_count,
-                     int *__restrict__ st_off, ListEntry *__restrict__ entries)
+                     const RoiWin *__restrict__ win, const RoiAxes *__restrict__ axes, int N, BwdParams P,
+                     const int *__restrict__ st_count, int *__restrict__ st_off, void *__restrict__ entries_raw)
 {
+    ListEntry *__restrict__ entries = static_cast<ListEntry *>(entries_raw);
+    ListEntryA *__restrict__ entries_a = static_cast<ListEntryA *>(entries_raw);
     __shared__ int s_cnt[FILL_PER_THREAD][FILL_THREADS / 32];
     __shared__ int s_base;
     const int st = blockIdx.x;
@@ -430,10 +451,21 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ le
 #pragma unroll
         for (int it = 0; it < FILL_PER_THREAD; ++it) {
             if ((masks[it] >> lane) & 1u) {
-                ListEntry e;
-                e.win = w[it];
-                e.roi = start + it * FILL_THREADS + tid;
-                entries[base + s_cnt[it][warp] + __popc(masks[it] & ((1u << lane) - 1u))] = e;
+                const int slot = base + s_cnt[it][warp] + __popc(masks[it] & ((1u << lane) - 1u));
+                const int roi = start + it * FILL_THREADS + tid;
+                if (WITH_AXES) {
+                    ListEntryA e;
+                    e.win = w[it];
+                    e.roi = roi;
+                    e.pad = 0;
+                    e.ax = axes[roi];
+                    entries_a[slot] = e;
+                } else {
+                    ListEntry e;
+                    e.win = w[it];
+                    e.roi = roi;
+                    entries[slot] = e;
+                }
             }
         }
         base += s_base;
@@ -990,6 +1022,7 @@ static int crop_fwd_nhwc(const PyramidMaps &pm, int n_levels, bool levels, int B
 
 struct BwdWs {
     RoiWin *win;
+    RoiAxes *axes;
     Tap *taps;
     int *st_count;
     int *st_off;
@@ -1003,9 +1036,10 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
 {
     // every ROI lives on one level and meets at most 64 supertiles of its image
     const size_t n_st = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
-    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256) +
+    return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(RoiAxes) * (size_t)N, 256) +
+           align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256) +
            2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) +
-           align_up(sizeof(ListEntry) * (size_t)N * BWD_MAX_ST, 256);
+           align_up(sizeof(ListEntryA) * (size_t)N * BWD_MAX_ST, 256);
 }
 
 // Which gather kernel serves a call (A/B on B200, 8 x 1000 ROIs, C = 256, all four levels, ms per call incl. prep):
@@ -1039,19 +1073,23 @@ static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &
                           cudaStream_t st)
 {
     const int chunks = cdiv(C, bwdtma::CH_MAX);
-    SLN_REQUIRE(chunks <= 65535, SLN_ERR_ARG, "too many channel chunks");
-    if (tiles == 0) return SLN_OK;
+    const long long n_work = tiles * chunks;                 // work item = (tile, channel chunk)
+    SLN_REQUIRE(n_work < (1ll << 24), SLN_ERR_ARG, "too many tiles x channel chunks (%lld)", n_work);
+    if (n_work == 0) return SLN_OK;
     BwdTileBases TB{};
     TB.n_levels = P.n_levels;
     for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
-    dim3 grid((unsigned)tiles, chunks);
     const size_t smem = bwdtma::smem_bytes();
     auto kern = C % 256 == 0  ? bwdtma::crop_bwd_tma_kernel<2, EXACT, true>
                 : C == 128    ? bwdtma::crop_bwd_tma_kernel<1, EXACT, true>
                 : C > 128     ? bwdtma::crop_bwd_tma_kernel<2, EXACT, false>
                               : bwdtma::crop_bwd_tma_kernel<1, EXACT, false>;
     SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, ws.taps, ws.entries, ws.st_off, ws.st_count, ws.lv_table, TB, C, ph, pw);
+    // persistent: two CTAs per SM, CTA i plans work items i, i + grid, ... (heaviest levels first)
+    const long long resident = 2LL * sm_count();
+    const unsigned grid = (unsigned)(n_work < resident ? n_work : resident);
+    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, reinterpret_cast<const ListEntryA *>(ws.entries), ws.st_off,
+                                              ws.st_count, ws.lv_table, TB, C, ph, pw, (int)n_work, chunks);
     SLN_LAUNCH_OK("crop_bwd_tma_kernel");
     return SLN_OK;
 }
@@ -1170,6 +1208,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     const size_t n_st_cap = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
     BwdWs ws;
     ws.win = reinterpret_cast<RoiWin *>(p);        p += align_up(sizeof(RoiWin) * (size_t)N, 256);
+    ws.axes = reinterpret_cast<RoiAxes *>(p);      p += align_up(sizeof(RoiAxes) * (size_t)N, 256);
     ws.taps = reinterpret_cast<Tap *>(p);          p += align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256);
     ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * n_st_cap, 256);
     ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
@@ -1178,12 +1217,18 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
 
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
     // the windows kernel also publishes the level table, so it always runs (>= 1 CTA)
+    // the bulk-async kernel plans from the ROI's sampling grid (axes), the strip / tile forms from tap tables
     crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
-        boxes, box_ind, level, N, B, ph, pw, P, ws.win, ws.taps, ws.st_count, ws.lv_table);
+        boxes, box_ind, level, N, B, ph, pw, P, ws.win, use_tma ? nullptr : ws.taps, use_tma ? ws.axes : nullptr,
+        ws.st_count, ws.lv_table);
     SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
-        crop_bwd_fill_kernel<<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, N, P, ws.st_count, ws.st_off,
-                                                            ws.entries);
+        if (use_tma)
+            crop_bwd_fill_kernel<true><<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, ws.axes, N, P, ws.st_count,
+                                                                      ws.st_off, ws.entries);
+        else
+            crop_bwd_fill_kernel<false><<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, ws.axes, N, P, ws.st_count,
+                                                                       ws.st_off, ws.entries);
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
     if (use_tma) {
