@@ -376,10 +376,13 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
     }
 
     // =============================================================== consumers
-    const int j = warp;                                     // tile row
-    float4 acc[TW][NV];
+    // Warp c owns pixel COLUMN c of the tile (8 rows x C channels in registers).  A staged sample row reaches two pixel
+    // rows but, with its ~8-16 samples, every column of the tile: column ownership keeps all eight warps busy on every
+    // stage row (row ownership, the first version of this kernel, had two of eight at work and was latency-bound).
+    const int c = warp;                                     // tile column
+    float4 acc[TH][NV];
 #pragma unroll
-    for (int k = 0; k < TW; ++k)
+    for (int k = 0; k < TH; ++k)
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -390,53 +393,53 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
         const int4 hdr = *reinterpret_cast<const int4 *>(d);        // flags, n_s, n_rows, chb
         if (hdr.x != ST_DATA) {
             if (hdr.x == ST_EXIT) break;
-            // ---- end of tile: write the row exactly once (zeros included), clear the accumulators
+            // ---- end of tile: write the column exactly once (zeros included), clear the accumulators
             const TileOut o = *reinterpret_cast<const TileOut *>(d->rows);
             const int CH = hdr.y;
             const bool ok0 = FULL || lane * 4 < CH, ok1 = NV == 2 && (FULL || lane * 4 + 128 < CH);
-            if (j < o.ny) {
-                float4 *__restrict__ op = reinterpret_cast<float4 *>(o.out) + (size_t)j * o.row_stride + lane;
+            if (c < o.nx) {
+                float4 *__restrict__ op = reinterpret_cast<float4 *>(o.out) + (size_t)c * o.pix_stride + lane;
 #pragma unroll
-                for (int k = 0; k < TW; ++k) {
-                    if (k < o.nx) {
-                        if (ok0) __stcs(op + (size_t)k * o.pix_stride, acc[k][0]);
-                        if (ok1) __stcs(op + (size_t)k * o.pix_stride + 32, acc[k][1]);
+                for (int k = 0; k < TH; ++k) {
+                    if (k < o.ny) {
+                        if (ok0) __stcs(op + (size_t)k * o.row_stride, acc[k][0]);
+                        if (ok1) __stcs(op + (size_t)k * o.row_stride + 32, acc[k][1]);
                     }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < TW; ++k)
+            for (int k = 0; k < TH; ++k)
 #pragma unroll
                 for (int v = 0; v < NV; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
             continue;
         }
-        // the stage rows that reach my tile row: top tap on row j, or bottom tap (top on j - 1, lerp != 0); a run
-        int2 rr;
+        // the samples of a stage row whose left or right tap lands on my column: a run (tap columns are monotone in sx)
+        const int n_s = hdr.y;
+        int s0, ns;
         {
             bool hit = false;
-            if (lane < hdr.z) {
-                const int2 rd = d->rowd[lane];
-                hit = rd.x == j || (rd.x == j - 1 && __int_as_float(rd.y) != 0.f);
+            if (lane < n_s) {
+                const XEnt e = d->x[lane];
+                hit = e.pl == c || (e.pl == c - 1 && e.xl != 0.f);
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
-            rr = make_int2(m ? __ffs(m) - 1 : 0, __popc(m));
+            s0 = m ? __ffs(m) - 1 : 0;
+            ns = __popc(m);
         }
-        if (rr.y > 0) {
-            const int n_s = hdr.y;
+        if (ns > 0) {
             const int chb = FULL ? NV * 512 : hdr.w;
-            const unsigned char *rowp = stages + (size_t)s * STAGE_BYTES + (size_t)rr.x * n_s * chb + lane * 16;
             const bool ok0 = FULL || lane * 16 < chb, ok1 = NV == 2 && (FULL || lane * 16 + 512 < chb);
-            for (int r = rr.x; r < rr.x + rr.y; ++r) {
+            const unsigned char *stage = stages + (size_t)s * STAGE_BYTES + (size_t)s0 * chb + lane * 16;
+            for (int r = 0; r < hdr.z; ++r) {
                 const int2 rd = d->rowd[r];
+                const int rel = rd.x;                           // tile row of the top tap, -1 .. 7 (other values: no tap here)
                 const float yl = __int_as_float(rd.y);
-                const bool top = rd.x == j;
-                const float wy = top ? __fsub_rn(1.f, yl) : yl;
-                // integral sample row: the reference's bottom taps land on the same pixel row with weight 0
-                const int npass = (EXACT && top && yl == 0.f) ? 2 : 1;
-                const XEnt *xe = d->x;
-                for (int k = n_s; k > 0; --k, rowp += chb, ++xe) {
+                const float wt = __fsub_rn(1.f, yl);
+                const unsigned char *rowp = stage + (size_t)r * n_s * chb;
+                const XEnt *xe = d->x + s0;
+                for (int k = ns; k > 0; --k, rowp += chb, ++xe) {
                     const XEnt e = *xe;
                     float4 g0, g1;
                     if (FULL) {
@@ -450,8 +453,10 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                     }
                     const float wl = __fsub_rn(1.f, e.xl);
                     if (!EXACT) {
-                        const float a = __fmul_rn(wy, wl), bb = __fmul_rn(wy, e.xl);
-                        switch (e.pl) {
+                        // one x tap of the sample is mine (an integral column has its whole weight on the left tap)
+                        const float wx = e.pl == c ? wl : e.xl;
+                        const float a = __fmul_rn(wt, wx), bb = __fmul_rn(yl, wx);
+                        switch (rel) {
                         case -1: SLN_TMA_ADD(0, bb, 0.f, 0.f) break;
                         case 0: SLN_TMA_ADD(0, a, 0.f, 0.f) SLN_TMA_ADD(1, bb, 0.f, 0.f) break;
                         case 1: SLN_TMA_ADD(1, a, 0.f, 0.f) SLN_TMA_ADD(2, bb, 0.f, 0.f) break;
@@ -461,19 +466,23 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                         case 5: SLN_TMA_ADD(5, a, 0.f, 0.f) SLN_TMA_ADD(6, bb, 0.f, 0.f) break;
                         case 6: SLN_TMA_ADD(6, a, 0.f, 0.f) SLN_TMA_ADD(7, bb, 0.f, 0.f) break;
                         case 7: SLN_TMA_ADD(7, a, 0.f, 0.f) break;
-                        default: break;                      // not a column of this tile
+                        default: break;                      // not a row of this tile
                         }
                     } else {
-                        // reference order per sample: TL, TR (this row as the top row), then BL, BR when the sample row
-                        // is integral; the right tap coincides with the left one when the sample column is integral
+                        // reference order per sample and pixel: TL, TR on the top row, then BL, BR on the bottom row, which
+                        // is the same row (weight 0) when the sample row is integral; the right tap coincides with the left
+                        // one when the sample column is integral
                         const int pr = e.pl + (e.xl != 0.f);
-                        for (int pass = 0; pass < npass; ++pass) {
-                            const float w_y = pass == 0 ? wy : yl;
+                        const int rb = rel + (yl != 0.f);
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int row = pass == 0 ? rel : rb;
+                            const float w_y = pass == 0 ? wt : yl;
 #pragma unroll
                             for (int side = 0; side < 2; ++side) {
-                                const int p = side == 0 ? e.pl : pr;
+                                if ((side == 0 ? e.pl : pr) != c) continue;
                                 const float w_x = side == 0 ? wl : e.xl;
-                                switch (p) {
+                                switch (row) {
                                 case 0: SLN_TMA_ADD(0, 0.f, w_y, w_x) break;
                                 case 1: SLN_TMA_ADD(1, 0.f, w_y, w_x) break;
                                 case 2: SLN_TMA_ADD(2, 0.f, w_y, w_x) break;
