@@ -328,10 +328,11 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
                                         const int *__restrict__ level, int N, int B, int ph, int pw,
                                         BwdParams P, RoiWin *__restrict__ win, Tap *__restrict__ taps,
                                         RoiAxes *__restrict__ axes, int *__restrict__ st_count,
-                                        BwdLevel *__restrict__ lv_table)
+                                        BwdLevel *__restrict__ lv_table, int *__restrict__ queue, int queue_init)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
+    if (r == 0) *queue = queue_init;                 // ticket counter of the bulk-async kernel
     if (r >= N) return;
     RoiWin w;
     w.y0 = 1; w.y1 = 0; w.x0 = 1; w.x1 = 0;
@@ -1027,6 +1028,7 @@ struct BwdWs {
     int *st_count;
     int *st_off;
     BwdLevel *lv_table;
+    int *queue;
     ListEntry *entries;
 };
 
@@ -1038,7 +1040,7 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
     const size_t n_st = (size_t)B * BWD_MAX_ST * (size_t)n_levels + 1;
     return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(RoiAxes) * (size_t)N, 256) +
            align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256) +
-           2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) +
+           2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) + 256 +
            align_up(sizeof(ListEntryA) * (size_t)N * BWD_MAX_ST, 256);
 }
 
@@ -1068,6 +1070,14 @@ static bool bwd_use_tile(int ph, int pw)
     return ph * pw <= BWD_TILE_MAX_SAMPLES;
 }
 
+// persistent grid of the bulk-async kernel: two CTAs per SM; CTA i starts with work item i and then draws tickets
+// (heaviest levels first)
+static unsigned bwd_tma_grid(long long n_work)
+{
+    const long long resident = 2LL * sm_count();
+    return (unsigned)(n_work < resident ? n_work : resident);
+}
+
 template <bool EXACT>
 static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
                           cudaStream_t st)
@@ -1085,11 +1095,11 @@ static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &
                 : C > 128     ? bwdtma::crop_bwd_tma_kernel<2, EXACT, false>
                               : bwdtma::crop_bwd_tma_kernel<1, EXACT, false>;
     SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent: two CTAs per SM, CTA i plans work items i, i + grid, ... (heaviest levels first)
-    const long long resident = 2LL * sm_count();
-    const unsigned grid = (unsigned)(n_work < resident ? n_work : resident);
+    const unsigned grid = bwd_tma_grid(n_work);
+    // work-item tickets: tickets below `grid` are the CTAs' first items
+    // (the counter starts at `grid`, set by the windows kernel)
     kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, reinterpret_cast<const ListEntryA *>(ws.entries), ws.st_off,
-                                              ws.st_count, ws.lv_table, TB, C, ph, pw, (int)n_work, chunks);
+                                              ws.st_count, ws.lv_table, TB, C, ph, pw, (int)n_work, chunks, ws.queue);
     SLN_LAUNCH_OK("crop_bwd_tma_kernel");
     return SLN_OK;
 }
@@ -1213,6 +1223,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     ws.st_count = reinterpret_cast<int *>(p);      p += align_up(sizeof(int) * n_st_cap, 256);
     ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
     ws.lv_table = reinterpret_cast<BwdLevel *>(p); p += align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256);
+    ws.queue = reinterpret_cast<int *>(p);         p += 256;
     ws.entries = reinterpret_cast<ListEntry *>(p);
 
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
@@ -1220,7 +1231,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     // the bulk-async kernel plans from the ROI's sampling grid (axes), the strip / tile forms from tap tables
     crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
         boxes, box_ind, level, N, B, ph, pw, P, ws.win, use_tma ? nullptr : ws.taps, use_tma ? ws.axes : nullptr,
-        ws.st_count, ws.lv_table);
+        ws.st_count, ws.lv_table, ws.queue, (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX)));
     SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
         if (use_tma)

@@ -207,7 +207,7 @@ template <int NV, bool EXACT, bool FULL>
 __global__ void __launch_bounds__(THREADS, 2)
 crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restrict__ entries, const int *__restrict__ st_off,
                     const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
-                    BwdTileBases TB, int C, int ph, int pw, int n_work, int chunks)
+                    BwdTileBases TB, int C, int ph, int pw, int n_work, int chunks, int *__restrict__ queue)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -247,10 +247,16 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
             e.ax.by = e.ax.sy = e.ax.bx = e.ax.sx = 0.f;
             return e;
         };
-        // tile pipeline: while tile C is planned, the first list chunk of tile B (the next one of this CTA) and the list
-        // count / offset of tile A (the one after) are in flight
-        const int stride = gridDim.x;
-        int wC = blockIdx.x, wB = wC + stride;
+        // tile pipeline: work items come from a global ticket counter (heaviest levels first, so the light P2 tiles fill
+        // the tail); while item C is planned, the first list chunk of item B, the list count / offset of item A and the
+        // ticket of the item after that are in flight.  Tickets 0 .. gridDim.x - 1 are the CTAs' first items.
+        auto ticket = [&]() -> int {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(queue, 1);
+            return t;                                      // lane 0 only; broadcast when it is needed
+        };
+        int wC = blockIdx.x;
+        int wB = __shfl_sync(0xffffffffu, ticket(), 0), wA = __shfl_sync(0xffffffffu, ticket(), 0);
         int cntC = 0, offC = 0, cntB = 0, offB = 0;
         TileGeom gC{}, gB{};
         ListEntryA eC = no_entry();
@@ -266,9 +272,9 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
             offB = st_off[gB.st];
         }
         while (wC < n_work) {
+            const int tF = ticket();
             ListEntryA eB = no_entry();
             if (wB < n_work && lane < cntB) eB = entries[offB + lane];
-            const int wA = wB + stride;
             int cntA = 0, offA = 0;
             TileGeom gA{};
             if (wA < n_work) {
@@ -366,6 +372,7 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
             }
             wC = wB; cntC = cntB; offC = offB; eC = eB; gC = gB;
             wB = wA; cntB = cntA; offB = offA; gB = gA;
+            wA = __shfl_sync(0xffffffffu, tF, 0);
         }
         const unsigned s = acquire();
         if (lane == 0) {
