@@ -328,7 +328,8 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
                                         const int *__restrict__ level, int N, int B, int ph, int pw,
                                         BwdParams P, RoiWin *__restrict__ win, Tap *__restrict__ taps,
                                         RoiAxes *__restrict__ axes, int *__restrict__ st_count,
-                                        BwdLevel *__restrict__ lv_table, int *__restrict__ queue, int queue_init)
+                                        BwdLevel *__restrict__ lv_table, int *__restrict__ queue, int queue_init,
+                                        int *__restrict__ gid)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
@@ -336,6 +337,7 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
     if (r >= N) return;
     RoiWin w;
     w.y0 = 1; w.y1 = 0; w.x0 = 1; w.x1 = 0;
+    int my_gid = -1;                                 // (image, level) group of the ROI; -1: contributes nothing
     const int b = box_ind[r];
     const int l = level ? level[r] : 0;
     Tap *tp = taps + (size_t)r * (ph + pw);          // [ph] y taps then [pw] x taps of this ROI
@@ -357,6 +359,7 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
         axis_window(y1, y2, L.H, ph, a0, a1);
         axis_window(x1, x2, L.W, pw, c0, c1);
         if (a0 <= a1 && c0 <= c1) {
+            my_gid = b * P.n_levels + l;
             w.y0 = (short)a0; w.y1 = (short)a1; w.x0 = (short)c0; w.x1 = (short)c1;
             for (int sy = a0 >> L.sg_shift; sy <= (a1 >> L.sg_shift); ++sy)
                 for (int sx = c0 >> L.sg_shift; sx <= (c1 >> L.sg_shift); ++sx)
@@ -364,18 +367,70 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
         }
     }
     win[r] = w;
+    gid[r] = my_gid;
 }
 
-// prep 2: ordered fill.  One CTA per supertile: its list offset is the sum of the counts of
+// prep 2: ordered ROI list of every (image, level) group.  One CTA per group walks the group ids of all ROIs (4 bytes each)
+// and compacts the ids of its own ROIs in index order; the supertile fill below then looks at its group's ROIs only
+// (~N / groups of them) instead of all N.  glist [n_groups][N], gcount [n_groups].
+constexpr int GROUP_THREADS = 1024;
+constexpr int GROUP_PER_THREAD = 8;
+
+__global__ void __launch_bounds__(GROUP_THREADS)
+crop_bwd_group_kernel(const int *__restrict__ gid, int N, int *__restrict__ glist, int *__restrict__ gcount)
+{
+    __shared__ int s_cnt[GROUP_PER_THREAD][GROUP_THREADS / 32];
+    __shared__ int s_total;
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *__restrict__ out = glist + (size_t)g * N;
+    int base = 0;
+    for (int start = 0; start < N; start += GROUP_THREADS * GROUP_PER_THREAD) {
+        unsigned masks[GROUP_PER_THREAD];
+        __syncthreads();                                          // s_cnt reuse
+#pragma unroll
+        for (int it = 0; it < GROUP_PER_THREAD; ++it) {
+            const int r = start + it * GROUP_THREADS + tid;
+            const bool take = r < N && gid[r] == g;
+            masks[it] = __ballot_sync(0xffffffffu, take);
+            if (lane == 0) s_cnt[it][warp] = __popc(masks[it]);
+        }
+        __syncthreads();
+        if (warp == 0) {                                          // exclusive scan over the (it, warp) grid in ROI order
+            int run = 0;
+#pragma unroll
+            for (int it = 0; it < GROUP_PER_THREAD; ++it) {
+                const int c = s_cnt[it][lane];
+                int incl = c;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                s_cnt[it][lane] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < GROUP_PER_THREAD; ++it)
+            if ((masks[it] >> lane) & 1u)
+                out[base + s_cnt[it][warp] + __popc(masks[it] & ((1u << lane) - 1u))] = start + it * GROUP_THREADS + tid;
+        base += s_total;
+    }
+    if (tid == 0) gcount[g] = base;
+}
+
+// prep 3: ordered fill.  One CTA per supertile: its list offset is the sum of the counts of
 // the supertiles before it; it then takes the ROIs in index order, FILL_PER_THREAD x 1024 at
 // a time (all loads issued up front), and compacts the hits with one block-wide scan so the
 // list keeps the original box order.  st_off[st] is published for the main kernel.
 constexpr int FILL_THREADS = 1024;
-constexpr int FILL_PER_THREAD = 8;
+constexpr int FILL_PER_THREAD = 2;
 
 template <bool WITH_AXES>
 __global__ void __launch_bounds__(FILL_THREADS)
-crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ level,
+crop_bwd_fill_kernel(const int *__restrict__ glist, const int *__restrict__ gcount,
                      const RoiWin *__restrict__ win, const RoiAxes *__restrict__ axes, int N, BwdParams P,
                      const int *__restrict__ st_count, int *__restrict__ st_off, void *__restrict__ entries_raw)
 {
@@ -408,26 +463,26 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ le
     const int local = st - L.st_base;
     const int sx = local % L.sg.nx, sy = (local / L.sg.nx) % L.sg.ny, b = local / (L.sg.nx * L.sg.ny);
     const int y0 = sy << L.sg_shift, y1 = y0 + L.sg.side - 1, x0 = sx << L.sg_shift, x1 = x0 + L.sg.side - 1;
-    for (int start = 0; start < N; start += FILL_THREADS * FILL_PER_THREAD) {
+    // the ROIs of this supertile's (image, level) group, in index order
+    const int g = b * P.n_levels + l;
+    const int n_g = gcount[g];
+    const int *__restrict__ gl = glist + (size_t)g * N;
+    for (int start = 0; start < n_g; start += FILL_THREADS * FILL_PER_THREAD) {
         RoiWin w[FILL_PER_THREAD];
-        int bi[FILL_PER_THREAD], lv[FILL_PER_THREAD];
+        int roi[FILL_PER_THREAD];
 #pragma unroll
         for (int it = 0; it < FILL_PER_THREAD; ++it) {          // all loads first
-            const int r = start + it * FILL_THREADS + tid;
-            bi[it] = -1;
-            lv[it] = l;
-            if (r < N) {
-                bi[it] = box_ind[r];
-                if (level) lv[it] = level[r];
-                w[it] = win[r];
-            }
+            const int i = start + it * FILL_THREADS + tid;
+            roi[it] = i < n_g ? gl[i] : -1;
         }
+#pragma unroll
+        for (int it = 0; it < FILL_PER_THREAD; ++it)
+            if (roi[it] >= 0) w[it] = win[roi[it]];
         unsigned masks[FILL_PER_THREAD];
         __syncthreads();                                          // s_cnt reuse
 #pragma unroll
         for (int it = 0; it < FILL_PER_THREAD; ++it) {
-            const bool take = bi[it] == b && lv[it] == l && (w[it].y0 <= w[it].y1) &&
-                              !(w[it].y1 < y0 || w[it].y0 > y1 || w[it].x1 < x0 || w[it].x0 > x1);
+            const bool take = roi[it] >= 0 && !(w[it].y1 < y0 || w[it].y0 > y1 || w[it].x1 < x0 || w[it].x0 > x1);
             masks[it] = __ballot_sync(0xffffffffu, take);
             if (lane == 0) s_cnt[it][warp] = __popc(masks[it]);
         }
@@ -453,18 +508,17 @@ crop_bwd_fill_kernel(const int *__restrict__ box_ind, const int *__restrict__ le
         for (int it = 0; it < FILL_PER_THREAD; ++it) {
             if ((masks[it] >> lane) & 1u) {
                 const int slot = base + s_cnt[it][warp] + __popc(masks[it] & ((1u << lane) - 1u));
-                const int roi = start + it * FILL_THREADS + tid;
                 if (WITH_AXES) {
                     ListEntryA e;
                     e.win = w[it];
-                    e.roi = roi;
+                    e.roi = roi[it];
                     e.pad = 0;
-                    e.ax = axes[roi];
+                    e.ax = axes[roi[it]];
                     entries_a[slot] = e;
                 } else {
                     ListEntry e;
                     e.win = w[it];
-                    e.roi = roi;
+                    e.roi = roi[it];
                     entries[slot] = e;
                 }
             }
@@ -1029,6 +1083,9 @@ struct BwdWs {
     int *st_off;
     BwdLevel *lv_table;
     int *queue;
+    int *gid;       // [N] (image, level) group of every ROI
+    int *gcount;    // [B * n_levels]
+    int *glist;     // [B * n_levels][N] ROI ids per group, in index order
     ListEntry *entries;
 };
 
@@ -1041,6 +1098,8 @@ static size_t bwd_ws_bytes(int N, int B, int n_levels, int ph, int pw)
     return align_up(sizeof(RoiWin) * (size_t)N, 256) + align_up(sizeof(RoiAxes) * (size_t)N, 256) +
            align_up(sizeof(Tap) * (size_t)N * (size_t)(ph + pw), 256) +
            2 * align_up(sizeof(int) * n_st, 256) + align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256) + 256 +
+           align_up(sizeof(int) * (size_t)N, 256) + align_up(sizeof(int) * (size_t)B * n_levels, 256) +
+           align_up(sizeof(int) * (size_t)B * n_levels * (size_t)N, 256) +
            align_up(sizeof(ListEntryA) * (size_t)N * BWD_MAX_ST, 256);
 }
 
@@ -1078,6 +1137,25 @@ static unsigned bwd_tma_grid(long long n_work)
     return (unsigned)(n_work < resident ? n_work : resident);
 }
 
+// One configuration of the bulk-async kernel (stage size, ring depth; see crop_bwd_tma.cuh).
+template <bool EXACT, int STG_S, int NST>
+static int launch_bwd_tma_cfg(const float *grads, const BwdWs &ws, const BwdTileBases &TB, long long n_work, int chunks, int C,
+                              int ph, int pw, cudaStream_t st)
+{
+    const size_t smem = bwdtma::smem_bytes<STG_S, NST>();
+    auto kern = C % 256 == 0  ? bwdtma::crop_bwd_tma_kernel<2, EXACT, true, STG_S, NST>
+                : C == 128    ? bwdtma::crop_bwd_tma_kernel<1, EXACT, true, STG_S, NST>
+                : C > 128     ? bwdtma::crop_bwd_tma_kernel<2, EXACT, false, STG_S, NST>
+                              : bwdtma::crop_bwd_tma_kernel<1, EXACT, false, STG_S, NST>;
+    SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // work-item tickets: tickets below `grid` are the CTAs' first items (the counter starts there, set by the windows kernel)
+    const unsigned grid = bwd_tma_grid(n_work);
+    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, reinterpret_cast<const ListEntryA *>(ws.entries), ws.st_off, ws.st_count,
+                                              ws.lv_table, TB, C, ph, pw, (int)n_work, chunks, ws.queue);
+    SLN_LAUNCH_OK("crop_bwd_tma_kernel");
+    return SLN_OK;
+}
+
 template <bool EXACT>
 static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &P, long long tiles, int C, int ph, int pw,
                           cudaStream_t st)
@@ -1089,19 +1167,12 @@ static int launch_bwd_tma(const float *grads, const BwdWs &ws, const BwdParams &
     BwdTileBases TB{};
     TB.n_levels = P.n_levels;
     for (int j = 0; j < P.n_levels; ++j) { TB.base[j] = P.sched_base[j]; TB.lvl[j] = P.sched_lvl[j]; }
-    const size_t smem = bwdtma::smem_bytes();
-    auto kern = C % 256 == 0  ? bwdtma::crop_bwd_tma_kernel<2, EXACT, true>
-                : C == 128    ? bwdtma::crop_bwd_tma_kernel<1, EXACT, true>
-                : C > 128     ? bwdtma::crop_bwd_tma_kernel<2, EXACT, false>
-                              : bwdtma::crop_bwd_tma_kernel<1, EXACT, false>;
-    SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = bwd_tma_grid(n_work);
-    // work-item tickets: tickets below `grid` are the CTAs' first items
-    // (the counter starts at `grid`, set by the windows kernel)
-    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, reinterpret_cast<const ListEntryA *>(ws.entries), ws.st_off,
-                                              ws.st_count, ws.lv_table, TB, C, ph, pw, (int)n_work, chunks, ws.queue);
-    SLN_LAUNCH_OK("crop_bwd_tma_kernel");
-    return SLN_OK;
+    // small crops stage ~8 samples per (ROI, tile) hit: more, smaller stages; large crops: fewer, larger ones.
+    // SLN_BWD_CFG=0/1 in the environment forces one for A/B runs.
+    const char *e = getenv("SLN_BWD_CFG");
+    const bool small = (e && (e[0] == '0' || e[0] == '1')) ? e[0] == '1' : ph * pw <= 64;
+    if (small) return launch_bwd_tma_cfg<EXACT, 16, 6>(grads, ws, TB, n_work, chunks, C, ph, pw, st);
+    return launch_bwd_tma_cfg<EXACT, 32, 3>(grads, ws, TB, n_work, chunks, C, ph, pw, st);
 }
 
 template <int VEC, int NV, bool EXACT>
@@ -1224,6 +1295,9 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     ws.st_off = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * n_st_cap, 256);
     ws.lv_table = reinterpret_cast<BwdLevel *>(p); p += align_up(sizeof(BwdLevel) * BWD_MAX_LEVELS, 256);
     ws.queue = reinterpret_cast<int *>(p);         p += 256;
+    ws.gid = reinterpret_cast<int *>(p);           p += align_up(sizeof(int) * (size_t)N, 256);
+    ws.gcount = reinterpret_cast<int *>(p);        p += align_up(sizeof(int) * (size_t)B * n_levels, 256);
+    ws.glist = reinterpret_cast<int *>(p);         p += align_up(sizeof(int) * (size_t)B * n_levels * (size_t)N, 256);
     ws.entries = reinterpret_cast<ListEntry *>(p);
 
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
@@ -1231,14 +1305,16 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     // the bulk-async kernel plans from the ROI's sampling grid (axes), the strip / tile forms from tap tables
     crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
         boxes, box_ind, level, N, B, ph, pw, P, ws.win, use_tma ? nullptr : ws.taps, use_tma ? ws.axes : nullptr,
-        ws.st_count, ws.lv_table, ws.queue, (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX)));
+        ws.st_count, ws.lv_table, ws.queue, (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX)), ws.gid);
     SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
+        crop_bwd_group_kernel<<<B * n_levels, GROUP_THREADS, 0, st>>>(ws.gid, N, ws.glist, ws.gcount);
+        SLN_LAUNCH_OK("crop_bwd_group_kernel");
         if (use_tma)
-            crop_bwd_fill_kernel<true><<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, ws.axes, N, P, ws.st_count,
+            crop_bwd_fill_kernel<true><<<n_st, FILL_THREADS, 0, st>>>(ws.glist, ws.gcount, ws.win, ws.axes, N, P, ws.st_count,
                                                                       ws.st_off, ws.entries);
         else
-            crop_bwd_fill_kernel<false><<<n_st, FILL_THREADS, 0, st>>>(box_ind, level, ws.win, ws.axes, N, P, ws.st_count,
+            crop_bwd_fill_kernel<false><<<n_st, FILL_THREADS, 0, st>>>(ws.glist, ws.gcount, ws.win, ws.axes, N, P, ws.st_count,
                                                                        ws.st_off, ws.entries);
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }

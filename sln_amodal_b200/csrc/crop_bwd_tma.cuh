@@ -34,42 +34,33 @@ constexpr int TH = 8;                  // tile rows = consumer warps
 constexpr int TW = 8;                  // tile columns = accumulator pixels per consumer lane
 constexpr int NCONS = TH;
 constexpr int THREADS = 32 * (NCONS + 1);
-#ifndef SLN_BWD_STG_S
-#define SLN_BWD_STG_S 32
-#endif
-#ifndef SLN_BWD_NST
-#define SLN_BWD_NST 3
-#endif
-constexpr int STG_S = SLN_BWD_STG_S;   // samples (and at most as many rows / sample columns) per stage, <= 64
-constexpr int NST = SLN_BWD_NST;       // stages in the ring
-constexpr int MAX_POOL = 32;           // tap tables live one tap per lane
+constexpr int MAX_POOL = 32;           // one sample row / column per lane
 constexpr int CH_MAX = 256;            // channels per CTA (two float4 per consumer lane)
-constexpr int STAGE_BYTES = STG_S * CH_MAX * 4;
-static_assert(STG_S >= 8 && STG_S <= 32, "a consumer finds its sample columns with one 32-lane ballot");
+// Per launch configuration (template parameters of the kernel): STG_S samples per stage (and at most as many rows /
+// sample columns), 8 .. 32; NST stages in the ring.  Shared memory allows STG_S * NST = 96 KB per CTA at two CTAs per SM.
+// Measured on B200 (8 x 1000 ROIs, C = 256, ms per call incl. prep; A/B in profiles/README.md): 7x7 prefers 16 x 6
+// (0.309 against 0.318 for 32 x 3), 14x14 and 16x16 prefer 32 x 3 (0.497 / 0.578 against 0.510 / 0.599).
 
 struct XEnt {
     int pl;          // tile column of the left tap (-1 .. 7)
     float xl;        // lerp
 };
-enum { ST_TILE_END = 1, ST_EXIT = 2 };   // StageDesc::flags bits
-struct TileOut {              // valid when flags & ST_TILE_END
+enum { ST_DATA = 0, ST_TILE_END = 1, ST_EXIT = 2 };
+template <int STG_S>
+struct StageDesc {
+    int flags;       // ST_*
+    int n_s;         // ST_DATA: samples per stage row.  ST_TILE_END: channels of the work item
+    int n_rows;
+    int chb;         // bytes per staged sample (channels of the work item * 4)
+    int2 rows[TH];   // ST_TILE_END: the write-out record (TileOut)
+    int2 rowd[STG_S];   // per stage row: (tile row of its top tap, -1 .. 7; lerp bits)
+    XEnt x[STG_S];      // per sample column of the stage
+};
+struct TileOut {     // overlays StageDesc::rows for ST_TILE_END
     unsigned long long out;   // float4* of pixel (b, y0, x0), channel c0
     int row_stride;           // float4 per map row
     int pix_stride;           // float4 per pixel
     int ny, nx;               // valid rows / columns of the tile
-};
-// A stage holds sample rows of one or more (ROI, tile) hits, packed back to back: row r = n_s staged samples starting
-// at sample offset soff of the stage's data; its sample columns are x[x_off .. x_off + n_s).
-struct StageDesc {
-    int flags;       // ST_* bits: after the rows, write the tile out / leave
-    int n_rows;
-    int n_x;         // entries of x[] in use
-    int chb;         // bytes per staged sample (channels of the work item * 4)
-    TileOut tile;
-    int pad[2];
-    int2 rowd[STG_S];   // per stage row: (rel + 1) | x_off << 8 | n_s << 16 | soff << 24 ; lerp bits.  rel = tile row of the
-                        // row's top tap, -1 .. 7
-    XEnt x[STG_S];      // sample columns
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,10 +76,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // try_wait suspends the thread in hardware for a bounded time, so the loop does not spin on the issue port
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -212,7 +199,7 @@ __device__ __forceinline__ TileGeom tile_geom(int w, int chunks, const BwdTileBa
 }
 
 // FULL: the CTA's channel chunk fills every lane's vectors (CH == 128 * NV), so no lane predicates
-template <int NV, bool EXACT, bool FULL>
+template <int NV, bool EXACT, bool FULL, int STG_S, int NST>
 __global__ void __launch_bounds__(THREADS, 2)
 crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restrict__ entries, const int *__restrict__ st_off,
                     const int *__restrict__ st_count, const BwdLevel *__restrict__ lv_table,
@@ -221,9 +208,12 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    static_assert(STG_S >= 8 && STG_S <= 32, "a consumer finds its sample columns with one 32-lane ballot");
+    constexpr int STAGE_BYTES = STG_S * CH_MAX * 4;
+    using Desc = StageDesc<STG_S>;
     // ---- shared memory carve-up
     unsigned char *stages = s_raw;                                                    // [NST][STAGE_BYTES]
-    StageDesc *sdesc = reinterpret_cast<StageDesc *>(s_raw + (size_t)NST * STAGE_BYTES);
+    Desc *sdesc = reinterpret_cast<Desc *>(s_raw + (size_t)NST * STAGE_BYTES);
     BwdLevel *lv = reinterpret_cast<BwdLevel *>(sdesc + NST);
     uint64_t *bars = reinterpret_cast<uint64_t *>(lv + BWD_MAX_LEVELS);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NST;
@@ -246,29 +236,6 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
             const unsigned s = sc % NST;
             mbar_wait(empty0 + 8 * s, ((sc / NST) & 1) ^ 1);
             return s;
-        };
-        // the open stage: rows are appended (descriptor entries by the lanes that hold them, bytes announced with
-        // expect_tx, one bulk copy per row) until the next hit does not fit; closing it is the producer's one arrival
-        bool open = false;
-        unsigned s_cur = 0;
-        int u_rows = 0, u_x = 0, u_smp = 0;
-        auto open_stage = [&]() {
-            s_cur = acquire();
-            open = true;
-            u_rows = u_x = u_smp = 0;
-        };
-        auto close_stage = [&](int flags, int chb) {
-            __syncwarp();
-            if (lane == 0) {
-                StageDesc *d = sdesc + s_cur;
-                d->flags = flags;
-                d->n_rows = u_rows;
-                d->n_x = u_x;
-                d->chb = chb;
-                mbar_arrive(full0 + 8 * s_cur);
-            }
-            ++sc;
-            open = false;
         };
         auto no_entry = []() {
             ListEntryA e;
@@ -347,31 +314,31 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                     const int sy0 = pk & 0xff, nsy = (pk >> 8) & 0xff, sx0 = (pk >> 16) & 0xff, nsx = (pk >> 24) & 0xff;
                     // lane i: tap of sample row sy0 + i and of sample column sx0 + i (same arithmetic as the forward)
                     const Tap ty = tap_at(by, sy, em1y, sy0 + lane), tx = tap_at(bx, sx, em1x, sx0 + lane);
+                    const int2 my_row = make_int2(ty.lo - y0, __float_as_int(ty.lerp));
                     XEnt my_col;
                     my_col.pl = tx.lo - x0;
                     my_col.xl = tx.lerp;
                     const float *gr = grads + ((size_t)r * S + (size_t)sy0 * pw + sx0) * C + c0;
-                    // append the hit to the open stage, row by row; sample columns in chunks of at most STG_S
-                    for (int sb = 0; sb < nsx; sb += STG_S) {
-                        const int n_s = min(STG_S, nsx - sb);
-                        const int rcol = lane - sb;
-                        int ra = 0;
-                        while (ra < nsy) {
-                            if (open && (u_x + n_s > STG_S || u_smp + n_s > STG_S)) close_stage(0, chb);
-                            if (!open) open_stage();
-                            const int n_rows = min(nsy - ra, (STG_S - u_smp) / n_s);
-                            StageDesc *d = sdesc + s_cur;
-                            const int rrow = lane - ra;
+                    // stages: whole sample rows, as many as fit; a row longer than a stage takes several stages
+                    const int n_s_full = min(nsx, STG_S);
+                    const int rows_per = nsx <= STG_S ? STG_S / nsx : 1;
+                    for (int ra = 0; ra < nsy; ra += rows_per) {
+                        const int n_rows = min(rows_per, nsy - ra);
+                        for (int sb = 0; sb < nsx; sb += STG_S) {
+                            const int n_s = min(n_s_full, nsx - sb);
+                            const unsigned s = acquire();
+                            Desc *d = sdesc + s;
+                            if (lane == 0) *reinterpret_cast<int4 *>(d) = make_int4(ST_DATA, n_s, n_rows, chb);
+                            const int rrow = lane - ra, rcol = lane - sb;
                             const bool row_mine = rrow >= 0 && rrow < n_rows;
-                            const int soff = u_smp + rrow * n_s;
-                            if (row_mine) d->rowd[u_rows + rrow] = make_int2((ty.lo - y0 + 1) | (u_x << 8) | (n_s << 16) | (soff << 24),
-                                                                             __float_as_int(ty.lerp));
-                            if (rcol >= 0 && rcol < n_s) d->x[u_x + rcol] = my_col;
-                            const uint32_t bar = full0 + 8 * s_cur;
-                            if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_rows * n_s * chb));
+                            if (row_mine) d->rowd[rrow] = my_row;
+                            if (rcol >= 0 && rcol < n_s) d->x[rcol] = my_col;
                             __syncwarp();
-                            if (row_mine) {                  // lane ra + i fetches row i of this batch
-                                const uint32_t dst = smem_u32(stages + (size_t)s_cur * STAGE_BYTES) + soff * chb;
+                            const uint32_t bar = full0 + 8 * s;
+                            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(n_rows * n_s * chb));
+                            __syncwarp();
+                            if (row_mine) {                  // lane ra + i fetches stage row i
+                                const uint32_t dst = smem_u32(stages + (size_t)s * STAGE_BYTES) + rrow * n_s * chb;
                                 const float *src = gr + ((size_t)lane * pw + sb) * C;
                                 if (CH == C) {
                                     bulk_g2s(dst, src, (uint32_t)(n_s * chb), bar);
@@ -379,32 +346,37 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                                     for (int k = 0; k < n_s; ++k) bulk_g2s(dst + k * chb, src + (size_t)k * C, (uint32_t)chb, bar);
                                 }
                             }
-                            u_rows += n_rows;
-                            u_x += n_s;
-                            u_smp += n_rows * n_s;
-                            ra += n_rows;
+                            ++sc;
                         }
                     }
                 }
             }
-            // end of tile: the write-out record rides on the tile's last stage (an empty one if the tile saw no ROI);
-            // the CTA's last tile also tells the consumers to leave
+            // end of tile: the write-out record
             {
-                if (!open) open_stage();
+                const unsigned s = acquire();
+                Desc *d = sdesc + s;
                 if (lane == 0) {
+                    d->flags = ST_TILE_END;
+                    d->n_s = CH;
                     TileOut o;
                     o.out = (unsigned long long)(L.out + (((size_t)gC.b * L.H + y0) * L.W + x0) * C + c0);
                     o.row_stride = L.W * (C / 4);
                     o.pix_stride = C / 4;
                     o.ny = y1 - y0 + 1;
                     o.nx = x1 - x0 + 1;
-                    sdesc[s_cur].tile = o;
+                    *reinterpret_cast<TileOut *>(d->rows) = o;
+                    mbar_arrive(full0 + 8 * s);
                 }
-                close_stage(ST_TILE_END | (wB >= n_work ? ST_EXIT : 0), chb);
+                ++sc;
             }
             wC = wB; cntC = cntB; offC = offB; eC = eB; gC = gB;
             wB = wA; cntB = cntA; offB = offA; gB = gA;
             wA = __shfl_sync(0xffffffffu, tF, 0);
+        }
+        const unsigned s = acquire();
+        if (lane == 0) {
+            sdesc[s].flags = ST_EXIT;
+            mbar_arrive(full0 + 8 * s);
         }
         return;
     }
@@ -414,46 +386,65 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
     // rows but, with its ~8-16 samples, every column of the tile: column ownership keeps all eight warps busy on every
     // stage row (row ownership, the first version of this kernel, had two of eight at work and was latency-bound).
     const int c = warp;                                     // tile column
-    unsigned sc = 0;                                        // stages consumed so far
-    for (;;) {                                              // one iteration per tile
     float4 acc[TH][NV];
 #pragma unroll
     for (int k = 0; k < TH; ++k)
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    TileOut o;
-    int flags, CH;
-    for (;; ++sc) {                                         // the tile's stages
+
+    for (unsigned sc = 0;; ++sc) {
         const unsigned s = sc % NST;
         mbar_wait(full0 + 8 * s, (sc / NST) & 1);
-        const StageDesc *d = sdesc + s;
-        const int4 hdr = *reinterpret_cast<const int4 *>(d);        // flags, n_rows, n_x, chb
-        // the sample columns of the stage whose left or right tap lands on my pixel column
-        unsigned m;
+        const Desc *d = sdesc + s;
+        const int4 hdr = *reinterpret_cast<const int4 *>(d);        // flags, n_s, n_rows, chb
+        if (hdr.x != ST_DATA) {
+            if (hdr.x == ST_EXIT) break;
+            // ---- end of tile: write the column exactly once (zeros included), clear the accumulators
+            const TileOut o = *reinterpret_cast<const TileOut *>(d->rows);
+            const int CH = hdr.y;
+            const bool ok0 = FULL || lane * 4 < CH, ok1 = NV == 2 && (FULL || lane * 4 + 128 < CH);
+            if (c < o.nx) {
+                float4 *__restrict__ op = reinterpret_cast<float4 *>(o.out) + (size_t)c * o.pix_stride + lane;
+#pragma unroll
+                for (int k = 0; k < TH; ++k) {
+                    if (k < o.ny) {
+                        if (ok0) __stcs(op + (size_t)k * o.row_stride, acc[k][0]);
+                        if (ok1) __stcs(op + (size_t)k * o.row_stride + 32, acc[k][1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TH; ++k)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            continue;
+        }
+        // the samples of a stage row whose left or right tap lands on my column: a run (tap columns are monotone in sx)
+        const int n_s = hdr.y;
+        int s0, ns;
         {
             bool hit = false;
-            if (lane < hdr.z) {
+            if (lane < n_s) {
                 const XEnt e = d->x[lane];
                 hit = e.pl == c || (e.pl == c - 1 && e.xl != 0.f);
             }
-            m = __ballot_sync(0xffffffffu, hit);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            s0 = m ? __ffs(m) - 1 : 0;
+            ns = __popc(m);
         }
-        if (m) {
+        if (ns > 0) {
             const int chb = FULL ? NV * 512 : hdr.w;
             const bool ok0 = FULL || lane * 16 < chb, ok1 = NV == 2 && (FULL || lane * 16 + 512 < chb);
-            const unsigned char *stage = stages + (size_t)s * STAGE_BYTES + lane * 16;
-            for (int r = 0; r < hdr.y; ++r) {
+            const unsigned char *stage = stages + (size_t)s * STAGE_BYTES + (size_t)s0 * chb + lane * 16;
+            for (int r = 0; r < hdr.z; ++r) {
                 const int2 rd = d->rowd[r];
-                const int x_off = (rd.x >> 8) & 0xff, n_s = (rd.x >> 16) & 0xff, soff = (rd.x >> 24) & 0x7f;
-                // my run of this row's samples (tap columns are monotone in the sample index, so the hits are a run)
-                const unsigned mr = (m >> x_off) & (n_s >= 32 ? 0xffffffffu : ((1u << n_s) - 1u));
-                if (!mr) continue;
-                const int s0 = __ffs(mr) - 1, ns = __popc(mr);
-                const int rel = (rd.x & 0xff) - 1;              // tile row of the top tap, -1 .. 7
+                const int rel = rd.x;                           // tile row of the top tap, -1 .. 7 (other values: no tap here)
                 const float yl = __int_as_float(rd.y);
                 const float wt = __fsub_rn(1.f, yl);
-                const unsigned char *rowp = stage + (size_t)(soff + s0) * chb;
-                const XEnt *xe = d->x + x_off + s0;
+                const unsigned char *rowp = stage + (size_t)r * n_s * chb;
+                const XEnt *xe = d->x + s0;
                 for (int k = ns; k > 0; --k, rowp += chb, ++xe) {
                     const XEnt e = *xe;
                     float4 g0, g1;
@@ -514,40 +505,16 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                 }
             }
         }
-        flags = hdr.x;
-        if (flags & ST_TILE_END) {
-            o = d->tile;
-            CH = hdr.w >> 2;
-        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
-        if (flags & ST_TILE_END) {
-            ++sc;
-            break;
-        }
-    }
-    // ---- end of tile: write the column exactly once (zeros included); the accumulators restart from zero above
-    {
-        const bool ok0 = FULL || lane * 4 < CH, ok1 = NV == 2 && (FULL || lane * 4 + 128 < CH);
-        if (c < o.nx) {
-            float4 *__restrict__ op = reinterpret_cast<float4 *>(o.out) + (size_t)c * o.pix_stride + lane;
-#pragma unroll
-            for (int k = 0; k < TH; ++k) {
-                if (k < o.ny) {
-                    if (ok0) __stcs(op + (size_t)k * o.row_stride, acc[k][0]);
-                    if (ok1) __stcs(op + (size_t)k * o.row_stride + 32, acc[k][1]);
-                }
-            }
-        }
-    }
-    if (flags & ST_EXIT) break;
     }
 }
 #undef SLN_TMA_ADD
 
+template <int STG_S, int NST>
 static size_t smem_bytes()
 {
-    return (size_t)NST * STAGE_BYTES + sizeof(StageDesc) * NST + sizeof(BwdLevel) * BWD_MAX_LEVELS +
+    return (size_t)NST * STG_S * CH_MAX * 4 + sizeof(StageDesc<STG_S>) * NST + sizeof(BwdLevel) * BWD_MAX_LEVELS +
            sizeof(uint64_t) * 2 * NST + 128;
 }
 

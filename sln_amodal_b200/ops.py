@@ -153,7 +153,7 @@ def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_ou
                                             LAYOUT_NHWC, flags, ptr(ws), ws.numel(), stream_ptr()),
               "sln_crop_and_resize_bwd")
     if out.numel():
-        _lib.count_launches(3 if N else 1)
+        _lib.count_launches(4 if N else 1)
     if not channels_last_out:
         out = to_contiguous_nchw(out)
     return out
@@ -182,7 +182,7 @@ def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last
         ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), grads.device)
         check(lib().sln_pyramid_crop_bwd(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), N, Cc, ph, pw, mp, hs, ws_, nl, B,
                                          flags, ptr(ws), ws.numel(), stream_ptr()), "sln_pyramid_crop_bwd")
-    _lib.count_launches(3 if N else 1)
+    _lib.count_launches(4 if N else 1)
     if channels_last_out is not None:
         outs = [o if cl else to_contiguous_nchw(o) for o, cl in zip(outs, channels_last_out)]
     return outs

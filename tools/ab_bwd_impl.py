@@ -40,17 +40,22 @@ for per in pers:
         bb = sum(bench.bwd_bytes(int((level_np == l).sum()), side, p) for l, side in enumerate(bench.LEVEL_SIDES))
         row = {"rois_per_img": per, "pool": p}
         outs = {}
-        for impl in ("2", "3"):
-            os.environ["SLN_BWD_IMPL"] = impl
+        for impl in ("2", "3") + tuple("3c%d" % k for k in range(2)):
+            os.environ["SLN_BWD_IMPL"] = impl[0]
+            os.environ.pop("SLN_BWD_CFG", None)
+            if len(impl) > 1:
+                os.environ["SLN_BWD_CFG"] = impl[2]
             for exact in (False, True):
                 outs[(impl, exact)] = ops.pyramid_crop_backward(g, boxes, ind, level, maps_shape, exact=exact)
             ms = timed(lambda: ops.pyramid_crop_backward(g, boxes, ind, level, maps_shape))
             row["ms_impl%s" % impl] = round(ms, 4)
             row["frac_impl%s" % impl] = round(bb / ms / 1e6 / peak, 3)
-        row["exact_bit_equal"] = all(torch.equal(a, b) for a, b in zip(outs[("2", True)], outs[("3", True)]))
+        row["exact_bit_equal"] = all(all(torch.equal(a, b) for a, b in zip(outs[("2", True)], outs[(k, True)]))
+                                     for k in ("3", "3c0", "3c1"))
         err = 0.0
-        for a, b, e in zip(outs[("2", False)], outs[("3", False)], outs[("2", True)]):
-            err = max(err, float((b - e).abs().max() / e.abs().max()), float((a - b).abs().max() / e.abs().max()))
+        for k in ("3", "3c0", "3c1"):
+            for b, e in zip(outs[(k, False)], outs[("2", True)]):
+                err = max(err, float((b - e).abs().max() / e.abs().max()))
         row["default_max_rel_err"] = err
         rows.append(row)
         print(row, flush=True)
