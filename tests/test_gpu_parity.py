@@ -624,6 +624,42 @@ def test_edt_bit_exact():
     assert np.all(ops.edt_sq_device(cuda(full)).cpu().numpy() == (9 + 12) ** 2)
 
 
+@pytest.mark.parametrize("L", [1, 2, 4])
+def test_edt_config4_planes_bit_exact(L):
+    """BASELINE config 4 on the 1024^2 path the bench times: the planes of the four distinct label maps of the bench
+    workload (20 instances, L visibility layers: 80 L planes) plus the hard shapes -- an all-foreground plane, a
+    full-height and a full-width blob (the longest envelope chains), a one-pixel hole, salt-and-pepper noise, stripes --
+    every one bit-exact against the oracle."""
+    from sln_amodal_b200 import ops
+    n_inst = 20
+    labels = np.stack([synth.label_map(1024, 1024, n=n_inst, seed=2024 + i) for i in range(4)])
+    planes, n_obj = ops.layer_decode_device(cuda(labels.view(np.int64)), L, n_inst)          # [4, 20, L, 1024, 1024]
+    rng = np.random.default_rng(40 + L)
+    hard = np.zeros((8, 1024, 1024), np.uint8)
+    hard[0] = 1                                             # all foreground: the (H + W)^2 sentinel
+    hard[1, :, 300:620] = 1                                 # full-height blob
+    hard[2, 200:777, :] = 1                                 # full-width blob
+    hard[3] = 1
+    hard[3, 511, 512] = 0                                   # one hole: distances up to the far corners
+    hard[4] = (rng.random((1024, 1024)) < 0.97).astype(np.uint8)
+    hard[5] = (rng.random((1024, 1024)) < 0.5).astype(np.uint8)
+    hard[6, :, ::37] = 1
+    hard[6, ::53, :] = 1                                    # thin stripes both ways
+    yy, xx = np.mgrid[0:1024, 0:1024]
+    hard[7] = (((yy - 500) / 480.0) ** 2 + ((xx - 530) / 470.0) ** 2 <= 1.0).astype(np.uint8)   # one huge ellipse
+    allp = torch.cat([planes.reshape(-1, 1024, 1024), cuda(hard)], 0).contiguous()
+    dist = ops.edt_sq_device(allp).cpu().numpy()
+    host = allp.cpu().numpy()
+    checked = 0
+    for i in range(host.shape[0]):
+        if i < host.shape[0] - 8 and not host[i].any():
+            assert not dist[i].any()                        # empty plane (object absent from that layer)
+            continue
+        assert np.array_equal(dist[i], oracle.edt_sq(host[i])), f"plane {i}"
+        checked += 1
+    assert checked >= 32
+
+
 def test_sem_dist_targets_end_to_end():
     from sln_amodal_b200 import sem_dist_targets
     labels = np.stack([synth.label_map(256, 256, n=8, seed=50 + i, min_piece=32) for i in range(2)])
@@ -671,6 +707,90 @@ def test_full_size_properties():
     d = ops.edt_sq_device(cuda(m)).cpu().numpy()
     assert np.array_equal(d == 0, m == 0)
     assert np.array_equal(d, oracle.edt_sq(m))
+
+
+def _ref_or_oracle():
+    """The reference's own C (oracle/_ref, compiled from /root/reference in place) when it travelled to this box, else the
+    restatement that tests/test_oracle_pin.py holds bit-identical to it."""
+    if oracle.ref_available():
+        return oracle.ref_crop_and_resize_fwd, oracle.ref_crop_and_resize_bwd, "reference C (oracle/_ref)"
+    return oracle.crop_and_resize_fwd, oracle.crop_and_resize_bwd, "oracle restatement"
+
+
+@pytest.mark.parametrize("pool", [7, 14, 16])
+def test_config2_full_size_values_vs_reference_c(pool):
+    """BASELINE config 2 at FULL size -- 8 images, C = 256, P2..P5 = 256^2 .. 32^2, 8 x 1000 ROIs assigned to levels by the
+    FPN formula -- compared VALUE BY VALUE with the reference's own crop_and_resize.c: forward bit-exact; backward (all
+    levels in one call, the bulk-async kernel) bit-exact in exact mode and within 1e-5 (north star) in the default mode."""
+    from sln_amodal_b200 import ops
+    ref_fwd, ref_bwd, _ = _ref_or_oracle()
+    B, C, per = 8, 256, 1000
+    sides = (256, 128, 64, 32)
+    n = B * per
+    boxes = synth.roi_boxes(n, seed=4321, outside_frac=0.05)
+    level = (synth.fpn_level(boxes) - 2).astype(np.int32)
+    ind = np.repeat(np.arange(B, dtype=np.int32), per)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + pool)
+    maps = [torch.randn((B, C, s, s), generator=gen) for s in sides]
+    tm = [m.to(dev()).contiguous(memory_format=torch.channels_last) for m in maps]
+    tb, ti, tl = cuda(boxes), cuda(ind), cuda(level)
+    got_f = ops.pyramid_crop_forward(tm, tb, ti, tl, pool, pool, 0.0).contiguous().cpu().numpy()
+    g = torch.randn((n, C, pool, pool), generator=gen)
+    gt = g.to(dev()).contiguous(memory_format=torch.channels_last)
+    sizes = [tuple(m.shape) for m in maps]
+    got_exact = [o.contiguous().cpu().numpy() for o in ops.pyramid_crop_backward(gt, tb, ti, tl, sizes, exact=True)]
+    got_fast = [o.contiguous().cpu().numpy() for o in ops.pyramid_crop_backward(gt, tb, ti, tl, sizes, exact=False)]
+    gn = g.numpy()
+    for l, m in enumerate(maps):
+        ix = np.nonzero(level == l)[0]
+        assert ix.size > 500                                       # every level is populated
+        want_f = ref_fwd(m.numpy(), boxes[ix], ind[ix], pool, pool, 0.0)
+        assert got_f[ix].tobytes() == want_f.tobytes(), f"forward differs on level {l}"
+        want_b = ref_bwd(np.ascontiguousarray(gn[ix]), boxes[ix], ind[ix], tuple(m.shape))
+        assert got_exact[l].tobytes() == want_b.tobytes(), f"exact backward differs on level {l}"
+        assert_close_rel(got_fast[l], want_b)
+        assert_close_rel(got_fast[l], want_b, rtol=2e-6)
+
+
+def test_config2_contention_4000_rois_per_image_vs_reference_c():
+    """The 4000-ROIs-per-image contention case: every ROI of an image inside one small window of a 64^2 map, so a few
+    hundred pixels each collect thousands of terms.  Values against the reference's crop_and_resize.c."""
+    from sln_amodal_b200 import ops
+    _, ref_bwd, _ = _ref_or_oracle()
+    B, C, H, per, pool = 2, 256, 64, 4000, 14
+    n = B * per
+    boxes = synth.roi_boxes(n, seed=99, window=(0.5, 0.5, 0.06))
+    ind = np.repeat(np.arange(B, dtype=np.int32), per)
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    g = torch.randn((n, C, pool, pool), generator=gen)
+    want = ref_bwd(g.numpy(), boxes, ind, (B, C, H, H))
+    gt = g.to(dev()).contiguous(memory_format=torch.channels_last)
+    got = ops.crop_and_resize_backward(gt, cuda(boxes), cuda(ind), (B, C, H, H), exact=True).contiguous().cpu().numpy()
+    assert got.tobytes() == want.tobytes()
+    got = ops.crop_and_resize_backward(gt, cuda(boxes), cuda(ind), (B, C, H, H), exact=False).contiguous().cpu().numpy()
+    assert_close_rel(got, want)
+
+
+@pytest.mark.parametrize("impl", ["0", "1", "3"])
+def test_backward_kernel_forms_agree(impl, monkeypatch):
+    """The three backward forms (strip, tile owner, bulk-async; SLN_BWD_IMPL) produce the same bits in exact mode,
+    also for flipped / degenerate boxes, ragged maps and crops that need several stages per sample row."""
+    from sln_amodal_b200 import ops
+    rng = np.random.default_rng(5)
+    for C, H, W, N, ph, pw in ((256, 40, 40, 200, 7, 7), (128, 50, 70, 150, 32, 32), (68, 21, 37, 120, 9, 20), (512, 24, 24, 60, 14, 14)):
+        B = 2
+        boxes = synth.roi_boxes(N, seed=N, outside_frac=0.2, degenerate_frac=0.1)
+        boxes[::7] = boxes[::7][:, [2, 1, 0, 3]]                   # y-flipped
+        boxes[::11] = boxes[::11][:, [0, 3, 2, 1]]                 # x-flipped
+        ind = rng.integers(0, B, N).astype(np.int32)
+        g = rng.standard_normal((N, C, ph, pw), dtype=np.float32)
+        want = oracle.crop_and_resize_bwd(g, boxes, ind, (B, C, H, W))
+        monkeypatch.setenv("SLN_BWD_IMPL", impl)
+        gt = cuda(g).contiguous(memory_format=torch.channels_last)
+        got = ops.crop_and_resize_backward(gt, cuda(boxes), cuda(ind), (B, C, H, W), exact=True).contiguous().cpu().numpy()
+        assert got.tobytes() == want.tobytes(), (impl, C, H, W, ph, pw)
+        got = ops.crop_and_resize_backward(gt, cuda(boxes), cuda(ind), (B, C, H, W), exact=False).contiguous().cpu().numpy()
+        assert_close_rel(got, want, rtol=2e-6)
 
 
 # --------------------------------------------------------------------------- SURVEY 8(f)-2: extract_bboxes
