@@ -375,6 +375,18 @@ def run_ours(args):
     # ---- config 1 on every rank: images/s of the detection-head path over rank-sharded images (BASELINE metric 3)
     images = head_throughput(dev, rank, world, barrier, sdist)
 
+    # ---- config 5 on every rank: the full training step, data-parallel with DDP all-reduce (tools/train_step.py)
+    train = None
+    if os.environ.get("SLN_BENCH_TRAIN", "1") != "0":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_step
+            torch.cuda.empty_cache()
+            train = train_step.run(dev, rank, world, steps=2, warmup=1)
+        except Exception as e:                               # the harness is outside the hot path: never lose the headline to it
+            train = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+
     # ---- the rest of the config-2 sweep (rank 0): 16x16, and 4000 ROIs per image, same maps
     sweep = []
     if rank == 0:
@@ -425,7 +437,9 @@ def run_ours(args):
                 "proposal_layer_us": extra.get("proposal_layer", {}).get("us_median"),
                 "edt_frac": extra.get("edt", {}).get("frac"), "edt_us_320_maps": extra.get("edt", {}).get("us_median"),
                 "layer_decode_frac": extra.get("layer_decode", {}).get("frac"),
-                "images_per_s": images["images_per_s"], "images_per_s_e2e": images["e2e"]["images_per_s"]}
+                "images_per_s": images["images_per_s"], "images_per_s_e2e": images["e2e"]["images_per_s"],
+                "train_step_images_per_s": (train or {}).get("images_per_s"),
+                "train_step_allreduce_share": (train or {}).get("allreduce_share")}
         roofline["also_measured"] = also
         line = {
             "metric": "roialign_fwd_bwd_roi_crops_per_s", "value": round(value, 1), "unit": "roi_crops/s",
@@ -440,6 +454,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kernels],
             "images": images,
+            "train_step": train,
             "extra": extra,
         }
         sys.stdout.flush()
