@@ -423,6 +423,15 @@ def run_ours(args):
         extra["unmold"] = unmold_metric(dev, peak, cpu=(world == 1))
         extra["rpn_pack"] = rpn_pack_metric(dev, peak, cpu=(world == 1))
         extra["resize_image"] = resize_image_metric(dev, cpu=(world == 1))
+        try:
+            extra["nchw_dropin"] = nchw_dropin_metric(dev, maps, boxes, box_ind, level, peak)
+        except Exception as e:
+            extra["nchw_dropin"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if world == 1:
+            try:
+                extra["ref_cuda"] = ref_cuda_metric(dev, maps, boxes_np, ind_np, level_np)
+            except Exception as e:
+                extra["ref_cuda"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1:
             cpu_baseline = cpu_reference_sample(boxes_np, ind_np, level_np, maps)
 
@@ -438,6 +447,7 @@ def run_ours(args):
                 "edt_frac": extra.get("edt", {}).get("frac"), "edt_us_320_maps": extra.get("edt", {}).get("us_median"),
                 "layer_decode_frac": extra.get("layer_decode", {}).get("frac"),
                 "images_per_s": images["images_per_s"], "images_per_s_e2e": images["e2e"]["images_per_s"],
+                "ref_cuda_sm100a": extra.get("ref_cuda"), "nchw_dropin": extra.get("nchw_dropin"),
                 "train_step_images_per_s": (train or {}).get("images_per_s"),
                 "train_step_allreduce_share": (train or {}).get("allreduce_share")}
         roofline["also_measured"] = also
@@ -535,6 +545,145 @@ def head_throughput(dev, rank, world, barrier, sdist, n_img=32):
            "timing": "CUDA events on the launching stream, barrier on both sides, max over ranks"}
     del host, devs
     torch.cuda.empty_cache()
+    return res
+
+
+def nchw_dropin_metric(dev, maps, boxes, box_ind, level, peak):
+    """What the UNMODIFIED reference pays: its tensors are NCHW (cuDNN's default), so every map is transposed to
+    channels_last once per forward pass (remembered across the crop calls that share it), crops come back channels_last,
+    and the backward converts the incoming NCHW gradient and returns NCHW gradient maps (two more transposes).  Same
+    config-2 inputs as the headline; `first` = with the map transposes, `cached` = later calls on the same maps."""
+    import torch
+    from sln_amodal_b200 import ops
+
+    def ev_ms(fn, reps=5):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    sizes = [tuple(m.shape) for m in maps]
+    rows = []
+    for p in POOLS:
+        def fresh():
+            return [m.contiguous(memory_format=torch.contiguous_format).clone() for m in maps]
+        # first call on new NCHW tensors: includes the four map transposes
+        ts = []
+        for _ in range(3):
+            nchw = fresh()
+            ts.append(ev_ms(lambda: ops.pyramid_crop_forward(nchw, boxes, box_ind, level, p, p, 0.0), reps=1))
+        nchw = fresh()
+        ops.pyramid_crop_forward(nchw, boxes, box_ind, level, p, p, 0.0)
+        cached = ev_ms(lambda: ops.pyramid_crop_forward(nchw, boxes, box_ind, level, p, p, 0.0))
+        nhwc = ev_ms(lambda: ops.pyramid_crop_forward(maps, boxes, box_ind, level, p, p, 0.0))
+        g_nchw = torch.randn((boxes.shape[0], CHANNELS, p, p), device=dev)
+        g_nhwc = g_nchw.contiguous(memory_format=torch.channels_last)
+        b_nchw = ev_ms(lambda: ops.pyramid_crop_backward(g_nchw, boxes, box_ind, level, sizes, channels_last_out=[False] * 4))
+        b_nhwc = ev_ms(lambda: ops.pyramid_crop_backward(g_nhwc, boxes, box_ind, level, sizes))
+        rows.append({"pool": p, "fwd_ms_nhwc": round(nhwc, 4), "fwd_ms_nchw_first": round(float(np.median(ts)), 4),
+                     "fwd_ms_nchw_cached": round(cached, 4), "bwd_ms_nhwc": round(b_nhwc, 4), "bwd_ms_nchw": round(b_nchw, 4),
+                     "fwd_bwd_ratio_nchw_over_nhwc": round((float(np.median(ts)) + b_nchw) / (nhwc + b_nhwc), 3)})
+        del g_nchw, g_nhwc, nchw
+    return {"what": "config 2 with NCHW tensors in and out (the unmodified reference's layout)", "rows": rows,
+            "note": "model.to(memory_format=torch.channels_last) -- install(channels_last_model=...) -- removes the transposes"}
+
+
+def ref_cuda_metric(dev, maps, boxes_np, ind_np, level_np):
+    """Speed-only comparator: the reference's own CUDA kernels, unmodified, recompiled for sm_100a
+    (oracle/_ref/libref_cuda.so), on the same config-2 inputs -- per FPN level like modals.py:70-97 drives them, NCHW maps,
+    with the memsets the reference's host code issues (crop_and_resize_gpu.c:25, :57) -- and the reference's GPU NMS
+    (nms_kernel.cu bit matrix + the blocking D2H copy + the host scan of nms_cuda.c:33-58) at 12k boxes.  torchvision's
+    roi_align / nms ride along as a second, stock point.  None of this is a parity check."""
+    import torch
+    from oracle import oracle
+    if not oracle.ref_cuda_available():
+        return {"unavailable": "oracle/_ref/libref_cuda.so was not built (needs nvcc and the reference checkout at build time)"}
+
+    def ev_ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    st = torch.cuda.current_stream().cuda_stream
+    res = {"what": "reference CUDA kernels (unmodified, sm_100a) on the config-2 inputs, per FPN level, NCHW", "crop": []}
+    nchw = [m.contiguous(memory_format=torch.contiguous_format) for m in maps]
+    lv = [np.nonzero(level_np == l)[0] for l in range(4)]
+    bx = [torch.from_numpy(boxes_np[ix]).to(dev) for ix in lv]
+    bi = [torch.from_numpy(ind_np[ix]).to(dev) for ix in lv]
+    for p in (7, 14):
+        outs = [torch.empty((len(ix), CHANNELS, p, p), device=dev) for ix in lv]
+        gin = [torch.randn((len(ix), CHANNELS, p, p), device=dev) for ix in lv]
+        gout = [torch.empty_like(m) for m in nchw]
+
+        def fwd():
+            for l in range(4):
+                outs[l].zero_()
+                oracle.ref_cuda_crop_fwd(nchw[l].data_ptr(), bx[l].data_ptr(), bi[l].data_ptr(), len(lv[l]), IMAGES_PER_GPU,
+                                         LEVEL_SIDES[l], LEVEL_SIDES[l], p, p, CHANNELS, 0.0, outs[l].data_ptr(), st)
+
+        def bwd():
+            for l in range(4):
+                gout[l].zero_()
+                oracle.ref_cuda_crop_bwd(gin[l].data_ptr(), bx[l].data_ptr(), bi[l].data_ptr(), len(lv[l]), IMAGES_PER_GPU,
+                                         LEVEL_SIDES[l], LEVEL_SIDES[l], p, p, CHANNELS, gout[l].data_ptr(), st)
+        row = {"pool": p, "fwd_ms": round(ev_ms(fwd), 4), "bwd_ms": round(ev_ms(bwd), 4)}
+        try:
+            from torchvision.ops import roi_align
+            rois = [torch.cat([bi[l].float().unsqueeze(1), bx[l][:, [1, 0, 3, 2]] * (LEVEL_SIDES[l] - 1)], 1) for l in range(4)]
+            row["torchvision_roi_align_fwd_ms"] = round(ev_ms(lambda: [roi_align(nchw[l], rois[l], (p, p), 1.0, 1, True) for l in range(4)]), 4)
+        except Exception as e:
+            row["torchvision_roi_align_fwd_ms"] = "unavailable: %s" % type(e).__name__
+        res["crop"].append(row)
+        del outs, gin, gout
+    # NMS at 12k RPN-like boxes, thresh 0.7: the reference GPU path wants boxes sorted by score (nms_kernel.cu:16-24 reads
+    # x1,y1,x2,y2,score rows)
+    n = 12000
+    d_np = np.concatenate([synth.nms_boxes(n, seed=7, kind="rpn"), synth.nms_scores(n, seed=8)[:, None]], 1).astype(np.float32)
+    d_np = d_np[np.argsort(-d_np[:, 4], kind="stable")]
+    dets = torch.from_numpy(d_np).to(dev)
+    col = (n + 63) // 64
+    mask = torch.empty((n, col), dtype=torch.int64, device=dev)
+    h_mask = torch.empty((n, col), dtype=torch.int64).pin_memory()
+    torch.cuda.synchronize()
+
+    def ref_nms():
+        oracle.ref_cuda_nms_mask(n, dets.data_ptr(), mask.data_ptr(), 0.7)       # default stream, like nms_kernel.cu:79
+        h_mask.copy_(mask)                                                      # blocking D2H (nms_cuda.c:30-33)
+        torch.cuda.synchronize()
+        return oracle.nms_mask_scan(h_mask.numpy().view(np.uint64))
+    ref_nms()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        keep = ref_nms()
+        ts.append(time.perf_counter() - t0)
+    res["nms_12k_rpn"] = {"us_wall_incl_d2h_and_host_scan": round(float(np.median(ts)) * 1e6, 1), "kept": int(keep.size),
+                          "mask_bytes": int(n * col * 8)}
+    try:
+        from torchvision.ops import nms as tv_nms
+        b_xyxy = dets[:, [1, 0, 3, 2]].contiguous()
+        sc = dets[:, 4].contiguous()
+        tv_nms(b_xyxy, sc, 0.7)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            k2 = tv_nms(b_xyxy, sc, 0.7)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        res["nms_12k_rpn"]["torchvision_nms_us_wall"] = round(float(np.median(ts)) * 1e6, 1)
+    except Exception as e:
+        res["nms_12k_rpn"]["torchvision_nms_us_wall"] = "unavailable: %s" % type(e).__name__
     return res
 
 

@@ -30,6 +30,7 @@ _ORC_SO = os.path.join(_HERE, "_build", "libsln_oracle.so")
 _REF_CROP_SO = os.path.join(_HERE, "_ref", "libref_crop.so")
 _REF_NMS_SO = os.path.join(_HERE, "_ref", "libref_nms.so")
 _REF_MASK_SO = os.path.join(_HERE, "_ref", "libref_mask.so")
+_REF_CUDA_SO = os.path.join(_HERE, "_ref", "libref_cuda.so")
 
 
 def build(quiet: bool = True) -> None:
@@ -65,6 +66,7 @@ def _lib():
         lib.orc_layer_decode.restype = C.c_int
         lib.orc_edt_sq.restype = None
         lib.orc_edt_sq_banded.restype = None
+        lib.orc_nms_mask_scan.restype = C.c_long
         _orc = lib
     return _orc
 
@@ -843,3 +845,53 @@ def resize_image_pil(image, out_hw):
     mode = "L" if a.ndim == 2 else {3: "RGB", 4: "RGBA"}[a.shape[2]]
     im = Image.frombytes(mode, (a.shape[1], a.shape[0]), a.tobytes())
     return np.asarray(im.resize((int(out_hw[1]), int(out_hw[0])), resample=Image.BILINEAR), dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------
+# Speed-only comparator: the reference's CUDA kernels, unmodified, recompiled for sm_100a (oracle/_ref/libref_cuda.so;
+# BASELINE.md section 4).  NOT a parity oracle (FMA contraction, `>` instead of `>=`, atomicAdd order).  The callers pass
+# raw device pointers (torch tensors' data_ptr()); nothing here touches the product path.
+# ---------------------------------------------------------------------------
+_ref_cuda = None
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(_REF_CUDA_SO)
+
+
+def _ref_cuda_lib():
+    global _ref_cuda
+    if _ref_cuda is None:
+        _ref_cuda = C.CDLL(_REF_CUDA_SO)
+        _ref_cuda.CropAndResizeLaucher.restype = None
+        _ref_cuda.CropAndResizeBackpropImageLaucher.restype = None
+        _ref_cuda._nms.restype = None
+    return _ref_cuda
+
+
+def ref_cuda_crop_fwd(image_ptr, boxes_ptr, ind_ptr, n, B, H, W, ph, pw, depth, ext, crops_ptr, stream=0):
+    """CropAndResizeLaucher (cuda/crop_and_resize_kernel.cu:166-192): NCHW image, crops [n, depth, ph, pw]."""
+    _ref_cuda_lib().CropAndResizeLaucher(C.c_void_p(image_ptr), C.c_void_p(boxes_ptr), C.c_void_p(ind_ptr), C.c_int(n), C.c_int(B),
+                                         C.c_int(H), C.c_int(W), C.c_int(ph), C.c_int(pw), C.c_int(depth), C.c_float(ext),
+                                         C.c_void_p(crops_ptr), C.c_void_p(stream))
+
+
+def ref_cuda_crop_bwd(grads_ptr, boxes_ptr, ind_ptr, n, B, H, W, ph, pw, depth, grads_image_ptr, stream=0):
+    """CropAndResizeBackpropImageLaucher (crop_and_resize_kernel.cu:195-220): atomicAdd scatter into a ZEROED image."""
+    _ref_cuda_lib().CropAndResizeBackpropImageLaucher(C.c_void_p(grads_ptr), C.c_void_p(boxes_ptr), C.c_void_p(ind_ptr), C.c_int(n),
+                                                      C.c_int(B), C.c_int(H), C.c_int(W), C.c_int(ph), C.c_int(pw), C.c_int(depth),
+                                                      C.c_void_p(grads_image_ptr), C.c_void_p(stream))
+
+
+def ref_cuda_nms_mask(n, boxes_ptr, mask_ptr, thresh):
+    """_nms (cuda/nms_kernel.cu:73-84): the n x ceil(n/64) IoU bit matrix of boxes sorted by score, default stream."""
+    _ref_cuda_lib()._nms(C.c_int(n), C.c_void_p(boxes_ptr), C.c_void_p(mask_ptr), C.c_float(thresh))
+
+
+def nms_mask_scan(mask):
+    """Host scan of the bit matrix (restatement of nms_cuda.c:33-58): positions of the survivors in the sorted order."""
+    mask = np.ascontiguousarray(mask, np.uint64)
+    n = mask.shape[0]
+    keep = np.empty(n, np.int64)
+    k = _lib().orc_nms_mask_scan(mask.ctypes.data_as(C.c_void_p), C.c_int(n), keep.ctypes.data_as(C.c_void_p))
+    return keep[:k]

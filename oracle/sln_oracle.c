@@ -347,3 +347,26 @@ int orc_layer_decode(const uint64_t *label, int H, int W, int L, int n_max,
     }
     return n_obj;
 }
+
+/* ---------------------------------------------------------------------------
+ * Host scan over the 64x64-tile IoU bit matrix of the reference's GPU NMS: restatement of nms_cuda.c:33-58 (which
+ * needs THC and cannot be compiled here).  mask [n][ceil(n/64)] u64 as written by nms_kernel.cu:26-70; keep receives
+ * the positions (in the sorted order the kernel was given) of the survivors; returns their count.  Used by the
+ * speed-only comparator of the reference's CUDA path (bench.py extra.ref_cuda).
+ * ------------------------------------------------------------------------- */
+long orc_nms_mask_scan(const unsigned long long *mask, int n, long long *keep)
+{
+    const int col_blocks = (n + 63) / 64;
+    unsigned long long *remv = (unsigned long long *)calloc((size_t)col_blocks, sizeof(unsigned long long));
+    long num = 0;
+    for (int i = 0; i < n; i++) {
+        const int nblock = i / 64, inblock = i % 64;
+        if (!(remv[nblock] & (1ULL << inblock))) {
+            keep[num++] = i;
+            const unsigned long long *p = mask + (size_t)i * col_blocks;
+            for (int j = nblock; j < col_blocks; j++) remv[j] |= p[j];
+        }
+    }
+    free(remv);
+    return num;
+}

@@ -138,6 +138,39 @@ def test_crop_backward_deterministic():
             assert torch.equal(a, b)
 
 
+def test_nchw_maps_take_the_nhwc_kernel_through_a_remembered_copy():
+    """NCHW images with >= 32 channels (what the unmodified reference passes) are transposed once and the copy is
+    remembered while the tensor lives: the result must track in-place updates, views of the same storage, and a new
+    tensor that reuses the address of a dead one."""
+    import gc
+    from sln_amodal_b200 import ops
+    img, boxes, ind = _crop_inputs(77, 2, 64, 40, 48, 120, outside_frac=0.1)
+    tb, ti = cuda(boxes), cuda(ind)
+    t = cuda(img)
+    assert t.is_contiguous()
+    for _ in range(2):                                              # second call: served from the remembered copy
+        got = ops.crop_and_resize_forward(t, tb, ti, 7, 7)
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        assert got.contiguous().cpu().numpy().tobytes() == oracle.crop_and_resize_fwd(img, boxes, ind, 7, 7).tobytes()
+    t.mul_(2.0)                                                     # in-place update bumps the version counter
+    got = ops.crop_and_resize_forward(t, tb, ti, 7, 7)
+    assert got.contiguous().cpu().numpy().tobytes() == oracle.crop_and_resize_fwd(img * 2, boxes, ind, 7, 7).tobytes()
+    v = t[1:2]                                                      # a view of the same storage (other offset / shape)
+    got = ops.crop_and_resize_forward(v, tb, torch.zeros_like(ti), 5, 5)
+    want = oracle.crop_and_resize_fwd(img[1:2] * 2, boxes, np.zeros_like(ind), 5, 5)
+    assert got.contiguous().cpu().numpy().tobytes() == want.tobytes()
+    sq = t[0].unsqueeze(0)                                          # the reference's squeeze(0) / unsqueeze(0) dance
+    got = ops.crop_and_resize_forward(sq, tb, torch.zeros_like(ti), 5, 5)
+    assert got.contiguous().cpu().numpy().tobytes() == oracle.crop_and_resize_fwd(img[0:1] * 2, boxes, np.zeros_like(ind), 5, 5).tobytes()
+    ptr0 = t.data_ptr()
+    del t, v, sq, got
+    gc.collect()
+    img2 = np.random.default_rng(5).standard_normal(img.shape, dtype=np.float32)
+    t2 = cuda(img2)                                                 # usually lands on the freed block
+    got = ops.crop_and_resize_forward(t2, tb, ti, 7, 7)
+    assert got.contiguous().cpu().numpy().tobytes() == oracle.crop_and_resize_fwd(img2, boxes, ind, 7, 7).tobytes(), (ptr0 == t2.data_ptr())
+
+
 def test_autograd_function_api():
     from roialign.roi_align.crop_and_resize import CropAndResizeFunction, CropAndResize
     img, boxes, ind = _crop_inputs(9, 2, 16, 24, 24, 30)
