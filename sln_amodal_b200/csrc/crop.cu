@@ -989,6 +989,8 @@ crop_bwd_tile_kernel(const float *__restrict__ grads, const Tap *__restrict__ ta
 // ===========================================================================
 // layout converters: per image, [C][HW] <-> [HW][C]
 // ===========================================================================
+static bool aligned16_ptr(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols)
 {
@@ -1008,9 +1010,48 @@ transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int row
     }
 }
 
+// Vector form for rows % 4 == 0, cols % 4 == 0 and 16-byte aligned pointers (every FPN map and crop tensor): a 64 x 64
+// tile per CTA, 16-byte loads along the source rows, 16-byte stores along the destination rows.  The tile is stored
+// transposed with a 65-word pitch, so the four scalar writes of a loaded vector hit four different rows (banks 4 apart
+// plus the lane's own offset: conflict-free per quarter warp) and the 16-byte reads along a row are contiguous.
+__global__ void __launch_bounds__(256)
+transpose_v4_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols)
+{
+    __shared__ float tile[64][65];                              // tile[c][r] = src[r0 + r][c0 + c]
+    const size_t boff = (size_t)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int q = threadIdx.x & 15, j0 = threadIdx.x >> 4;      // 16 vectors per 64-float row, 16 rows per pass
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + j0 + 16 * k, c = c0 + 4 * q;
+        if (r < rows && c < cols) {
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + boff + (size_t)r * cols + c));
+            tile[4 * q + 0][j0 + 16 * k] = v.x;
+            tile[4 * q + 1][j0 + 16 * k] = v.y;
+            tile[4 * q + 2][j0 + 16 * k] = v.z;
+            tile[4 * q + 3][j0 + 16 * k] = v.w;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + j0 + 16 * k, r = r0 + 4 * q;          // destination row c, columns r .. r + 3
+        if (c < cols && r < rows) {
+            const float *t = &tile[j0 + 16 * k][4 * q];
+            __stcs(reinterpret_cast<float4 *>(dst + boff + (size_t)c * rows + r), make_float4(t[0], t[1], t[2], t[3]));
+        }
+    }
+}
+
 static int launch_transpose(const float *src, float *dst, int batch, int rows, int cols, cudaStream_t st)
 {
     if (batch == 0 || rows == 0 || cols == 0) return SLN_OK;
+    if (rows % 4 == 0 && cols % 4 == 0 && aligned16_ptr(src) && aligned16_ptr(dst) && batch <= 65535 && cdiv(rows, 64) <= 65535) {
+        dim3 grid(cdiv(cols, 64), cdiv(rows, 64), batch);
+        transpose_v4_kernel<<<grid, 256, 0, st>>>(src, dst, rows, cols);
+        SLN_LAUNCH_OK("transpose_v4_kernel");
+        return SLN_OK;
+    }
     SLN_REQUIRE(cdiv(rows, 32) <= 65535 && batch <= 65535, SLN_ERR_ARG,
                 "transpose: rows/batch too large (%d, %d)", rows, batch);
     dim3 grid(cdiv(cols, 32), cdiv(rows, 32), batch);

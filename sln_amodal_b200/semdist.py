@@ -15,7 +15,11 @@ from . import ops
 
 def _as_label_tensor(label, device):
     if isinstance(label, np.ndarray):
+        if label.dtype.itemsize != 8 or label.dtype.kind not in "ui":
+            raise TypeError("layer label maps are 64-bit integers (uint64 on disk, Functions.py:1012-1095), got %s" % label.dtype)
         label = torch.from_numpy(np.ascontiguousarray(label).view(np.int64))
+    elif label.dtype != torch.int64:
+        raise TypeError("layer label tensors must be int64 (the bits of the uint64 map), got %s" % label.dtype)
     return label.to(device)
 
 
@@ -36,7 +40,11 @@ def load_layer2(dataset, image_id, config):
     planes, n_obj = decode_layers(layer, config.NUM_CLASSES, n_max=32)
     n = int(n_obj[0].item())
     if n == 0:
-        return super(type(dataset), dataset).load_mask(image_id)
+        # the reference calls super(AmodalDataset, self).load_mask (amodal_train.py:268-270): the empty mask of utils.Dataset.
+        # install() binds this function onto AmodalDataset, so "the class that owns load_layer2" is found in the MRO --
+        # for an instance of a SUBCLASS, super(type(dataset), ...) would land on AmodalDataset.load_mask instead.
+        owner = next((k for k in type(dataset).__mro__ if "load_layer2" in k.__dict__), type(dataset))
+        return super(owner, dataset).load_mask(image_id)
     mask_layers = planes[0, :n].permute(2, 3, 1, 0).contiguous().cpu().numpy().astype(bool)
     return mask_layers, np.ones(n, dtype=np.int32)
 

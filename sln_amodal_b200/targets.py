@@ -148,6 +148,13 @@ def build_rpn_targets(image_shape, anchors, gt_class_ids, gt_boxes, config, devi
         no_crowd_bool = crowd_iou_max < 0.001
     else:
         no_crowd_bool = np.ones([A], dtype=bool)
+    if gt_boxes.shape[0] == 0:
+        # the reference fails here too: np.argmax over the empty axis of the [A, 0] overlap matrix (Functions.py:786)
+        raise ValueError("build_rpn_targets: no non-crowd GT box left (attempt to get argmax of an empty sequence)")
+    if anchors.dtype != np.float64:
+        # the reference computes the IoU in the anchors' dtype; the device reductions are float64 (what the reference's
+        # generate_pyramid_anchors produces), so narrower anchors would no longer be bit-identical
+        raise TypeError("build_rpn_targets: float64 anchors expected (utils.generate_pyramid_anchors), got %s" % anchors.dtype)
     mx, am, ga = ops.rpn_overlap_reductions_device(d_anchors, torch.from_numpy(np.ascontiguousarray(gt_boxes, dtype=np.float64)))
     anchor_iou_max, anchor_iou_argmax, gt_iou_argmax = mx.cpu().numpy(), am.cpu().numpy(), ga.cpu().numpy()
     # matching rules (:789-795): negatives first, then one anchor per GT box whatever its IoU, then every anchor >= 0.7
@@ -253,11 +260,15 @@ def resize_image_device(image, out_hw):
     return out
 
 
-def resize_image(image, min_dim=None, max_dim=None, padding=False):
+def resize_image(image, min_dim=None, max_dim=None, padding=False, device=False):
     """Drop-in for utils.resize_image (utils.py:301-356): the reference squashes every image to (max_dim, max_dim) with
-    scipy.misc.imresize and returns (image, window, scale, padding).  The image comes back as a CUDA u8 tensor."""
+    scipy.misc.imresize -- min_dim and padding are ignored by its body too -- and returns (image, window, scale, padding).
+    The image comes back as a numpy uint8 array like the reference's (callers do image.astype(np.float32), model.py
+    mold_inputs); device=True keeps it a CUDA u8 tensor.  uint8 input only (imresize would bytescale anything else)."""
     h, w = image.shape[:2]
     out = resize_image_device(image, (max_dim, max_dim))
+    if not device:
+        out = out.cpu().numpy()
     window = (0, 0, max_dim, max_dim)
     scale = (max_dim / h, max_dim / w)
     return out, window, scale, [(0, 0), (0, 0), (0, 0)]

@@ -38,13 +38,19 @@ def unmold_masks(masks, boxes, image_shape):
     return out
 
 
-def unmold_mask(mask, bbox, image_shape):
-    """utils.py:447-465: one small float mask -> binary full-image mask (u8 [H, W], CUDA tensor)."""
+def unmold_mask(mask, bbox, image_shape, device=False):
+    """utils.py:447-465: one small float mask -> binary full-image mask, numpy u8 [H, W] like the reference's (callers
+    np.stack the results, model.py:794-800); device=True keeps the CUDA tensor.  Like the reference, the box must lie
+    inside the image with positive height and width (there the paste raises a shape mismatch; here it is an error too)."""
     m = torch.as_tensor(mask, dtype=torch.float32)
     m = m.reshape([s for s in m.shape if s != 1] or [1, 1])               # mask.squeeze()
     if m.dim() != 2:
         raise _lib.SlnError("unmold_mask: a [height, width] mask expected")
-    return unmold_masks(m[None], np.asarray([[int(v) for v in bbox]], np.int32), image_shape)[0]
+    y1, x1, y2, x2 = (int(v) for v in bbox)
+    if not (0 <= y1 < y2 <= int(image_shape[0]) and 0 <= x1 < x2 <= int(image_shape[1])):
+        raise ValueError("unmold_mask: box %s is not inside the %dx%d image" % ((y1, x1, y2, x2), image_shape[0], image_shape[1]))
+    out = unmold_masks(m[None], np.asarray([[y1, x1, y2, x2]], np.int32), image_shape)[0]
+    return out if device else out.cpu().numpy()
 
 
 def unmold_detections(detections, mrcnn_mask, image_shape, window, return_device_planes=False):
@@ -71,7 +77,12 @@ def unmold_detections(detections, mrcnn_mask, image_shape, window, return_device
     scales = np.array([h_scale, w_scale, h_scale, w_scale])
     shifts = np.array([shift[0], shift[1], shift[0], shift[1]])
     boxes = np.multiply(boxes - shifts, scales).astype(np.int32)
-    keep = np.where((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]) > 0)[0]
+    # model.py:789-793 drops zero-area boxes (the product test also passes boxes with NEGATIVE height and width); a box
+    # that rounding pushed past the image border or turned inside out makes the reference's paste raise -- here such a
+    # detection is dropped together with its score and class, so boxes, scores and masks stay consistent
+    H_, W_ = int(image_shape[0]), int(image_shape[1])
+    keep = np.where(((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]) > 0) & (boxes[:, 2] > boxes[:, 0]) &
+                    (boxes[:, 0] >= 0) & (boxes[:, 1] >= 0) & (boxes[:, 2] <= H_) & (boxes[:, 3] <= W_))[0]
     if keep.shape[0] != N:
         boxes, class_ids, scores = boxes[keep], class_ids[keep], scores[keep]
         masks = masks[torch.as_tensor(keep, device=masks.device)] if isinstance(masks, torch.Tensor) else masks[keep]

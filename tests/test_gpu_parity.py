@@ -580,6 +580,36 @@ def test_refine_detections_without_nms_matches_oracle(n, K, bg_frac):
     assert det.cpu().numpy().tobytes() == want_det.tobytes()
 
 
+def test_nms_at_exactly_the_threshold_follows_the_cpu_extension():
+    """The reference's two NMS builds disagree at IoU == thresh: cpu_nms suppresses (`ovr >= thresh`, nms.c:58-61), the CUDA
+    kernel keeps (`> thresh`, nms_kernel.cu:63).  This library implements the CPU extension's rule -- the oracle the north
+    star names -- on CUDA tensors too.  Rounded pixel boxes (refine_detections, Functions.py:485) hit the case exactly:
+    10x10 boxes (the +1 convention) shifted by 5 columns overlap with IoU 50 / 150 = 1/3, exactly representable ratios
+    are rarer, so thresholds are taken from the computed float."""
+    from sln_amodal_b200 import nms
+    a = np.array([[0, 0, 9, 9, 0.9], [0, 5, 9, 14, 0.8], [50, 50, 59, 59, 0.7]], np.float32)
+    iou = np.float32(np.float32(50.0) / np.float32(100.0 + 100.0 - 50.0))
+    keep_at = nms(cuda(a), float(iou)).cpu().numpy()
+    assert np.array_equal(keep_at, oracle.nms(a, float(iou))) and np.array_equal(keep_at, [0, 2])      # suppressed at equality
+    above = float(np.nextafter(iou, np.float32(1.0)))
+    keep_above = nms(cuda(a), above).cpu().numpy()
+    assert np.array_equal(keep_above, oracle.nms(a, above)) and np.array_equal(keep_above, [0, 1, 2])
+
+
+def test_unmold_detections_drops_boxes_the_reference_cannot_paste():
+    """A detection whose box leaves the image after the window transform (or is turned inside out) makes the reference's
+    paste raise; here it is dropped with its class and score, so the four outputs stay consistent."""
+    from sln_amodal_b200 import unmold
+    rng = np.random.default_rng(2)
+    det = np.array([[10, 10, 60, 70, 1, 0.9], [90, 20, 130, 60, 1, 0.8], [70, 60, 40, 20, 1, 0.7], [5, 5, 50, 50, 1, 0.6]], np.float32)
+    masks = rng.random((4, 28, 28, 2)).astype(np.float32)
+    boxes, class_ids, scores, planes = unmold.unmold_detections(det, masks, (128, 128, 3), (0, 0, 128, 128))
+    assert boxes.tolist() == [[10, 10, 60, 70], [5, 5, 50, 50]] and scores.tolist() == [np.float32(0.9), np.float32(0.6)]
+    assert planes.shape == (128, 128, 2)
+    for k, i in enumerate((0, 3)):
+        assert np.array_equal(planes[:, :, k], oracle.unmold_mask(masks[i, :, :, 1], det[i, :4].astype(np.int32), (128, 128, 3)))
+
+
 # --------------------------------------------------------------------------- proposal layer
 class _Cfg:
     RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
@@ -944,8 +974,11 @@ def test_unmold_masks_match_oracle(H, W, mh, mw):
     for i in range(masks.shape[0]):
         want = oracle.unmold_mask(masks[i], boxes[i], (H, W, 3))
         assert np.array_equal(got[i], want), (i, boxes[i].tolist(), int((got[i] != want).sum()))
-    one = unmold.unmold_mask(masks[3][None], boxes[3], (H, W, 3)).cpu().numpy()
-    assert np.array_equal(one, got[3])
+    one = unmold.unmold_mask(masks[3][None], boxes[3], (H, W, 3))
+    assert isinstance(one, np.ndarray) and np.array_equal(one, got[3])          # numpy like the reference's; device=True keeps it
+    assert np.array_equal(unmold.unmold_mask(masks[3], boxes[3], (H, W, 3), device=True).cpu().numpy(), got[3])
+    with pytest.raises(ValueError):                                            # a box past the border: the reference's paste raises
+        unmold.unmold_mask(masks[3], [0, 0, H + 1, 5], (H, W, 3))
 
 
 def test_unmold_detections_full_size_and_rle():
@@ -1054,7 +1087,9 @@ def test_resize_image_matches_oracle(h, w, H2, W2):
     assert got.shape == (H2, W2, 3) and np.array_equal(got, want)
     if h == 480:
         out, window, scale, padding = targets.resize_image(img, max_dim=1024)
-        assert window == (0, 0, 1024, 1024) and scale == (1024 / 480, 1024 / 640) and np.array_equal(out.cpu().numpy(), want)
+        assert window == (0, 0, 1024, 1024) and scale == (1024 / 480, 1024 / 640)
+        assert isinstance(out, np.ndarray) and out.dtype == np.uint8 and np.array_equal(out, want)   # numpy, like utils.resize_image
+        assert np.array_equal(targets.resize_image(img, max_dim=1024, device=True)[0].cpu().numpy(), want)
         gray = targets.resize_image_device(img[:, :, 0].copy(), (H2, W2)).cpu().numpy()
         assert np.array_equal(gray, want[:, :, 0])
 
@@ -1072,4 +1107,4 @@ def test_unmold_and_resize_match_reference_fixtures():
     assert masks.shape == g["masks"].shape and np.array_equal(masks.astype(np.uint8), g["masks"])
     r = np.load(os.path.join(gd, "resize_image.npz"))
     out, window, scale, padding = targets.resize_image(r["image"], max_dim=64)
-    assert np.array_equal(out.cpu().numpy(), r["resized"]) and window == tuple(r["window"]) and np.allclose(scale, r["scale"])
+    assert np.array_equal(out, r["resized"]) and window == tuple(r["window"]) and np.allclose(scale, r["scale"])
