@@ -34,17 +34,21 @@ namespace sln {
 // (b) every label bit below n_max into per-image words; layer_fixup_kernel then derives
 // n_obj and, only if an object >= n_obj had pixels, clears those planes (the reference
 // drops objects after the first never-visible one, Functions.py:1074-1079).
-constexpr int LD_PX = 8;     // pixels per thread
+// LD_PX pixels per thread: 16 when the plane size allows (one 16-byte store per plane and thread: the kernel is bound by
+// its instruction count, 20 stores + loop per thread, so twice the pixels per thread is ~40 % fewer warp instructions), else 8
 
 __device__ __forceinline__ unsigned long long expand_bits(const unsigned long long *__restrict__ lut, unsigned m)
 {
     return lut[m & 0xffu];
 }
 
+template <int LD_PX>
 __global__ void __launch_bounds__(256)
 layer_decode_kernel(const unsigned long long *__restrict__ label, size_t px_per_image, int L, int n_max,
                     unsigned char *__restrict__ out, unsigned *__restrict__ seen /* [B][2]: top bits, any bits */)
 {
+    static_assert(LD_PX == 8 || LD_PX == 16, "8 or 16 pixels per thread");
+    pdl_prologue();
     __shared__ unsigned long long s_lut[256];
     {
         unsigned long long v = 0ull;
@@ -98,9 +102,15 @@ layer_decode_kernel(const unsigned long long *__restrict__ label, size_t px_per_
                 }
                 const unsigned long long bytes = expand_bits(s_lut, m);
                 if (full) {
-                    __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
+                    if (LD_PX == 16) {
+                        const unsigned long long b2 = expand_bits(s_lut, m >> 8);
+                        __stcs(reinterpret_cast<uint4 *>(dst), make_uint4((unsigned)bytes, (unsigned)(bytes >> 32), (unsigned)b2, (unsigned)(b2 >> 32)));
+                    } else {
+                        __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
+                    }
                 } else {
-                    for (int k = 0; k < LD_PX && p0 + k < px_per_image; ++k) dst[k] = (unsigned char)(bytes >> (8 * k));
+                    for (int k = 0; k < LD_PX && p0 + k < px_per_image; ++k)
+                        dst[k] = (unsigned char)((k < 8 ? bytes : expand_bits(s_lut, m >> 8)) >> (8 * (k & 7)));
                 }
             }
         } else {
@@ -124,9 +134,15 @@ layer_decode_kernel(const unsigned long long *__restrict__ label, size_t px_per_
                     }
                     const unsigned long long bytes = expand_bits(s_lut, m);
                     if (full) {
-                        __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
+                        if (LD_PX == 16) {
+                            const unsigned long long b2 = expand_bits(s_lut, m >> 8);
+                            __stcs(reinterpret_cast<uint4 *>(dst), make_uint4((unsigned)bytes, (unsigned)(bytes >> 32), (unsigned)b2, (unsigned)(b2 >> 32)));
+                        } else {
+                            __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
+                        }
                     } else {
-                        for (int k = 0; k < LD_PX && p0 + k < px_per_image; ++k) dst[k] = (unsigned char)(bytes >> (8 * k));
+                        for (int k = 0; k < LD_PX && p0 + k < px_per_image; ++k)
+                            dst[k] = (unsigned char)((k < 8 ? bytes : expand_bits(s_lut, m >> 8)) >> (8 * (k & 7)));
                     }
                 }
             }
@@ -145,6 +161,7 @@ __global__ void __launch_bounds__(256)
 layer_fixup_kernel(const unsigned *__restrict__ seen, size_t px_per_image, int L, int n_max,
                    unsigned char *__restrict__ out, int *__restrict__ n_obj_out)
 {
+    pdl_prologue();
     const int b = blockIdx.y;
     const unsigned top = seen[2 * b], any = seen[2 * b + 1];
     const int n_obj = __ffs(~top) == 0 ? 32 : __ffs(~top) - 1;     // max_objectID, Functions.py:1074-1079
@@ -893,13 +910,20 @@ extern "C" int sln_layer_decode(const uint64_t *label, int B, int H, int W, int 
     SLN_REQUIRE(label && (out || n_max == 0), SLN_ERR_ARG, "null pointer");
     SLN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7u) == 0 && (reinterpret_cast<uintptr_t>(label) & 15u) == 0,
                 SLN_ERR_LAYOUT, "label must be 16-byte and out 8-byte aligned");
-    const size_t threads = (px + LD_PX - 1) / LD_PX;
+    const bool wide = px % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    const int ld_px = wide ? 16 : 8;
+    const size_t threads = (px + ld_px - 1) / ld_px;
     SLN_REQUIRE((threads + 255) / 256 < (1ull << 31), SLN_ERR_ARG, "image too large");
-    layer_decode_kernel<<<dim3((unsigned)((threads + 255) / 256), B), 256, 0, st>>>(
-        reinterpret_cast<const unsigned long long *>(label), px, L, n_max, out, scratch);
+    const dim3 grid((unsigned)((threads + 255) / 256), B);
+    if (wide)
+        layer_decode_kernel<16><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(label), px, L, n_max, out, scratch);
+    else
+        layer_decode_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(label), px, L, n_max, out, scratch);
     SLN_LAUNCH_OK("layer_decode_kernel");
-    // grid-strided clearing loop; one CTA per SM and image is enough to stream the zeros when an image needs them
-    layer_fixup_kernel<<<dim3(sm_count(), B), 256, 0, st>>>(scratch, px, L, n_max, out, n_obj);
+    // grid-strided clearing loop; one CTA per SM and image is enough to stream the zeros when an image needs them.
+    // Programmatic dependent of the decode kernel: its CTAs are placed while the decode's last wave drains.
+    SLN_CUDA_OK(launch_chain(layer_fixup_kernel, dim3(sm_count(), B), dim3(256), 0, st, true, (const unsigned *)scratch, px, L, n_max,
+                             (unsigned char *)out, n_obj));
     SLN_LAUNCH_OK("layer_fixup_kernel");
     return SLN_OK;
 }
