@@ -434,6 +434,9 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
             s0 = m ? __ffs(m) - 1 : 0;
             ns = __popc(m);
         }
+#ifdef SLN_BWD_PROBE_NO_COMPUTE
+        ns = 0;                             // diagnostic build: the consumers only shake hands (pace of producer + copies)
+#endif
         if (ns > 0) {
             const int chb = FULL ? NV * 512 : hdr.w;
             const bool ok0 = FULL || lane * 16 < chb, ok1 = NV == 2 && (FULL || lane * 16 + 512 < chb);
