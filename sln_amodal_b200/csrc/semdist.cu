@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "edt_band.cuh"
 
 namespace sln {
 
@@ -888,6 +889,204 @@ static int edt_chunk_maps(int M, int H, int W)
     return (int)c;
 }
 
+
+// ---------------------------------------------------------------------------
+// Banded exact EDT (round 2): two launches, no row-distance buffer.
+// The per-column logic is edt_band.cuh (shared with the CPU simulation under tests/host_sim); the kernels below
+// add the row pass, the work distribution and the zero fill.
+//   edt_band_build_kernel : CTA = (band of 32 rows, map).  Loads the zero masks of its 34 rows (one extra above and
+//       below) -- 1 bit per pixel in shared memory -- and, per row that holds foreground, the distance from every
+//       32-pixel segment to the nearest zero pixel outside it (two warp scans).  A band without foreground is
+//       zero-filled on the spot (128 KB of streaming stores); otherwise the empty 32x32 tiles are zero-filled and the
+//       non-empty ones get their envelope stacks built, one warp per tile, the row distance of a pixel computed on the
+//       fly from (mask, left, right) -- g never exists in memory.
+//   edt_band_eval_kernel  : persistent warps that draw the non-empty tiles from a work list, launched as a programmatic
+//       dependent; only those tiles are evaluated and written (own stack staged in shared memory, the bands a run
+//       continues into read through L2).
+// ---------------------------------------------------------------------------
+namespace eb = edtband;
+constexpr int EB_WARPS = 8;
+
+__device__ __forceinline__ void st_zero16(int *p)
+{
+    asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p) : "memory");
+}
+
+__global__ void __launch_bounds__(EB_WARPS * 32)
+edt_band_build_kernel(const unsigned char *__restrict__ maps, int H, int W, int nb, unsigned *__restrict__ list,
+                      unsigned *__restrict__ counters, uint2 *__restrict__ meta, unsigned *__restrict__ stk, int *__restrict__ out)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NROW = eb::BAND + 2;
+    constexpr int PER_WARP = (NROW + EB_WARPS - 1) / EB_WARPS;
+    __shared__ unsigned s_mask[NROW][32];
+    __shared__ int s_ld[eb::BAND][32];
+    __shared__ int s_rd[eb::BAND][32];
+    __shared__ unsigned s_rowbits[eb::BAND];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x, m = blockIdx.y;
+    const int tx = W >> 5;
+    const int yb = b * eb::BAND, rows = min(eb::BAND, H - yb);
+    const unsigned char *__restrict__ src = maps + (size_t)m * H * W;
+
+    // ---- zero masks of rows yb-1 .. yb+32 (rows outside the map: no zero pixels), loads first
+    unsigned zr[PER_WARP];
+#pragma unroll
+    for (int j = 0; j < PER_WARP; ++j) {
+        const int i = warp + j * EB_WARPS, yy = yb - 1 + i;
+        zr[j] = 0u;
+        if (i < NROW && yy >= 0 && yy < H) zr[j] = seg_zero_mask(src + (size_t)yy * W, lane * 32, W, true);
+    }
+#pragma unroll
+    for (int j = 0; j < PER_WARP; ++j) {
+        const int i = warp + j * EB_WARPS;
+        if (i >= NROW) break;
+        const unsigned z = zr[j];
+        s_mask[i][lane] = z;
+        if (i >= 1 && i <= eb::BAND) {
+            const unsigned rb = __ballot_sync(FULL, lane < tx && z != FULL) & (yb - 1 + i < H ? FULL : 0u);
+            if (lane == 0) s_rowbits[i - 1] = rb;
+            if (rb) {                                   // the row holds foreground: nearest zero outside every segment
+                const int x0 = lane * 32;
+                int left = z ? x0 + 31 - __clz(z) : -eb::NONE_D;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, left, o);
+                    if (lane >= o) left = max(left, v);
+                }
+                left = __shfl_up_sync(FULL, left, 1);
+                if (lane == 0) left = -eb::NONE_D;
+                int right = z ? x0 + __ffs(z) - 1 : eb::NONE_D;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_down_sync(FULL, right, o);
+                    if (lane + o < 32) right = min(right, v);
+                }
+                right = __shfl_down_sync(FULL, right, 1);
+                if (lane == 31) right = eb::NONE_D;
+                s_ld[i - 1][lane] = left == -eb::NONE_D ? eb::NONE_D : x0 - left;
+                s_rd[i - 1][lane] = right == eb::NONE_D ? eb::NONE_D : right - (x0 + 31);
+            }
+        }
+    }
+    __syncthreads();
+
+    const unsigned anym = __reduce_or_sync(FULL, s_rowbits[lane]);          // segments that hold foreground
+    int *__restrict__ om = out + (size_t)m * H * W + (size_t)yb * W;
+    if (anym == 0u) {                                                        // background band: zeros, done
+        const int c4 = threadIdx.x * 4;
+        if (c4 < W) {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) st_zero16(om + (size_t)r * W + c4);
+        }
+        return;
+    }
+    // the band's non-empty tiles join the evaluation pass's work list (order: whatever the atomics give; every tile is
+    // evaluated independently, so the result does not depend on it)
+    if (warp == 0) {
+        const int n = __popc(anym);
+        unsigned base = 0u;
+        if (lane == 0) base = atomicAdd(counters, (unsigned)n);
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < n) list[base + lane] = (unsigned)((((size_t)m * nb + b) << 5) | __fns(anym, 0, lane + 1));
+    }
+    // flag word of segment `lane`: bit r <=> row yb + r holds foreground there
+    unsigned fmine = 0u;
+#pragma unroll
+    for (int r = 0; r < eb::BAND; ++r) fmine |= ((s_rowbits[r] >> lane) & 1u) << r;
+
+    // ---- zero fill of the band's empty tiles: rows dealt over the warps, one store instruction = 512 contiguous bytes
+    const unsigned segmask = tx >= 32 ? FULL : ((1u << tx) - 1u);
+    const unsigned emp = ~anym & segmask;
+    if (emp) {
+        for (int r = warp; r < rows; r += EB_WARPS) {
+#pragma unroll
+            for (int grp = 0; grp < 8; ++grp) {
+                if (!((emp >> (4 * grp)) & 0xfu)) continue;
+                if ((emp >> (4 * grp + (lane >> 3))) & 1u) st_zero16(om + (size_t)r * W + grp * 128 + lane * 4);
+            }
+        }
+    }
+    // ---- envelope stacks of the non-empty tiles, dealt over the warps by rank
+    unsigned ne = anym;
+    for (int k = 0; ne; ++k) {
+        const int s = __ffs(ne) - 1;
+        ne &= ne - 1u;
+        if ((k % EB_WARPS) != warp) continue;
+        const unsigned f = __shfl_sync(FULL, fmine, s);
+        const int x = s * 32 + lane;
+        const bool above = yb > 0, below = yb + eb::BAND < H;
+        const bool az = above && ((s_mask[0][s] >> lane) & 1u), bz = below && ((s_mask[NROW - 1][s] >> lane) & 1u);
+        unsigned *sc = stk + ((size_t)m * nb + b) * eb::SLOTS * W + x;
+        const eb::BuildResult res = eb::band_build_lane(f, rows, yb, H, lane, az, above && !az, bz, below && !bz, sc, W,
+                                                        [&](int r, unsigned &z, int &ld, int &rd) {
+                                                            z = s_mask[r + 1][s];
+                                                            ld = s_ld[r][s];
+                                                            rd = s_rd[r][s];
+                                                        });
+        meta[((size_t)m * nb + b) * W + x] = make_uint2(res.fgw, res.meta);
+    }
+}
+
+constexpr int EV_WARPS = 4;      // 4.3 KB of shared memory per warp (the tile's own stacks)
+constexpr int EV_CTAS_PER_SM = 8;
+
+// Persistent: every warp draws tiles from the list the build pass left (ticket counter), so the few bands that hold
+// a blob's tiles are spread over the whole GPU instead of queueing behind one another in one CTA.  The running minima
+// live in the output itself: the own-band walk stores every row of the tile once (zeros where the pixel is background),
+// the bands above / below then lower the rows of the runs that continue into them (same thread, same address).
+__global__ void __launch_bounds__(EV_WARPS * 32, EV_CTAS_PER_SM)
+edt_band_eval_kernel(const unsigned *__restrict__ list, unsigned *__restrict__ counters, const uint2 *__restrict__ meta,
+                     const unsigned *__restrict__ stk, int H, int W, int nb, int cap, int *__restrict__ out)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    pdl_prologue();
+    __shared__ unsigned s_own[EV_WARPS][eb::SLOTS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned count = __ldcg(counters);
+    for (;;) {
+        unsigned idx = 0u;
+        if (lane == 0) idx = atomicAdd(counters + 1, 1u);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= count) break;
+        const unsigned tile = __ldg(list + idx);
+        const int s = (int)(tile & 31u);
+        const size_t mb = tile >> 5;                                   // m * nb + b
+        const int m = (int)(mb / (unsigned)nb), b = (int)(mb - (size_t)m * nb);
+        const size_t band0 = (size_t)m * nb;
+        const int yb = b * eb::BAND, rows = min(eb::BAND, H - yb);
+        const int x = s * 32 + lane;
+        const uint2 mm = __ldg(meta + mb * W + x);
+        const int maxtot = __reduce_max_sync(FULL, eb::meta_total(mm.y));
+        const unsigned *__restrict__ own = stk + mb * eb::SLOTS * W + x;
+#pragma unroll 4
+        for (int q = 0; q < maxtot; ++q) s_own[warp][q][lane] = __ldg(own + (size_t)q * W);
+        __syncwarp();
+        eb::band_eval_lane(b, nb, yb, rows, cap, mm.x, mm.y, &s_own[warp][0][lane], 32, stk + band0 * eb::SLOTS * W + x,
+                           (size_t)eb::SLOTS * W, W, reinterpret_cast<const eb::Words2 *>(meta) + band0 * W + x, W,
+                           out + (size_t)m * H * W + (size_t)yb * W + x, W);
+        __syncwarp();
+    }
+}
+
+// shapes the banded kernels take: whole 32-column segments, entry fields s:11 | t:11 | g:10
+static bool edt_band_shape(int H, int W) { return W >= 32 && W % 32 == 0 && W <= 1024 && H <= 2048; }
+static bool edt_band_enabled()
+{
+    const char *e = getenv("SLN_EDT_IMPL");       // "legacy": the whole-column envelope kernels of round 1 (A/B)
+    return !(e && e[0] == 'l');
+}
+static size_t edt_band_map_bytes(int H, int W)
+{
+    const size_t nb = (size_t)cdiv(H, eb::BAND);
+    return nb * ((size_t)eb::SLOTS * W * sizeof(unsigned) + (size_t)W * sizeof(uint2) + 32 * sizeof(unsigned)) + 1;
+}
+static int edt_band_chunk_maps(int M, int H, int W)
+{
+    size_t c = (3072ull << 20) / edt_band_map_bytes(H, W);
+    if (c < 1) c = 1;
+    if (c > (size_t)M) c = (size_t)M;
+    return (int)c;
+}
+
 }  // namespace sln
 
 using namespace sln;
@@ -944,7 +1143,14 @@ extern "C" size_t sln_edt_workspace_bytes(int M, int H, int W)
 {
     if (M <= 0 || H <= 0 || W <= 0) return 0;
     const int mc = edt_chunk_maps(M, H, W);
-    return edt_g_bytes(mc, H, W) + edt_flags_bytes(mc, H, W) + edt_fgcol_bytes(mc, H, W);
+    size_t need = edt_g_bytes(mc, H, W) + edt_flags_bytes(mc, H, W) + edt_fgcol_bytes(mc, H, W);
+    if (edt_band_shape(H, W)) {      // the banded kernels' stacks + words + flags (either path may be taken at run time)
+        const size_t nb = (size_t)cdiv(H, eb::BAND), bc = (size_t)edt_band_chunk_maps(M, H, W);
+        const size_t band = align_up(bc * nb * eb::SLOTS * W * sizeof(unsigned), 256) + align_up(bc * nb * W * sizeof(uint2), 256) +
+                            align_up(bc * nb * 32 * sizeof(unsigned), 256) + 256;
+        if (band > need) need = band;
+    }
+    return need;
 }
 extern "C" int sln_edt_sq(const uint8_t *maps, int M, int H, int W, int32_t *out, void *workspace,
                           size_t workspace_bytes, void *stream)
@@ -957,6 +1163,30 @@ extern "C" int sln_edt_sq(const uint8_t *maps, int M, int H, int W, int32_t *out
     SLN_REQUIRE(workspace && workspace_bytes >= sln_edt_workspace_bytes(M, H, W), SLN_ERR_WORKSPACE,
                 "edt workspace: need %zu bytes, got %zu", sln_edt_workspace_bytes(M, H, W), workspace_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (edt_band_shape(H, W) && edt_band_enabled() &&
+        ((reinterpret_cast<uintptr_t>(maps) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(workspace)) & 15u) == 0) {
+        const int nb = cdiv(H, eb::BAND), bc = edt_band_chunk_maps(M, H, W);
+        unsigned char *w0 = static_cast<unsigned char *>(workspace);
+        unsigned *stk = reinterpret_cast<unsigned *>(w0);
+        uint2 *meta = reinterpret_cast<uint2 *>(w0 + align_up((size_t)bc * nb * eb::SLOTS * W * sizeof(unsigned), 256));
+        unsigned *tlist = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(meta) + align_up((size_t)bc * nb * W * sizeof(uint2), 256));
+        unsigned *counters = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(tlist) + align_up((size_t)bc * nb * 32 * sizeof(unsigned), 256));
+        const int bcap = (H + W) * (H + W);
+        SLN_REQUIRE((size_t)bc * nb < (1ull << 27), SLN_ERR_ARG, "too many bands per chunk");
+        for (int m0 = 0; m0 < M; m0 += bc) {
+            const int mc = (M - m0) < bc ? (M - m0) : bc;
+            SLN_REQUIRE(mc <= 65535, SLN_ERR_ARG, "too many maps per chunk");
+            SLN_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st));      // tiles listed, tickets drawn
+            edt_band_build_kernel<<<dim3(nb, mc), EB_WARPS * 32, 0, st>>>(maps + (size_t)m0 * H * W, H, W, nb, tlist, counters, meta, stk,
+                                                                          out + (size_t)m0 * H * W);
+            SLN_LAUNCH_OK("edt_band_build_kernel");
+            SLN_CUDA_OK(launch_chain(edt_band_eval_kernel, dim3(sm_count() * EV_CTAS_PER_SM), dim3(EV_WARPS * 32), 0, st, true,
+                                     (const unsigned *)tlist, counters, (const uint2 *)meta, (const unsigned *)stk, H, W, nb, bcap,
+                                     out + (size_t)m0 * H * W));
+            SLN_LAUNCH_OK("edt_band_eval_kernel");
+        }
+        return SLN_OK;
+    }
     const int chunk = edt_chunk_maps(M, H, W);
     unsigned char *wsb = static_cast<unsigned char *>(workspace);
     unsigned short *g = reinterpret_cast<unsigned short *>(wsb);              // u32 elements on the packed path

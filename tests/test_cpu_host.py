@@ -41,8 +41,8 @@ def test_workspace_queries_and_arg_errors(built_lib):
     n = 12000
     assert L.sln_nms_workspace_bytes(n) >= n * ((n + 63) // 64) * 8
     assert L.sln_crop_and_resize_bwd_workspace_bytes(8000, 8, 7, 7) >= 8000 * 12
-    # row distances / envelope stack (u32 per pixel on the packed path) + tile flags + one fg word per (tile, column)
-    assert L.sln_edt_workspace_bytes(320, 1024, 1024) <= 320 * 1024 * 1024 * 4 * (1 + 1 / 32) + (2 << 20)
+    # banded path: 34 stack slots per 32 rows (u32) + two words per (band, column) + tile flags
+    assert L.sln_edt_workspace_bytes(320, 1024, 1024) <= 320 * 1024 * 1024 * 4 * (34 / 32 + 2 / 32) + (2 << 20)
     assert L.sln_edt_workspace_bytes(4, 4096, 4096) <= 4 * 4096 * 4096 * 2 + (2 << 20)
     assert L.sln_proposal_workspace_bytes(261888, 6000) == L.sln_proposal_workspace_bytes(10 ** 6, 6000)
     # argument validation happens before any CUDA call
