@@ -128,42 +128,45 @@ SLN_HD int row_dist(unsigned z, int lane, int ldist, int rdist)
 constexpr int PK_D = 3;
 struct Stack {
     int q, base, ystart;         // top index (-1: empty), first entry and first breakpoint of the open run
+    unsigned *top;               // address of entry q (walked, never recomputed: 64-bit multiplies cost more than the pops)
     unsigned e[PK_D];            // entries q, q-1, q-2 (garbage below index 0)
     bool open;
 };
 
-SLN_HD void pk_pop(Stack &c, const unsigned *sc, int stride)
+SLN_HD void pk_pop(Stack &c, int stride)
 {
     --c.q;
+    c.top -= stride;
 #pragma unroll
     for (int i = 0; i + 1 < PK_D; ++i) c.e[i] = c.e[i + 1];
-    if (c.q >= PK_D - 1) c.e[PK_D - 1] = sc[(size_t)(c.q - (PK_D - 1)) * stride];
+    if (c.q >= PK_D - 1) c.e[PK_D - 1] = *(c.top - (PK_D - 1) * stride);
 }
 
-SLN_HD void pk_push(Stack &c, unsigned *sc, int stride, unsigned e)
+SLN_HD void pk_push(Stack &c, int stride, unsigned e)
 {
     ++c.q;
+    c.top += stride;
 #pragma unroll
     for (int i = PK_D - 1; i > 0; --i) c.e[i] = c.e[i - 1];
     c.e[0] = e;
-    sc[(size_t)c.q * stride] = e;
+    *c.top = e;
 }
 
 // add the parabola of site (u, gq); entries that would only win after row `limit` are dropped
-SLN_HD void pk_insert(Stack &c, unsigned *sc, int stride, int u, int gq, int limit)
+SLN_HD void pk_insert(Stack &c, int stride, int u, int gq, int limit)
 {
     const int gu2 = gq * gq;
     while (c.q >= c.base) {
         const int t = pk_t(c.e[0]);
-        if (env_at(t, c.e[0]) > env_f(t, u, gu2)) pk_pop(c, sc, stride);
+        if (env_at(t, c.e[0]) > env_f(t, u, gu2)) pk_pop(c, stride);
         else break;
     }
     if (c.q < c.base) {
-        pk_push(c, sc, stride, pk_make(u, c.ystart, gq));
+        pk_push(c, stride, pk_make(u, c.ystart, gq));
     } else {
         const int st = pk_s(c.e[0]);
         const int w = 1 + floor_div_small(u * u - st * st + gu2 - pk_g2(c.e[0]), 2 * (u - st));
-        if (w <= limit) pk_push(c, sc, stride, pk_make(u, w, gq));
+        if (w <= limit) pk_push(c, stride, pk_make(u, w, gq));
     }
 }
 
@@ -184,6 +187,7 @@ SLN_HD BuildResult band_build_lane(unsigned f, int rows, int yb, int H, int lane
 {
     Stack c;
     c.q = -1; c.base = 0; c.ystart = 0; c.open = false;
+    c.top = sc - stride;
 #pragma unroll
     for (int i = 0; i < PK_D; ++i) c.e[i] = 0u;
     unsigned fgw = 0u;
@@ -202,7 +206,7 @@ SLN_HD BuildResult band_build_lane(unsigned f, int rows, int yb, int H, int lane
         const int y = yb + r;
         if (gv == 0) {
             if (c.open) {                                           // the zero pixel at y closes the run
-                pk_insert(c, sc, stride, y, 0, y - 1);
+                pk_insert(c, stride, y, 0, y - 1);
                 gmin = 0;
                 c.open = false;
                 if (first_open) { n_first = c.q + 1; first_open = false; }
@@ -217,12 +221,12 @@ SLN_HD BuildResult band_build_lane(unsigned f, int rows, int yb, int H, int lane
                     if (above_fg) { top_open = true; first_open = true; }
                 } else {
                     c.ystart = y;
-                    pk_insert(c, sc, stride, y - 1, 0, H - 1);      // the zero pixel just above the run
+                    pk_insert(c, stride, y - 1, 0, H - 1);      // the zero pixel just above the run
                     gmin = 0;
                 }
             }
             if (gv != GQ_INF) {
-                pk_insert(c, sc, stride, y, gv, H - 1);
+                pk_insert(c, stride, y, gv, H - 1);
                 gmin = hd_min(gmin, gv);
             }
         }
@@ -231,7 +235,7 @@ SLN_HD BuildResult band_build_lane(unsigned f, int rows, int yb, int H, int lane
     int last_base = 0;
     if (c.open) {
         if (below_zero) {
-            pk_insert(c, sc, stride, yb + rows, 0, yb + rows - 1);
+            pk_insert(c, stride, yb + rows, 0, yb + rows - 1);
             gmin = 0;
             c.open = false;
             if (first_open) { n_first = c.q + 1; first_open = false; }
@@ -275,18 +279,22 @@ SLN_HD Words2 ld_ro(const Words2 *p)
 #endif
 }
 
-// Evaluation pass of one column of one band.  The column's running minima live in the output itself: the own-band
-// walk stores every row once (zero where the pixel is background, `cap` where the column's runs see no zero pixel at
-// all), the bands above / below then lower the rows of the runs that continue into them.
+// Evaluation pass of one column of one band.  best[r * best_stride] receives the squared distance of pixel (yb + r, x)
+// for the column's foreground rows (`cap` where the column's runs see no zero pixel at all; other rows: unspecified):
+// the own-band walk stores every row once, the bands above / below then lower the rows of the runs that continue into them.
 //   own[k * own_stride]                                  : entry k of this band's stack (staged in shared memory)
-//   stk_col[bb * band_stride + k * slot_stride]          : entry k of band bb's stack, same column
+//   stk_col + bb * band_stride                           : band bb's stack, same column (entry k at + k * slot_stride)
 //   meta_col[bb * meta_stride]                           : the two words of band bb, same column
-//   oc[r * out_stride]                                   : output pixel (yb + r, x)
-// Everything is addressed by walking pointers: the first form of this function went through index lambdas and spent
-// 50-60 instructions per row on 64-bit address arithmetic and re-unpacking the current entry.
+//   stage(bp, lo, hi, need, ptr, stride)                 : warp-wide; makes entries [lo, hi) of the stack at bp readable
+//                                                          as ptr[k * stride] for the lanes with `need`
+// Why the staging: a row's winner in a neighbouring band is usually a DIFFERENT entry for every row (inside a disc the
+// winner of a row sits tens of rows further out), so a walk touches most of that band's entries one after the other --
+// as dependent L2 / DRAM round trips of a lone warp that was 30 us per walk; staged, the loads are all in flight at once.
+// Everything is addressed by walking pointers (index lambdas cost 50-60 instructions per row in address arithmetic).
+template <class StageFn>
 SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fgw, unsigned mw, const unsigned *own,
                            int own_stride, const unsigned *stk_col, size_t band_stride, int slot_stride,
-                           const Words2 *meta_col, int meta_stride, int *oc, int out_stride)
+                           const Words2 *meta_col, int meta_stride, int *best, int best_stride, StageFn stage)
 {
     const int total = meta_total(mw);
     const int n1 = fgw == FULLW ? BAND : hd_ffs(~fgw) - 1;              // rows of the run that touches the band's top
@@ -298,9 +306,9 @@ SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fg
         unsigned e = total > 0 ? *op : 0u;
         int s = pk_s(e), g2 = total > 0 ? pk_g2(e) : cap;
         int tn = total > 1 ? pk_t(op[own_stride]) : T_NEVER;
-        int *o = oc;
+        int *o = best;
         const int d0 = total > 0 ? 1 : 0;                               // no entries: every row reads `cap`
-        for (int r = 0; r < rows; ++r, o += out_stride) {
+        for (int r = 0; r < rows; ++r, o += best_stride) {
             const int y = yb + r;
             while (tn <= y) {
                 op += own_stride;
@@ -311,37 +319,45 @@ SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fg
             }
             const int dy = (y - s) * d0;
             const int v = dy * dy + g2;
-            *o = ((fgw >> r) & 1u) ? v : 0;
+            *o = v;
             if (r < n1) mx_up = hd_max(mx_up, v);
             if (r >= BAND - nl) mx_dn = hd_max(mx_dn, v);
         }
     }
     // ---- bands above: rows of the first run, trailing entries of those bands
-    {                                   // (every lane runs the loop: the votes inside are full-warp)
+    {                                   // (every lane runs the loop: the votes and the staging inside are warp-wide)
         bool cont = meta_top_open(mw);
         int mx = mx_up;
         const Words2 *mp = meta_col + (size_t)b * meta_stride;
         const unsigned *bp = stk_col + (size_t)b * band_stride;
+        Words2 wn;
+        wn.x = wn.y = 0u;
+        if (b >= 1) wn = ld_ro(mp - meta_stride);                       // the next band's words, one band ahead
         for (int d = 1; b - d >= 0; ++d) {
             mp -= meta_stride;
             bp -= band_stride;
             const int gap = BAND * (d - 1) + 1;
             const bool act = cont && gap * gap < mx;
             if (!SLN_WARP_ANY(act)) break;
-            if (act) {
-                const Words2 w2 = ld_ro(mp);
-                const int tot2 = meta_total(w2.y), lb2 = meta_last_base(w2.y), gm = meta_gmin(w2.y);
-                if (tot2 > lb2 && gap * gap + gm * gm < mx) {
-                    const unsigned *sp = bp + (size_t)(tot2 - 1) * slot_stride;
-                    const unsigned *const first = bp + (size_t)lb2 * slot_stride;
-                    unsigned e = ld_ro(sp);
+            const Words2 w2 = wn;
+            if (b - d >= 1) wn = ld_ro(mp - meta_stride);
+            const int tot2 = meta_total(w2.y), lb2 = meta_last_base(w2.y), gm = meta_gmin(w2.y);
+            const bool need = act && tot2 > lb2 && gap * gap + gm * gm < mx;
+            if (SLN_WARP_ANY(need)) {
+                const unsigned *ep;
+                int es;
+                stage(bp, lb2, tot2, need, ep, es);
+                if (need) {
+                    const unsigned *sp = ep + (tot2 - 1) * es;
+                    const unsigned *const first = ep + lb2 * es;
+                    unsigned e = *sp;
                     int s = pk_s(e), g2 = pk_g2(e), t = pk_t(e);
-                    int *o = oc + (size_t)(n1 - 1) * out_stride;
+                    int *o = best + (n1 - 1) * best_stride;
                     mx = 0;
-                    for (int y = yb + n1 - 1; y >= yb; --y, o -= out_stride) {
+                    for (int y = yb + n1 - 1; y >= yb; --y, o -= best_stride) {
                         while (t > y && sp != first) {
-                            sp -= slot_stride;
-                            e = ld_ro(sp);
+                            sp -= es;
+                            e = *sp;
                             s = pk_s(e);
                             g2 = pk_g2(e);
                             t = pk_t(e);
@@ -355,8 +371,8 @@ SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fg
                         mx = hd_max(mx, v);
                     }
                 }
-                cont = w2.x == FULLW && meta_top_open(w2.y);
             }
+            if (act) cont = w2.x == FULLW && meta_top_open(w2.y);
         }
     }
     // ---- bands below: rows of the last run, leading entries of those bands
@@ -365,30 +381,38 @@ SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fg
         int mx = mx_dn;
         const Words2 *mp = meta_col + (size_t)b * meta_stride;
         const unsigned *bp = stk_col + (size_t)b * band_stride;
+        Words2 wn;
+        wn.x = wn.y = 0u;
+        if (b + 1 < nb) wn = ld_ro(mp + meta_stride);
         for (int d = 1; b + d < nb; ++d) {
             mp += meta_stride;
             bp += band_stride;
             const int gap = BAND * (d - 1) + 1;
             const bool act = cont && gap * gap < mx;
             if (!SLN_WARP_ANY(act)) break;
-            if (act) {
-                const Words2 w2 = ld_ro(mp);
-                const int nf2 = meta_n_first(w2.y), gm = meta_gmin(w2.y);
-                if (nf2 > 0 && gap * gap + gm * gm < mx) {
-                    const unsigned *sp = bp;
-                    const unsigned *const last = bp + (size_t)(nf2 - 1) * slot_stride;
-                    unsigned e = ld_ro(sp);
+            const Words2 w2 = wn;
+            if (b + d + 1 < nb) wn = ld_ro(mp + meta_stride);
+            const int nf2 = meta_n_first(w2.y), gm = meta_gmin(w2.y);
+            const bool need = act && nf2 > 0 && gap * gap + gm * gm < mx;
+            if (SLN_WARP_ANY(need)) {
+                const unsigned *ep;
+                int es;
+                stage(bp, 0, nf2, need, ep, es);
+                if (need) {
+                    const unsigned *sp = ep;
+                    const unsigned *const last = ep + (nf2 - 1) * es;
+                    unsigned e = *sp;
                     int s = pk_s(e), g2 = pk_g2(e);
-                    int tn = nf2 > 1 ? pk_t(ld_ro(sp + slot_stride)) : T_NEVER;
-                    int *o = oc + (size_t)(BAND - nl) * out_stride;
+                    int tn = nf2 > 1 ? pk_t(sp[es]) : T_NEVER;
+                    int *o = best + (BAND - nl) * best_stride;
                     mx = 0;
-                    for (int y = yb + BAND - nl; y < yb + BAND; ++y, o += out_stride) {
+                    for (int y = yb + BAND - nl; y < yb + BAND; ++y, o += best_stride) {
                         while (tn <= y) {
-                            sp += slot_stride;
-                            e = ld_ro(sp);
+                            sp += es;
+                            e = *sp;
                             s = pk_s(e);
                             g2 = pk_g2(e);
-                            tn = sp != last ? pk_t(ld_ro(sp + slot_stride)) : T_NEVER;
+                            tn = sp != last ? pk_t(sp[es]) : T_NEVER;
                         }
                         const int c = (y - s) * (y - s) + g2;
                         int v = *o;
@@ -399,8 +423,8 @@ SLN_HD void band_eval_lane(int b, int nb, int yb, int rows, int cap, unsigned fg
                         mx = hd_max(mx, v);
                     }
                 }
-                cont = w2.x == FULLW && meta_bot_open(w2.y);
             }
+            if (act) cont = w2.x == FULLW && meta_bot_open(w2.y);
         }
     }
 }

@@ -912,7 +912,7 @@ __device__ __forceinline__ void st_zero16(int *p)
     asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p) : "memory");
 }
 
-__global__ void __launch_bounds__(EB_WARPS * 32)
+__global__ void __launch_bounds__(EB_WARPS * 32, 5)
 edt_band_build_kernel(const unsigned char *__restrict__ maps, int H, int W, int nb, unsigned *__restrict__ list,
                       unsigned *__restrict__ counters, uint2 *__restrict__ meta, unsigned *__restrict__ stk, int *__restrict__ out)
 {
@@ -1026,44 +1026,69 @@ edt_band_build_kernel(const unsigned char *__restrict__ maps, int H, int W, int 
     }
 }
 
-constexpr int EV_WARPS = 4;      // 4.3 KB of shared memory per warp (the tile's own stacks)
-constexpr int EV_CTAS_PER_SM = 8;
+constexpr int EV_WARPS = 4;      // 8.3 KB of shared memory per warp: one stack buffer (own band, then each neighbour) + the minima
+constexpr int EV_CTAS_PER_SM = 6;
 
-// Persistent: every warp draws tiles from the list the build pass left (ticket counter), so the few bands that hold
-// a blob's tiles are spread over the whole GPU instead of queueing behind one another in one CTA.  The running minima
-// live in the output itself: the own-band walk stores every row of the tile once (zeros where the pixel is background),
-// the bands above / below then lower the rows of the runs that continue into them (same thread, same address).
+// Persistent: every warp draws tiles from the list the build pass left (ticket counter), so the few bands that hold a
+// blob's tiles are spread over the whole GPU instead of queueing behind one another in one CTA.  The next tile's ticket,
+// list entry and words are fetched while the current tile is processed.  A tile's running minima stay in shared memory
+// until every band in reach has been seen; the tile is then written once (zeros where the pixel is background).
 __global__ void __launch_bounds__(EV_WARPS * 32, EV_CTAS_PER_SM)
 edt_band_eval_kernel(const unsigned *__restrict__ list, unsigned *__restrict__ counters, const uint2 *__restrict__ meta,
                      const unsigned *__restrict__ stk, int H, int W, int nb, int cap, int *__restrict__ out)
 {
     constexpr unsigned FULL = 0xffffffffu;
     pdl_prologue();
-    __shared__ unsigned s_own[EV_WARPS][eb::SLOTS][32];
+    __shared__ unsigned s_buf[EV_WARPS][eb::SLOTS][32];
+    __shared__ int s_best[EV_WARPS][eb::BAND][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = __ldcg(counters);
+    auto draw = [&]() {
+        unsigned t = 0u;
+        if (lane == 0) t = atomicAdd(counters + 1, 1u);
+        return __shfl_sync(FULL, t, 0);
+    };
+    // every lane copies ITS column's entries [kmin, kmax) of the stack at bp (kmin / kmax: over the lanes that need them);
+    // a lane only ever reads back what it wrote itself, so no barrier is involved
+    auto stage = [&](const unsigned *bp, int lo, int hi, bool need, const unsigned *&ptr, int &stride) {
+        const int kmin = __reduce_min_sync(FULL, need ? lo : eb::SLOTS), kmax = __reduce_max_sync(FULL, need ? hi : 0);
+        const unsigned *src = bp + (size_t)kmin * W;
+        unsigned *dst = &s_buf[warp][kmin][lane];
+#pragma unroll 4
+        for (int q = kmin; q < kmax; ++q, src += W, dst += 32) *dst = __ldg(src);
+        ptr = &s_buf[warp][0][lane];
+        stride = 32;
+    };
+    unsigned idx = draw();
+    if (idx >= count) return;
+    unsigned tile = __ldg(list + idx);
+    uint2 mm = __ldg(meta + (size_t)(tile >> 5) * W + (tile & 31u) * 32 + lane);
     for (;;) {
-        unsigned idx = 0u;
-        if (lane == 0) idx = atomicAdd(counters + 1, 1u);
-        idx = __shfl_sync(FULL, idx, 0);
-        if (idx >= count) break;
-        const unsigned tile = __ldg(list + idx);
+        const unsigned idx_n = draw();
+        unsigned tile_n = 0u;
+        uint2 mm_n = make_uint2(0u, 0u);
+        if (idx_n < count) {
+            tile_n = __ldg(list + idx_n);
+            mm_n = __ldg(meta + (size_t)(tile_n >> 5) * W + (tile_n & 31u) * 32 + lane);
+        }
         const int s = (int)(tile & 31u);
         const size_t mb = tile >> 5;                                   // m * nb + b
         const int m = (int)(mb / (unsigned)nb), b = (int)(mb - (size_t)m * nb);
         const size_t band0 = (size_t)m * nb;
         const int yb = b * eb::BAND, rows = min(eb::BAND, H - yb);
         const int x = s * 32 + lane;
-        const uint2 mm = __ldg(meta + mb * W + x);
-        const int maxtot = __reduce_max_sync(FULL, eb::meta_total(mm.y));
-        const unsigned *__restrict__ own = stk + mb * eb::SLOTS * W + x;
-#pragma unroll 4
-        for (int q = 0; q < maxtot; ++q) s_own[warp][q][lane] = __ldg(own + (size_t)q * W);
-        __syncwarp();
-        eb::band_eval_lane(b, nb, yb, rows, cap, mm.x, mm.y, &s_own[warp][0][lane], 32, stk + band0 * eb::SLOTS * W + x,
+        const unsigned *own;
+        int own_stride;
+        stage(stk + mb * eb::SLOTS * W + x, 0, eb::meta_total(mm.y), true, own, own_stride);
+        eb::band_eval_lane(b, nb, yb, rows, cap, mm.x, mm.y, own, own_stride, stk + band0 * eb::SLOTS * W + x,
                            (size_t)eb::SLOTS * W, W, reinterpret_cast<const eb::Words2 *>(meta) + band0 * W + x, W,
-                           out + (size_t)m * H * W + (size_t)yb * W + x, W);
-        __syncwarp();
+                           &s_best[warp][0][lane], 32, stage);
+        int *__restrict__ oc = out + (size_t)m * H * W + (size_t)yb * W + x;
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r) __stcs(oc + (size_t)r * W, ((mm.x >> r) & 1u) ? s_best[warp][r][lane] : 0);
+        if (idx_n >= count) break;
+        tile = tile_n;
+        mm = mm_n;
     }
 }
 

@@ -90,8 +90,14 @@ extern "C" int edt_band_sim(const uint8_t *map, int H, int W, int32_t *out, int 
                 const int x = s * 32 + lane;
                 const unsigned fgw = mwords[(size_t)b * W + x].x, mw = mwords[(size_t)b * W + x].y;
                 // bands whose tile was never built hold no words: reading them would be a bug of the pruning logic
+                int best[BAND];
                 band_eval_lane(b, nb, yb, rows, cap, fgw, mw, stk.data() + (size_t)b * SLOTS * W + x, W, stk.data() + x,
-                               (size_t)SLOTS * W, W, mwords.data() + x, W, out + (size_t)yb * W + x, W);
+                               (size_t)SLOTS * W, W, mwords.data() + x, W, best, 1,
+                               [&](const unsigned *bp, int, int, bool, const unsigned *&ptr, int &stride) {
+                                   ptr = bp;            // no staging on the host: the stack itself
+                                   stride = W;
+                               });
+                for (int r = 0; r < rows; ++r) out[(size_t)(yb + r) * W + x] = ((fgw >> r) & 1u) ? best[r] : 0;
             }
         }
     }
