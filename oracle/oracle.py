@@ -895,3 +895,47 @@ def nms_mask_scan(mask):
     keep = np.empty(n, np.int64)
     k = _lib().orc_nms_mask_scan(mask.ctypes.data_as(C.c_void_p), C.c_int(n), keep.ctypes.data_as(C.c_void_p))
     return keep[:k]
+
+
+# ---------------------------------------------------------------------------
+# restatement: load_image_gt (modal/Functions.py:675-736) from the pieces above
+# ---------------------------------------------------------------------------
+def load_image_gt(label, image, num_classes, max_dim, augment, seed, image_id=0):
+    """load_image_gt on an in-memory (label map, image) pair: AmodalDataset.load_layer2 (layer_decode), utils.resize_image
+    (resize_image: Pillow-exact), utils.resize_layer (scipy.ndimage.zoom order 0 -- the library the reference calls), the
+    seeded flip (`random.randint`), utils.extract_bboxes' jitter (`np.random.rand`, 4 per instance), compose_image_meta
+    and the final [H,W,n,L] uint8 layout.  Seeds both generators like tests/golden/make_golden_loadgt.py does."""
+    import random
+    import scipy.ndimage
+    random.seed(seed)
+    np.random.seed(seed)
+    L = num_classes - 1
+    planes, n = layer_decode(label, L, n_max=32)                 # [32, L, H, W]
+    mask_layers = planes[:n].transpose(2, 3, 1, 0).astype(bool)    # [H, W, L, n] as load_layer2 returns it
+    shape = image.shape
+    h, w = shape[:2]
+    img = resize_image(image, (max_dim, max_dim))
+    scale = (max_dim / h, max_dim / w)
+    window = (0, 0, max_dim, max_dim)
+    mask_layers = scipy.ndimage.zoom(mask_layers, zoom=[scale[0], scale[1], 1, 1], order=0)
+    if augment and random.randint(0, 1):
+        img = np.fliplr(img)
+        mask_layers = np.fliplr(mask_layers)
+    amodal = np.sum(mask_layers, axis=2)
+    boxes = np.zeros([amodal.shape[-1], 4], dtype=np.int32)
+    for i in range(amodal.shape[-1]):
+        m = amodal[:, :, i]
+        hz = np.where(np.any(m, axis=0))[0]
+        vt = np.where(np.any(m, axis=1))[0]
+        if hz.shape[0]:
+            x1, x2 = hz[[0, -1]]
+            y1, y2 = vt[[0, -1]]
+            x2 += 1
+            y2 += 1
+        else:
+            x1, x2, y1, y2 = 0, 0, 0, 0
+        box = np.array([y1, x1, y2, x2]) + (np.random.rand(4) * 2 - 1) * (y2 - y1, x2 - x1, y2 - y1, x2 - x1) / 15
+        box[box < 0] = 0
+        boxes[i] = box
+    meta = np.array([image_id] + list(shape) + list(window) + [1] * 128)
+    return img, meta, np.ones(n, np.int32), boxes.astype(np.int32), (np.swapaxes(mask_layers, 2, 3) > 0).astype(np.uint8)

@@ -42,6 +42,7 @@ def install(model_module=None, functions_module=None, modals_module=None, datase
         bind(mod, "detection_target_layer", targets.detection_target_layer)
         bind(mod, "bbox_overlaps", targets.bbox_overlaps)
         bind(mod, "build_rpn_targets", targets.build_rpn_targets)
+        bind(mod, "load_image_gt", targets.load_image_gt)                     # model.py:80 looks it up in its own globals
         bind(mod, "pyramid_roi_align_image", pyramid.pyramid_roi_align_image)
     for mod in (modals_module, model_module):
         bind(mod, "pyramid_roi_align", pyramid.pyramid_roi_align)

@@ -35,8 +35,9 @@ def load_layer2(dataset, image_id, config):
     """Same contract as AmodalDataset.load_layer2 (amodal_train.py:236-271): reads the image's
     `<path>.npz['layer']`, returns (mask_layers bool [H,W,L,n_obj], class_ids int32 [n_obj]) as
     numpy arrays; falls through to dataset.load_mask's empty result when no object decodes."""
+    from . import npz
     image_info = dataset.image_info[image_id]
-    layer = np.load(image_info['path'][:-4] + '.npz')['layer']
+    layer = npz.load_layer_label(image_info['path'][:-4] + '.npz')       # inflate into pinned memory, asynchronous copy
     planes, n_obj = decode_layers(layer, config.NUM_CLASSES, n_max=32)
     n = int(n_obj[0].item())
     if n == 0:

@@ -184,6 +184,18 @@ def build_rpn_targets(image_shape, anchors, gt_class_ids, gt_boxes, config, devi
     return rpn_match, rpn_bbox
 
 
+def _jitter_boxes(tight):
+    """utils.extract_bboxes :51-53 on tight boxes [N,4]: jitter each by +-1/15 of its side with `np.random.rand(4)` drawn per
+    instance from the global numpy generator in the reference's order, negatives clipped to 0, truncated to int32."""
+    boxes = np.zeros([tight.shape[0], 4], dtype=np.int32)
+    for i in range(tight.shape[0]):
+        y1, x1, y2, x2 = (int(v) for v in tight[i])
+        box = np.array([y1, x1, y2, x2]) + (np.random.rand(4) * 2 - 1) * (y2 - y1, x2 - x1, y2 - y1, x2 - x1) / 15
+        box[box < 0] = 0
+        boxes[i] = box
+    return boxes.astype(np.int32)
+
+
 def extract_bboxes(mask):
     """Drop-in for utils.extract_bboxes (utils.py:28-54).  mask [H,W,N] (numpy, like the reference) or a CUDA tensor of
     planes [N,H,W] (what sem_dist_targets / decode_layers leave on the device: no trip of the masks through the host).
@@ -194,13 +206,67 @@ def extract_bboxes(mask):
     else:
         planes = mask
     tight = ops.plane_bboxes_device(planes).cpu().numpy().reshape(-1, 4)
-    boxes = np.zeros([tight.shape[0], 4], dtype=np.int32)
-    for i in range(tight.shape[0]):
-        y1, x1, y2, x2 = (int(v) for v in tight[i])
-        box = np.array([y1, x1, y2, x2]) + (np.random.rand(4) * 2 - 1) * (y2 - y1, x2 - x1, y2 - y1, x2 - x1) / 15
-        box[box < 0] = 0
-        boxes[i] = box
-    return boxes.astype(np.int32)
+    return _jitter_boxes(tight)
+
+
+def compose_image_meta(image_id, image_shape, window, active_class_ids):
+    """modal/Functions.py:612-630: [image_id] + shape (3) + window (4) + active_class_ids as one 1-D array."""
+    return np.array([image_id] + list(image_shape) + list(window) + list(active_class_ids))
+
+
+def load_image_gt(dataset, config, image_id, augment=False, use_mini_mask=False, device=False):
+    """Drop-in for load_image_gt (modal/Functions.py:675-736), the per-image ground-truth loader of the training set
+    (model.py:80), with the geometry on the device:
+      * the label map `<path>.npz['layer']` is inflated into pinned memory and copied asynchronously (npz.py), decoded into
+        the [n, L, H, W] visibility planes by sln_layer_decode -- what AmodalDataset.load_layer2 (amodal_train.py:236-271)
+        builds with one full-image compare per (object, label piece);
+      * utils.resize_image (Pillow-exact 8-bit bilinear, sln_resize_image_u8), utils.resize_layer + the horizontal flip
+        (one gather launch reproducing scipy.ndimage.zoom(order=0), sln_gather_planes);
+      * the amodal box of an instance = the union of its layers' tight boxes (sln_plane_bboxes; np.sum(mask_layers, 2)
+        + np.any in the reference, :718-720), jittered by utils.extract_bboxes' np.random.rand draws in the same order.
+    Same draws from the same generators as the reference (`random.randint(0, 1)` only when augment, then 4 numbers of
+    `np.random.rand` per instance), so a seeded run returns the reference's values: (image u8 [D,D,3], image_meta,
+    class_ids int32 [n], bbox int32 [n,4], mask_layers u8 [D,D,n,L]).  device=True keeps the planes as a CUDA tensor
+    [n, L, D, D] (what detection_target_layer's mask-target crop reads) instead of the reference's numpy layout.
+    use_mini_mask: the reference's shipped configuration is False (config.py:90) and utils.minimize_mask cannot take the
+    4-D layer array it is handed (:726-727), so True raises here instead of failing inside imresize."""
+    import random
+    from . import npz, semdist
+    if use_mini_mask:
+        raise ValueError("use_mini_mask=True is not supported: the reference's own minimize_mask cannot process the layer masks "
+                         "(modal/Functions.py:726-727, config.py:90 ships False)")
+    image = dataset.load_image(image_id)
+    info = dataset.image_info[image_id]
+    label = npz.load_layer_label(info['path'][:-4] + '.npz')
+    planes, n_obj = semdist.decode_layers(label, config.NUM_CLASSES, n_max=32)
+    n = int(n_obj[0].item())
+    if n == 0:
+        # no object decodes: the reference's load_layer2 returns utils.Dataset's empty mask here and load_image_gt then
+        # fails inside scipy.ndimage.zoom (a 4-element zoom on a 3-D array)
+        raise RuntimeError("image %r has no decodable instance: the reference's load_image_gt cannot process it either "
+                           "(utils.resize_layer expects [H,W,L,n])" % (image_id,))
+    class_ids = np.ones(n, dtype=np.int32)                               # amodal_train.py:262
+    shape = image.shape
+    image, window, scale, padding = resize_image(image, min_dim=config.IMAGE_MIN_DIM, max_dim=config.IMAGE_MAX_DIM,
+                                                 padding=config.IMAGE_PADDING)
+    flip = bool(random.randint(0, 1)) if augment else False              # :712-715
+    if flip:
+        image = np.fliplr(image)
+    planes = resize_layer_device(planes[0, :n], scale, flip=flip)        # [n, L, D, D]
+    per_layer = ops.plane_bboxes_device(planes).cpu().numpy()            # [n, L, 4], zeros for an empty plane
+    tight = np.zeros((n, 4), np.int64)
+    for i in range(n):
+        live = per_layer[i][per_layer[i][:, 2] > 0]
+        if live.shape[0]:
+            tight[i] = (live[:, 0].min(), live[:, 1].min(), live[:, 2].max(), live[:, 3].max())
+    bbox = _jitter_boxes(tight)
+    active_class_ids = np.zeros([128], dtype=np.int32)
+    active_class_ids[range(128)] = 1
+    image_meta = compose_image_meta(image_id, shape, window, active_class_ids)
+    if device:
+        return image, image_meta, class_ids, bbox, planes
+    mask_layers = planes.permute(2, 3, 0, 1).contiguous().cpu().numpy()   # np.swapaxes(mask_layers, 2, 3) > 0 as uint8
+    return image, image_meta, class_ids, bbox, mask_layers
 
 
 def zoom_index_map(n_in, n_out):

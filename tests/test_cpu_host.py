@@ -256,3 +256,25 @@ def test_refine_detections_has_no_cpu_path():
 
     with pytest.raises(RuntimeError):
         refine_detections(torch.zeros(3, 4), torch.zeros(3, 2), torch.zeros(3, 2, 4), (0, 0, 1, 1), Cfg())
+
+
+def test_npz_reader_is_bit_identical_to_numpy(tmp_path):
+    """npz.read_member (zip member inflated straight into one host buffer) against np.load: stored and deflated archives,
+    C and Fortran order, the uint64 label maps (as int64 bit patterns) and an ordinary dtype"""
+    from sln_amodal_b200 import npz
+    rng = np.random.default_rng(3)
+    label = rng.integers(0, 2 ** 63, (37, 53), dtype=np.uint64) | (np.uint64(1) << np.uint64(63))
+    other = rng.standard_normal((5, 7, 3)).astype(np.float32)
+    for k, save in enumerate((np.savez, np.savez_compressed)):
+        p = str(tmp_path / ("a%d.npz" % k))
+        save(p, layer=label, other=other, f=np.asfortranarray(label))
+        ref = np.load(p)
+        got = npz.read_member(p, "layer", pinned=False)
+        assert got.dtype == torch.int64 and np.array_equal(got.numpy().view(np.uint64), ref["layer"])
+        assert np.array_equal(npz.read_member(p, "other", pinned=False).numpy(), ref["other"])
+        assert np.array_equal(npz.read_member(p, "f", pinned=False).numpy().view(np.uint64), ref["f"])
+        assert np.array_equal(npz.load_layer_label(p, device="cpu").numpy().view(np.uint64), ref["layer"])
+    with pytest.raises(TypeError):
+        npz.load_layer_label(p, device="cpu", name="other")
+    with pytest.raises(KeyError):
+        npz.read_member(p, "missing", pinned=False)

@@ -323,3 +323,69 @@ def test_resize_image_oracle_matches_reference_resize_image():
     g = np.load(os.path.join(G, "resize_image.npz"))
     assert np.array_equal(oracle.resize_image(g["image"], (64, 64)), g["resized"])
     assert tuple(g["window"]) == (0, 0, 64, 64) and np.allclose(g["scale"], (64 / 75, 64 / 50))
+
+
+# --------------------------------------------------------------------------- load_image_gt (section 8(f)-2 glue)
+class _FakeDataset:
+    """the two members load_image_gt touches (modal/Functions.py:697-699): image_info[...]['path'] and load_image"""
+
+    def __init__(self, path, image):
+        self.image_info = [{"path": path, "height": image.shape[0], "width": image.shape[1], "id": 0}]
+        self._image = image
+
+    def load_image(self, image_id):
+        return self._image
+
+
+class _GtCfg:
+    IMAGE_PADDING = True
+    USE_MINI_MASK = False
+    MINI_MASK_SHAPE = (56, 56)
+
+
+def _loadgt_cases():
+    g = np.load(os.path.join(G, "load_image_gt.npz"))
+    for i in range(int(g["n_cases"])):
+        shape = tuple(g["masks_shape%d" % i])
+        masks = np.unpackbits(g["masks%d" % i])[: int(np.prod(shape))].reshape(shape)
+        yield i, g, masks
+
+
+def test_oracle_load_image_gt_matches_reference():
+    """the numpy restatement of load_image_gt reproduces what the reference's own function returned (same seeds)"""
+    for i, g, masks in _loadgt_cases():
+        img, meta, cls, bbox, m = oracle.load_image_gt(g["label%d" % i], g["image_in%d" % i], int(g["num_classes%d" % i]),
+                                                       int(g["max_dim"]), bool(g["augment%d" % i]), int(g["seed%d" % i]))
+        assert np.array_equal(img, g["image%d" % i]), i
+        assert np.array_equal(meta, g["meta%d" % i]) and np.array_equal(cls, g["class_ids%d" % i]), i
+        assert np.array_equal(bbox, g["bbox%d" % i]), i
+        assert m.dtype == np.uint8 and np.array_equal(m, masks), i
+
+
+@pytest.mark.gpu
+def test_load_image_gt_device_path_matches_reference(tmp_path):
+    """targets.load_image_gt (npz reader -> layer decode -> Pillow-exact resize -> zoom gather + flip -> plane boxes) against
+    the reference's own load_image_gt output, value for value, with the generators seeded like the reference run"""
+    import random
+    from sln_amodal_b200 import targets
+    for i, g, masks in _loadgt_cases():
+        path = str(tmp_path / ("img%d.jpg" % i))
+        np.savez_compressed(path[:-4] + ".npz", layer=g["label%d" % i])
+        ds = _FakeDataset(path, g["image_in%d" % i])
+        cfg = _GtCfg()
+        cfg.NUM_CLASSES = int(g["num_classes%d" % i])
+        cfg.IMAGE_MAX_DIM, cfg.IMAGE_MIN_DIM = int(g["max_dim"]), int(g["min_dim"])
+        random.seed(int(g["seed%d" % i]))
+        np.random.seed(int(g["seed%d" % i]))
+        img, meta, cls, bbox, m = targets.load_image_gt(ds, cfg, 0, augment=bool(g["augment%d" % i]))
+        assert isinstance(img, np.ndarray) and np.array_equal(img, g["image%d" % i]), i
+        assert np.array_equal(meta, g["meta%d" % i]) and np.array_equal(cls, g["class_ids%d" % i]), i
+        assert np.array_equal(bbox, g["bbox%d" % i]), i
+        assert m.dtype == np.uint8 and m.shape == masks.shape and np.array_equal(m, masks), i
+        # device=True: the same planes, left on the device in [n, L, H, W]
+        random.seed(int(g["seed%d" % i]))
+        np.random.seed(int(g["seed%d" % i]))
+        planes = targets.load_image_gt(ds, cfg, 0, augment=bool(g["augment%d" % i]), device=True)[4]
+        assert planes.is_cuda and np.array_equal(planes.permute(2, 3, 0, 1).cpu().numpy(), masks)
+    with pytest.raises(ValueError):
+        targets.load_image_gt(ds, cfg, 0, use_mini_mask=True)
