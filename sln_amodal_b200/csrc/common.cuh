@@ -42,7 +42,7 @@ void set_error(const char *fmt, ...);
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-int sm_count();   // cached per process, current device
+int sm_count();   // of the current device (not cached)
 
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_chain(pdl = true) may be scheduled while its

@@ -16,14 +16,13 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// SM count of the CURRENT device, asked every time (the runtime answers from its own table in well under a microsecond):
+// no process-global cache, so a process that switches devices -- or the header's "no global state" -- stays correct
 int sm_count()
 {
-    static int cached = 0;
-    if (cached > 0) return cached;
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
     return n;
 }
 

@@ -1100,7 +1100,28 @@ nms_pairs_kernel(const float4 *__restrict__ boxes, const float *__restrict__ are
 //   box b is dead   as soon as one predecessor is in KF,
 //   box b is kept   as soon as all predecessors are in DF          (no predecessors: kept at once).
 // Both rules only ever state final facts, so the sets can be read while other CTAs extend them and the fixed point
-// (every box decided) is the greedy result whatever the interleaving.  Ownership: 32-box word w belongs to CTA
+// (every box decided) is the greedy result whatever the interleaving.
+//
+// Why the reads that compute-sanitizer's racecheck flags (a warp publishing KF / DF words through DSMEM while another
+// warp reads the same words in sp_scan8, no barrier in between) cannot change the result -- the argument, in full:
+//   (1) Single writer: word w of KF and of DF is written only by the one warp that owns w (CTA w % SP_CLUSTER, a fixed
+//       warp of it), in all SP_CLUSTER copies.  A 32-bit shared-memory store is atomic, so a reader sees either the old
+//       or the new word, never a mixture.
+//   (2) Monotone: the owner only ever ORs bits in; a bit, once set, stays set in every copy.  A stale read therefore
+//       shows a SUBSET of the true sets at that instant.
+//   (3) Soundness by induction over the visiting order (the greedy NMS order, nms.c:25-67): assume every bit that is
+//       set for a box a < b is correct (a in KF => greedy keeps a; a in DF => greedy suppresses a).  Rule "dead" sets
+//       b in DF only after reading some predecessor a (IoU(a, b) >= t, a < b) in KF: greedy keeps a, so it suppresses b.
+//       Rule "kept" sets b in KF only after reading ALL predecessors in DF: greedy suppressed every box that could have
+//       suppressed b, so it keeps b.  Both conclusions need only that the bits READ were correct, which (2) and the
+//       induction hypothesis give for any subset.  KF and DF stay disjoint because a box is decided once by its owner.
+//   (4) Progress: the lowest undecided box has all its predecessors decided; after the next cluster barrier
+//       (barrier.cluster.arrive.release / wait.acquire: every copy sees every earlier store) its owner decides it.
+//       So every round decides at least one box, and the loop ends with KF = the greedy survivors exactly.  Early
+//       visibility between barriers can only decide boxes SOONER (fewer rounds), never differently.
+//   (5) The sentinel word 2047 (bit 31 clear in KF, set in DF) is written once before the first barrier and never again.
+// tests/test_gpu_parity.py::test_nms_sparse_resolve_is_interleaving_independent repeats the same inputs a few hundred
+// times (the hardware interleaving differs from launch to launch) and demands identical survivors every time.  Ownership: 32-box word w belongs to CTA
 // w % SP_CLUSTER, one warp per word, lane = box; the warp builds the word's new bits with ballots and stores the
 // updated words into all SP_CLUSTER copies through DSMEM.  One hardware cluster barrier per round; a box costs work only while it is undecided, and its inline
 // predecessor row sits in the owner's shared memory (one coalesced 32-byte load per box).

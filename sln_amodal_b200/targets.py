@@ -28,38 +28,68 @@ def box_refinement(box, gt_box):
 def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
     """proposals [1,N,4] normalised, gt_class_ids [1,G], gt_boxes [1,G,4] normalised, gt_masks [1,L,G,H,W]
     -> (rois [R,4], roi_gt_class_ids [R], deltas [R,4], masks [R,L,mh,mw]); empty tensors when nothing is sampled
-    (Functions.py:223-416, batch 1 like the reference)."""
+    (Functions.py:223-416, batch 1 like the reference).
+
+    Host round trips: the reference pays one per `if tensor.size()` / `nonzero` (about ten per image).  Here the
+    per-proposal decisions (positive / negative, one byte each) come back in ONE copy together with the class ids; the
+    index selection and the reference's `torch.randperm` draws (CPU generator, same sizes in the same order, so a seeded
+    run samples the same ROIs) happen on the host, and the chosen indices go back in one copy."""
     dev = proposals.device
     proposals = proposals.squeeze(0).float().contiguous()
-    gt_class_ids = gt_class_ids.squeeze(0).to(dev)
+    gt_class_ids = gt_class_ids.squeeze(0)
     gt_boxes = gt_boxes.squeeze(0).float().to(dev)
     gt_masks = gt_masks.squeeze(0)
     n = proposals.shape[0]
+    G = gt_class_ids.shape[0]
 
-    if bool((gt_class_ids < 0).any()):                                        # COCO crowds, :253-267
-        crowd_ix = torch.nonzero(gt_class_ids < 0)[:, 0]
-        non_crowd_ix = torch.nonzero(gt_class_ids > 0)[:, 0]
+    # overlaps [proposals, gt_boxes] reduced on the fly: row maximum and its (first) index, :274-277, :297 -- launched for
+    # the common case of no crowd boxes before the class ids are known on the host
+    _, roi_iou_max, roi_argmax = ops.bbox_overlaps_device(proposals, gt_boxes, matrix=False, reduce=True)
+    codes = (roi_iou_max >= 0.5).to(torch.uint8)
+    if gt_class_ids.is_cuda:
+        packed = torch.cat([codes, gt_class_ids.to(torch.int32).view(torch.uint8)]).cpu().numpy()      # the one sync
+        codes_h, cls_h = packed[:n], packed[n:].view(np.int32)
+    else:
+        cls_h = gt_class_ids.to(torch.int32).numpy()
+        codes_h = None
+    gt_class_ids = gt_class_ids.to(dev)
+    no_crowd_h = np.ones(n, dtype=bool)
+    if (cls_h < 0).any():                                                     # COCO crowds, :253-267 (rare: redo without them)
+        crowd_ix = torch.from_numpy(np.nonzero(cls_h < 0)[0]).to(dev)
+        non_crowd_ix = torch.from_numpy(np.nonzero(cls_h > 0)[0]).to(dev)
         crowd_boxes = gt_boxes[crowd_ix]
         gt_class_ids = gt_class_ids[non_crowd_ix]
         gt_boxes = gt_boxes[non_crowd_ix]
         gt_masks = gt_masks[:, non_crowd_ix.to(gt_masks.device)]
         _, crowd_iou_max, _ = ops.bbox_overlaps_device(proposals, crowd_boxes, matrix=False, reduce=True)
-        no_crowd_bool = crowd_iou_max < 0.001
-    else:
-        no_crowd_bool = torch.ones(n, dtype=torch.bool, device=dev)
+        _, roi_iou_max, roi_argmax = ops.bbox_overlaps_device(proposals, gt_boxes, matrix=False, reduce=True)
+        both = torch.stack([(roi_iou_max >= 0.5), (crowd_iou_max < 0.001)]).to(torch.uint8).cpu().numpy()
+        codes_h, no_crowd_h = both[0], both[1].astype(bool)
+    elif codes_h is None:
+        codes_h = codes.cpu().numpy()
+    positive_h = codes_h.astype(bool)
+    negative_h = ~positive_h & no_crowd_h                                     # :351-352
 
-    # overlaps [proposals, gt_boxes] reduced on the fly: row maximum and its (first) index, :274-277, :297
-    _, roi_iou_max, roi_argmax = ops.bbox_overlaps_device(proposals, gt_boxes, matrix=False, reduce=True)
-    positive_roi_bool = roi_iou_max >= 0.5
     L = gt_masks.shape[0]
     mh, mw = int(config.MASK_SHAPE[0]), int(config.MASK_SHAPE[1])
-    positive_count = 0
-    if bool(positive_roi_bool.any()):
-        positive_indices = torch.nonzero(positive_roi_bool)[:, 0]
+    positive_count = negative_count = 0
+    pos_sel = neg_sel = None
+    if positive_h.any():                                                      # :281-291
+        positive_indices = np.nonzero(positive_h)[0]
         want = int(config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO)
-        rand_idx = torch.randperm(positive_indices.shape[0])[:want].to(dev)   # CPU generator, like the reference
-        positive_indices = positive_indices[rand_idx]
-        positive_count = positive_indices.shape[0]
+        rand_idx = torch.randperm(positive_indices.shape[0])[:want].numpy()   # CPU generator, like the reference
+        pos_sel = positive_indices[rand_idx]
+        positive_count = pos_sel.shape[0]
+    if positive_count > 0 and negative_h.any():                               # :353-366
+        negative_indices = np.nonzero(negative_h)[0]
+        r = 1.0 / config.ROI_POSITIVE_RATIO
+        negative_count = int(r * positive_count - positive_count)
+        rand_idx = torch.randperm(negative_indices.shape[0])[:negative_count].numpy()
+        neg_sel = negative_indices[rand_idx]
+        negative_count = neg_sel.shape[0]
+    if positive_count > 0:
+        sel = torch.from_numpy(np.concatenate([pos_sel, neg_sel]) if negative_count > 0 else pos_sel).to(dev)
+        positive_indices = sel[:positive_count]
         positive_rois = proposals[positive_indices]
         assignment = roi_argmax[positive_indices].long()
         roi_gt_boxes = gt_boxes[assignment]
@@ -80,17 +110,8 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
             crop = CropAndResizeFunction(mh, mw, 0)
             masks = torch.stack([crop(roi_masks[i].unsqueeze(1).float(), boxes, box_ids).detach() for i in range(L)], dim=1)
             masks = torch.round(masks.squeeze(2))                             # :346
-
-    negative_roi_bool = (roi_iou_max < 0.5) & no_crowd_bool                   # :351-352
-    negative_count = 0
-    if positive_count > 0 and bool(negative_roi_bool.any()):
-        negative_indices = torch.nonzero(negative_roi_bool)[:, 0]
-        r = 1.0 / config.ROI_POSITIVE_RATIO
-        negative_count = int(r * positive_count - positive_count)
-        rand_idx = torch.randperm(negative_indices.shape[0])[:negative_count].to(dev)
-        negative_indices = negative_indices[rand_idx]
-        negative_count = negative_indices.shape[0]
-        negative_rois = proposals[negative_indices]
+        if negative_count > 0:
+            negative_rois = proposals[sel[positive_count:]]
 
     if positive_count > 0 and negative_count > 0:                             # :370-384
         rois = torch.cat((positive_rois, negative_rois), dim=0)
