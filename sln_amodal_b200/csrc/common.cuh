@@ -142,10 +142,62 @@ __device__ __forceinline__ float lerp2v(float tl, float tr, float bl, float br, 
 {
     return lerp2(tl, tr, bl, br, xl, yl);
 }
+// ---------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, PTX .f32x2): two IEEE-rounded fp32 operations per instruction, each
+// half rounded exactly like the scalar instruction.  The bit-parity kernels need the reference's UN-fused sequence
+// (every multiply and add rounded on its own, crop_and_resize.c:102-106), and ptxas (12.9) contracts mul.rn.f32x2 +
+// add.rn.f32x2 into one FFMA2 -- unlike the scalar mul.rn / add.rn pair, which it never fuses; it even sees through
+// fma.rn.f32x2(a, b, -0.0) as a product and contracts that (checked in SASS).  So in the un-fused kernels only the
+// subtraction and the addition are packed and the product stays two scalar mul.rn.f32: 4 instructions per pair of
+// lerps instead of 6.  Where fusing is the defined behaviour (the backward's default mode) FFMA2 is used as it is.
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add2_rn(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t sub2_rn(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// a + (b - a) * w on a pair, each operation rounded on its own (the reference's sequence): FADD2, 2 x FMUL, FADD2
+__device__ __forceinline__ f32x2_t lerp_pair(f32x2_t a, f32x2_t b, float w)
+{
+    float d0, d1;
+    unpk2(sub2_rn(b, a), d0, d1);
+    return add2_rn(a, pk2(__fmul_rn(d0, w), __fmul_rn(d1, w)));
+}
+
 __device__ __forceinline__ float4 lerp2v(float4 tl, float4 tr, float4 bl, float4 br, float xl, float yl)
 {
-    return make_float4(lerp2(tl.x, tr.x, bl.x, br.x, xl, yl), lerp2(tl.y, tr.y, bl.y, br.y, xl, yl),
-                       lerp2(tl.z, tr.z, bl.z, br.z, xl, yl), lerp2(tl.w, tr.w, bl.w, br.w, xl, yl));
+    // 24 instructions instead of 36 per float4, same bits as lerp2() on every component
+    const f32x2_t top0 = lerp_pair(pk2(tl.x, tl.y), pk2(tr.x, tr.y), xl), top1 = lerp_pair(pk2(tl.z, tl.w), pk2(tr.z, tr.w), xl);
+    const f32x2_t bot0 = lerp_pair(pk2(bl.x, bl.y), pk2(br.x, br.y), xl), bot1 = lerp_pair(pk2(bl.z, bl.w), pk2(br.z, br.w), xl);
+    const f32x2_t r0 = lerp_pair(top0, bot0, yl), r1 = lerp_pair(top1, bot1, yl);
+    float4 r;
+    unpk2(r0, r.x, r.y);
+    unpk2(r1, r.z, r.w);
+    return r;
 }
 
 }  // namespace sln

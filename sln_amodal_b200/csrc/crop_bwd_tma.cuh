@@ -107,7 +107,12 @@ __device__ __forceinline__ float4 term(float4 a, float4 g, float w, float wy, fl
         return make_float4(__fadd_rn(a.x, __fmul_rn(wx, __fmul_rn(wy, g.x))), __fadd_rn(a.y, __fmul_rn(wx, __fmul_rn(wy, g.y))),
                            __fadd_rn(a.z, __fmul_rn(wx, __fmul_rn(wy, g.z))), __fadd_rn(a.w, __fmul_rn(wx, __fmul_rn(wy, g.w))));
     }
-    return make_float4(__fmaf_rn(w, g.x, a.x), __fmaf_rn(w, g.y, a.y), __fmaf_rn(w, g.z, a.z), __fmaf_rn(w, g.w, a.w));
+    // one fma per component, two components per instruction (FFMA2: each half rounded like the scalar fma)
+    const f32x2_t ww = pk2(w, w);
+    float4 r;
+    unpk2(fma2_rn(ww, pk2(g.x, g.y), pk2(a.x, a.y)), r.x, r.y);
+    unpk2(fma2_rn(ww, pk2(g.z, g.w), pk2(a.z, a.w)), r.z, r.w);
+    return r;
 }
 
 // acc[K] += weight * g for a warp-uniform, run-time K: a switch over statically indexed registers

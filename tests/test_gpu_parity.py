@@ -1135,3 +1135,63 @@ def test_unmold_and_resize_match_reference_fixtures():
     r = np.load(os.path.join(gd, "resize_image.npz"))
     out, window, scale, padding = targets.resize_image(r["image"], max_dim=64)
     assert np.array_equal(out, r["resized"]) and window == tuple(r["window"]) and np.allclose(scale, r["scale"])
+
+
+
+# --------------------------------------------------------------------------- the head path replayed from a CUDA graph
+class _GraphCfg:
+    IMAGE_SHAPE = np.array([1024, 1024, 3])
+    RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    RPN_NMS_THRESHOLD = 0.7
+    POOL_SIZE = 7
+    MASK_POOL_SIZE = 14
+    USE_NMS = False
+    DETECTION_MIN_CONFIDENCE = 0.0
+    DETECTION_NMS_THRESHOLD = 0.3
+    DETECTION_MAX_INSTANCES = 100
+
+
+def test_head_graph_replay_equals_the_eager_drop_ins():
+    """pipeline.HeadGraph (every step padded and sync-free, captured once, one launch per image) against the same image
+    through the reference-signature drop-ins with their host reads: proposals, classifier crops, detections and mask-head
+    crops identical below the counts; a second image through the SAME graph (inputs refreshed in place) too."""
+    from sln_amodal_b200 import pipeline, proposal_layer, pyramid_roi_align, refine_detections
+    A, K, Cc = 65472, 9, 64
+    cfg = _GraphCfg()
+    rng = np.random.default_rng(5)
+    anchors = cuda(synth.nms_boxes(A, seed=4, kind="rpn"))
+    sides = (128, 64, 32, 16)
+
+    def image(seed):
+        r = np.random.default_rng(seed)
+        fg = r.permutation(np.linspace(0, 1, A)).astype(np.float32)
+        lg = r.standard_normal((1000, K)).astype(np.float32) * 3.0
+        return {"probs": np.stack([1 - fg, fg], 1).astype(np.float32), "deltas": (r.standard_normal((A, 4)) * 0.5).astype(np.float32),
+                "cls_probs": (np.exp(lg) / np.exp(lg).sum(1, keepdims=True)).astype(np.float32),
+                "cls_deltas": (r.standard_normal((1000, K, 4)) * 0.3).astype(np.float32),
+                "maps": [r.standard_normal((1, Cc, s_, s_), dtype=np.float32) for s_ in sides]}
+
+    first = image(11)
+    st = {k: cuda(v) for k, v in first.items() if k != "maps"}
+    st["maps"] = [cuda(m).contiguous(memory_format=torch.channels_last) for m in first["maps"]]
+    graph = pipeline.HeadGraph(anchors, cfg, st["maps"], st["probs"], st["deltas"], (st["cls_probs"], st["cls_deltas"]))
+    for seed in (11, 12, 13):
+        img = image(seed)
+        for k in ("probs", "deltas", "cls_probs", "cls_deltas"):
+            st[k].copy_(cuda(img[k]))
+        for m, src in zip(st["maps"], img["maps"]):
+            m.copy_(cuda(src))
+        out = graph.replay()
+        torch.cuda.synchronize()
+        k = int(out["num_rois"].item())
+        nd = int(out["num_detections"].item())
+        rois = proposal_layer([st["probs"].unsqueeze(0).clone(), st["deltas"].unsqueeze(0).clone()], 1000, 0.7, anchors, cfg)
+        assert rois.shape[1] == k and torch.equal(rois[0], out["rois"][:k]) and not out["rois"][k:].any()
+        pooled = pyramid_roi_align([rois] + st["maps"], 7, cfg.IMAGE_SHAPE)
+        assert torch.equal(pooled, out["pooled"][:k])
+        det, keep = refine_detections(rois[0], st["cls_probs"][:k], st["cls_deltas"][:k], (0.0, 0.0, 1024.0, 1024.0), cfg)
+        assert det.shape[0] == nd and torch.equal(det, out["detections"][:nd]) and not out["detections"][nd:].any()
+        assert torch.equal(keep, out["keep"][:nd])
+        mask_in = pyramid_roi_align([(det[:, :4] / 1024.0).unsqueeze(0)] + st["maps"], 14, cfg.IMAGE_SHAPE)
+        assert torch.equal(mask_in, out["mask_pooled"][:nd])
