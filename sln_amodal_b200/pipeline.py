@@ -48,6 +48,7 @@ class HeadGraph:
         self.window = tuple(float(v) for v in (window if window is not None else (0, 0, h, w)))
         self.std_rpn = np.reshape(config.RPN_BBOX_STD_DEV, [4])
         self.out = None
+        self._bg = None
         self.graph = torch.cuda.CUDAGraph()
         self._capture()
 
@@ -57,7 +58,7 @@ class HeadGraph:
         cfg, R, D = self.cfg, self.R, self.D
         rois, num = ops.proposal_device(self.rpn_probs, self.rpn_bbox, self.anchors, R, float(cfg.RPN_NMS_THRESHOLD),
                                         self.std_rpn, self.image_hw, pre_nms_limit=PRE_NMS_LIMIT)
-        box_ind = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        box_ind = self._box_ind if self._bg is not None else torch.zeros(R, dtype=torch.int32, device=self.dev)
         level = ops.roi_levels_device(rois, self.image_hw)
         pooled = ops.pyramid_crop_forward(self.maps, rois, box_ind, level, int(cfg.POOL_SIZE), int(cfg.POOL_SIZE), 0.0)
         if callable(self.classifier):
@@ -66,17 +67,22 @@ class HeadGraph:
             probs, deltas = self.classifier
         # rows beyond the proposal count must not become detections: give them the background class (Functions.py:486-489
         # keeps only class_ids > 0)
-        valid = torch.arange(R, device=self.dev, dtype=torch.int32) < num
-        bg = torch.zeros_like(probs[:1])
-        bg[0, 0] = 1.0
-        probs = torch.where(valid[:, None], probs[:R], bg)
+        if self._bg is None:                       # constants: made in the eager warm-up pass (host -> device copies cannot be captured)
+            self._bg = torch.zeros_like(probs[:1])
+            self._bg[0, 0] = 1.0
+            h, w = self.image_hw
+            self._norm = torch.tensor([h, w, h, w], dtype=torch.float32, device=self.dev)
+            self._ar_r = torch.arange(R, device=self.dev, dtype=torch.int32)
+            self._ar_d = torch.arange(D, device=self.dev, dtype=torch.int32)
+            self._box_ind = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        valid = self._ar_r < num
+        probs = torch.where(valid[:, None], probs[:R], self._bg)
         dets, _, class_ids, n_excl = ops.refine_decode_device(rois, probs, deltas[:R], self.std_rpn, self.image_hw, self.window, 0.0)
         det, keep = ops.refine_topk_device(dets, class_ids, D)
         num_det = torch.clamp(R - n_excl, max=D)
-        rows = torch.arange(D, device=self.dev, dtype=torch.int32) < num_det
+        rows = self._ar_d < num_det
         det = torch.where(rows[:, None], det, torch.zeros_like(det))         # rows beyond num_det were never written
-        boxes = det[:, :4] / torch.tensor([self.image_hw[0], self.image_hw[1], self.image_hw[0], self.image_hw[1]],
-                                          dtype=torch.float32, device=self.dev)
+        boxes = det[:, :4] / self._norm
         lvl_d = ops.roi_levels_device(boxes, self.image_hw)
         mp = int(cfg.MASK_POOL_SIZE)
         mask_in = ops.pyramid_crop_forward(self.maps, boxes, box_ind[:D], lvl_d, mp, mp, 0.0)
