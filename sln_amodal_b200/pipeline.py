@@ -35,7 +35,7 @@ class HeadGraph:
     torch code: the model's classifier head); it may also be a pair of static tensors (probs, deltas)."""
 
     def __init__(self, anchors, config, feature_maps, rpn_probs, rpn_bbox, classifier, proposal_count=1000,
-                 max_detections=100, window=None):
+                 max_detections=100, window=None, capture=True):
         self.dev = rpn_probs.device
         self.cfg = config
         self.anchors = anchors
@@ -49,8 +49,10 @@ class HeadGraph:
         self.std_rpn = np.reshape(config.RPN_BBOX_STD_DEV, [4])
         self.out = None
         self._bg = None
-        self.graph = torch.cuda.CUDAGraph()
-        self._capture()
+        self.graph = None
+        if capture:
+            self.graph = torch.cuda.CUDAGraph()
+            self._capture()
 
     # the image's steps on the current stream, sync-free; called once eagerly (warm-up: workspaces, lazy module loads) and
     # once under capture
@@ -89,17 +91,49 @@ class HeadGraph:
         return {"rois": rois, "num_rois": num, "pooled": pooled, "detections": det, "keep": keep, "num_detections": num_det,
                 "mask_pooled": mask_in}
 
-    def _capture(self):
+    def _warm_up(self):
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(side):                     # warm-up outside the capture
+        with torch.cuda.stream(side):                     # outside the capture: workspaces, constants, lazy module loads
             self._steps()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
+
+    def _capture(self):
+        self._warm_up()
         with torch.cuda.graph(self.graph):
             self.out = self._steps()
 
     def replay(self):
         """One graph launch on the current stream; returns the static output tensors (valid until the next replay)."""
+        self.graph.replay()
+        return self.out
+
+
+class MultiHeadGraph:
+    """Several images per launch: the step chains of `heads` (HeadGraph objects built with capture=False, one per image,
+    each on its own static inputs) are captured into ONE graph as parallel branches (fork / join on side streams).  The
+    path's kernels are short and narrow -- the NMS stages are single clusters, the selects a few hundred CTAs -- so a lone
+    image leaves most of the GPU idle between dependent launches; independent images fill it.  Images never interact:
+    every branch has its own workspaces and outputs, and each image's results are those of its own HeadGraph."""
+
+    def __init__(self, heads):
+        self.heads = list(heads)
+        self.dev = self.heads[0].dev
+        for h in self.heads:
+            h._warm_up()
+        self.graph = torch.cuda.CUDAGraph()
+        streams = [torch.cuda.Stream(device=self.dev) for _ in self.heads]
+        with torch.cuda.graph(self.graph):
+            main = torch.cuda.current_stream(self.dev)
+            for h, st in zip(self.heads, streams):
+                st.wait_stream(main)                       # fork
+                with torch.cuda.stream(st):
+                    h.out = h._steps()
+            for st in streams:
+                main.wait_stream(st)                       # join
+        self.out = [h.out for h in self.heads]
+
+    def replay(self):
         self.graph.replay()
         return self.out

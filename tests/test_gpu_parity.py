@@ -1195,3 +1195,37 @@ def test_head_graph_replay_equals_the_eager_drop_ins():
         assert torch.equal(keep, out["keep"][:nd])
         mask_in = pyramid_roi_align([(det[:, :4] / 1024.0).unsqueeze(0)] + st["maps"], 14, cfg.IMAGE_SHAPE)
         assert torch.equal(mask_in, out["mask_pooled"][:nd])
+
+
+def test_multi_head_graph_images_do_not_interact():
+    """pipeline.MultiHeadGraph: three images as parallel branches of one graph; every image's outputs equal those of its
+    own single-image graph (same kernels, own workspaces)."""
+    from sln_amodal_b200 import pipeline
+    A, K, Cc = 65472, 9, 64
+    cfg = _GraphCfg()
+    anchors = cuda(synth.nms_boxes(A, seed=4, kind="rpn"))
+    sides = (128, 64, 32, 16)
+    sets = []
+    for seed in (21, 22, 23):
+        r = np.random.default_rng(seed)
+        fg = r.permutation(np.linspace(0, 1, A)).astype(np.float32)
+        lg = r.standard_normal((1000, K)).astype(np.float32) * 3.0
+        sets.append({"probs": cuda(np.stack([1 - fg, fg], 1).astype(np.float32)), "deltas": cuda((r.standard_normal((A, 4)) * 0.5).astype(np.float32)),
+                     "cls": (cuda((np.exp(lg) / np.exp(lg).sum(1, keepdims=True)).astype(np.float32)),
+                             cuda((r.standard_normal((1000, K, 4)) * 0.3).astype(np.float32))),
+                     "maps": [cuda(r.standard_normal((1, Cc, s_, s_), dtype=np.float32)).contiguous(memory_format=torch.channels_last) for s_ in sides]})
+    singles = [pipeline.HeadGraph(anchors, cfg, d["maps"], d["probs"], d["deltas"], d["cls"]) for d in sets]
+    want = []
+    for g in singles:
+        o = g.replay()
+        torch.cuda.synchronize()
+        want.append({k: v.clone() for k, v in o.items()})
+    multi = pipeline.MultiHeadGraph([pipeline.HeadGraph(anchors, cfg, d["maps"], d["probs"], d["deltas"], d["cls"], capture=False) for d in sets])
+    for _ in range(3):
+        outs = multi.replay()
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        k, nd = int(w["num_rois"].item()), int(w["num_detections"].item())
+        assert int(o["num_rois"].item()) == k and int(o["num_detections"].item()) == nd
+        assert torch.equal(o["rois"], w["rois"]) and torch.equal(o["pooled"][:k], w["pooled"][:k])
+        assert torch.equal(o["detections"], w["detections"]) and torch.equal(o["mask_pooled"][:nd], w["mask_pooled"][:nd])
