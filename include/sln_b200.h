@@ -280,7 +280,13 @@ SLN_API int sln_layer_decode(const uint64_t *label, int B, int H, int W, int L, 
 
 /* Exact squared Euclidean distance transform (absent from the reference; see
  * DESIGN.md): maps u8 [M,H,W] -> out i32 [M,H,W] = squared distance to the nearest
- * ZERO pixel of the same map, (H+W)^2 where a map has no zero pixel.               */
+ * ZERO pixel of the same map, (H+W)^2 where a map has no zero pixel.
+ * Shapes with W % 32 == 0, W <= 1024, H <= 2048 and 16-byte aligned pointers take the
+ * banded kernels (lower envelopes per 32-row band, no row-distance buffer; workspace:
+ * 34 u32 stack slots per 32 rows + two words per (band, column) + a tile list, about
+ * 4.5 bytes per pixel, contents undefined before and after the call); every other
+ * shape takes the row pass + whole-column envelope kernels.  The environment variable
+ * SLN_EDT_IMPL=legacy forces the latter (A/B).                                      */
 SLN_API size_t sln_edt_workspace_bytes(int M, int H, int W);
 SLN_API int sln_edt_sq(const uint8_t *maps, int M, int H, int W, int32_t *out,
                void *workspace, size_t workspace_bytes, void *stream);
