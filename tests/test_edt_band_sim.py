@@ -92,3 +92,22 @@ def test_band_sim_random_unions(sim):
         if it % 7 == 0:
             m = 1 - m
         assert np.array_equal(sim(m), oracle.edt_sq(m)), it
+
+
+def test_band_sim_field_limits_and_long_chains(sim):
+    """Row distances up to 1023 (W = 1024, one zero column), a single zero in the far corner (every other band has no
+    site at all and only passes the search on: the longest chain of look-ups), rows up to 2047 (H = 2048: the 11-bit
+    entry fields at their limit) on a thin map."""
+    m = np.ones((256, 1024), np.uint8)
+    m[:, 0] = 0
+    assert np.array_equal(sim(m), oracle.edt_sq(m))
+    m = np.ones((512, 1024), np.uint8)
+    m[511, 1023] = 0
+    assert np.array_equal(sim(m), oracle.edt_sq(m))
+    m = np.ones((2048, 64), np.uint8)
+    m[2047, 63] = 0
+    assert np.array_equal(sim(m), oracle.edt_sq(m))
+    m = np.ones((2048, 32), np.uint8)
+    m[0, 0] = 0
+    m[1000:1003, 5:9] = 0
+    assert np.array_equal(sim(m), oracle.edt_sq(m))

@@ -714,6 +714,41 @@ def test_edt_bit_exact():
     assert np.all(ops.edt_sq_device(cuda(full)).cpu().numpy() == (9 + 12) ** 2)
 
 
+def test_edt_banded_shapes_and_field_limits():
+    """The banded kernels at the edges of their contract: the tallest / widest map the packed entries allow (2048 x 1024:
+    s and t up to 2047, g up to 1023), a cut last band (H % 32 != 0), a single band, one segment, and maps whose runs
+    cross every band (columns of foreground from top to bottom next to far-away zeros) -- bit-exact against the oracle,
+    and identical to the round-1 whole-column kernels (SLN_EDT_IMPL=legacy) on the same input."""
+    import os
+    from sln_amodal_b200 import ops
+    rng = np.random.default_rng(91)
+    cases = []
+    m = np.ones((2048, 1024), np.uint8)
+    m[:, 0] = 0                                              # row distances up to 1023, no zero above / below anywhere
+    cases.append(m)
+    m = np.ones((2048, 1024), np.uint8)
+    m[2047, 1023] = 0                                        # one zero in the far corner: distances up to 2047^2 + 1023^2
+    cases.append(m)
+    m = (rng.random((2048, 1024)) < 0.9995).astype(np.uint8)
+    cases.append(m)
+    yy, xx = np.mgrid[0:2048, 0:1024]
+    cases.append((((yy - 1000) / 990.0) ** 2 + ((xx - 500) / 480.0) ** 2 <= 1.0).astype(np.uint8))
+    for H, W in ((1, 32), (31, 64), (33, 32), (95, 96), (250, 1024)):
+        a = (rng.random((H, W)) < 0.97).astype(np.uint8)
+        b = np.ones((H, W), np.uint8)
+        b[rng.integers(0, H), rng.integers(0, W)] = 0
+        cases += [a, b, np.ones((H, W), np.uint8)]
+    for m in cases:
+        got = ops.edt_sq_device(cuda(m[None])).cpu().numpy()[0]
+        assert np.array_equal(got, oracle.edt_sq(m)), m.shape
+        os.environ["SLN_EDT_IMPL"] = "legacy"
+        try:
+            old = ops.edt_sq_device(cuda(m[None])).cpu().numpy()[0]
+        finally:
+            os.environ.pop("SLN_EDT_IMPL", None)
+        assert np.array_equal(got, old), m.shape
+
+
 @pytest.mark.parametrize("L", [1, 2, 4])
 def test_edt_config4_planes_bit_exact(L):
     """BASELINE config 4 on the 1024^2 path the bench times: the planes of the four distinct label maps of the bench
