@@ -37,5 +37,9 @@ ops.proposal_device(probs, dl, an, 300, 0.7, (0.1, 0.1, 0.2, 0.2), (1024, 1024),
 # layer decode + EDT (packed path needs W >= 128)
 lab = synth.label_map(160, 256, n=6, seed=5, min_piece=16)
 sem_dist_targets(lab, 3, n_max=6)
+# banded EDT kernels: cut last band, single segment, all foreground (runs through every band), noise
+rng_e = np.random.default_rng(9)
+for shp, p in (((70, 96), 0.97), ((40, 64), 2.0), ((33, 32), 0.5), ((130, 1024), 0.999)):
+    ops.edt_sq_device(torch.from_numpy((rng_e.random(shp) < p).astype(np.uint8)[None]).to(dev))
 torch.cuda.synchronize()
 print("sanitize_small done")
