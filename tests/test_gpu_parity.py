@@ -1264,3 +1264,44 @@ def test_multi_head_graph_images_do_not_interact():
         assert int(o["num_rois"].item()) == k and int(o["num_detections"].item()) == nd
         assert torch.equal(o["rois"], w["rois"]) and torch.equal(o["pooled"][:k], w["pooled"][:k])
         assert torch.equal(o["detections"], w["detections"]) and torch.equal(o["mask_pooled"][:nd], w["mask_pooled"][:nd])
+
+
+def test_head_graph_with_a_classifier_module_inside_the_capture():
+    """HeadGraph with a torch module as the classifier callback (the place of the model's own head): the module runs inside
+    the capture on the pooled crops; detections equal the eager sequence proposal_layer -> pyramid_roi_align -> the same
+    module -> refine_detections."""
+    from sln_amodal_b200 import pipeline, proposal_layer, pyramid_roi_align, refine_detections
+    A, K, Cc = 65472, 5, 32
+    cfg = _GraphCfg()
+    torch.manual_seed(3)
+    anchors = cuda(synth.nms_boxes(A, seed=4, kind="rpn"))
+    r = np.random.default_rng(31)
+    fg = r.permutation(np.linspace(0, 1, A)).astype(np.float32)
+    probs, deltas = cuda(np.stack([1 - fg, fg], 1).astype(np.float32)), cuda((r.standard_normal((A, 4)) * 0.5).astype(np.float32))
+    maps = [cuda(r.standard_normal((1, Cc, s_, s_), dtype=np.float32)).contiguous(memory_format=torch.channels_last) for s_ in (128, 64, 32, 16)]
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(Cc, 16, 7)
+            self.cls = torch.nn.Linear(16, K)
+            self.box = torch.nn.Linear(16, 4 * K)
+
+        def forward(self, pooled, rois):
+            x = torch.relu(self.conv(pooled)).flatten(1)
+            return torch.softmax(self.cls(x), dim=1), self.box(x).view(-1, K, 4) * 0.1
+
+    head = Head().to(dev()).eval()
+    with torch.no_grad():
+        graph = pipeline.HeadGraph(anchors, cfg, maps, probs, deltas, head)
+        out = graph.replay()
+        torch.cuda.synchronize()
+        k, nd = int(out["num_rois"].item()), int(out["num_detections"].item())
+        rois = proposal_layer([probs.unsqueeze(0).clone(), deltas.unsqueeze(0).clone()], 1000, 0.7, anchors, cfg)
+        assert rois.shape[1] == k
+        pooled = pyramid_roi_align([rois] + maps, 7, cfg.IMAGE_SHAPE)
+        # the module sees the padded batch inside the graph; rows are independent, so the first k match a k-row call
+        p_e, d_e = head(out["pooled"], out["rois"])
+        det, keep = refine_detections(rois[0], p_e[:k], d_e[:k], (0.0, 0.0, 1024.0, 1024.0), cfg)
+    assert torch.equal(pooled, out["pooled"][:k])
+    assert det.shape[0] == nd and torch.equal(det, out["detections"][:nd]) and torch.equal(keep, out["keep"][:nd])
