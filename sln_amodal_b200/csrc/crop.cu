@@ -331,6 +331,7 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
                                         BwdLevel *__restrict__ lv_table, int *__restrict__ queue, int queue_init,
                                         int *__restrict__ gid)
 {
+    pdl_prologue();          // the prep launches and the main kernel are a chain of programmatic dependents (common.cuh)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
     if (r == 0) *queue = queue_init;                 // ticket counter of the bulk-async kernel
@@ -381,6 +382,7 @@ crop_bwd_group_kernel(const int *__restrict__ gid, int N, int *__restrict__ glis
 {
     __shared__ int s_cnt[GROUP_PER_THREAD][GROUP_THREADS / 32];
     __shared__ int s_total;
+    pdl_prologue();
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int *__restrict__ out = glist + (size_t)g * N;
@@ -438,6 +440,7 @@ crop_bwd_fill_kernel(const int *__restrict__ glist, const int *__restrict__ gcou
     ListEntryA *__restrict__ entries_a = static_cast<ListEntryA *>(entries_raw);
     __shared__ int s_cnt[FILL_PER_THREAD][FILL_THREADS / 32];
     __shared__ int s_base;
+    pdl_prologue();
     const int st = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // offset = sum of counts before st
@@ -1191,8 +1194,11 @@ static int launch_bwd_tma_cfg(const float *grads, const BwdWs &ws, const BwdTile
     SLN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // work-item tickets: tickets below `grid` are the CTAs' first items (the counter starts there, set by the windows kernel)
     const unsigned grid = bwd_tma_grid(n_work);
-    kern<<<grid, bwdtma::THREADS, smem, st>>>(grads, reinterpret_cast<const ListEntryA *>(ws.entries), ws.st_off, ws.st_count,
-                                              ws.lv_table, TB, C, ph, pw, (int)n_work, chunks, ws.queue);
+    // programmatic dependent of the prep chain: its CTAs are placed and set their barriers up while the fill kernel's last
+    // wave drains, and block (griddepcontrol.wait in the kernel) before they read anything the prep wrote
+    SLN_CUDA_OK(launch_chain(kern, dim3(grid), dim3(bwdtma::THREADS), smem, st, true, grads,
+                             reinterpret_cast<const ListEntryA *>(ws.entries), (const int *)ws.st_off, (const int *)ws.st_count,
+                             (const BwdLevel *)ws.lv_table, TB, C, ph, pw, (int)n_work, chunks, ws.queue));
     SLN_LAUNCH_OK("crop_bwd_tma_kernel");
     return SLN_OK;
 }
@@ -1344,19 +1350,18 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
     // the windows kernel also publishes the level table, so it always runs (>= 1 CTA)
     // the bulk-async kernel plans from the ROI's sampling grid (axes), the strip / tile forms from tap tables
-    crop_bwd_windows_kernel<<<cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256), 256, 0, st>>>(
-        boxes, box_ind, level, N, B, ph, pw, P, ws.win, use_tma ? nullptr : ws.taps, use_tma ? ws.axes : nullptr,
-        ws.st_count, ws.lv_table, ws.queue, (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX)), ws.gid);
+    SLN_CUDA_OK(launch_chain(crop_bwd_windows_kernel, dim3(cdiv(N > BWD_MAX_LEVELS ? N : BWD_MAX_LEVELS, 256)), dim3(256), 0, st, true,
+                             boxes, box_ind, level, N, B, ph, pw, P, ws.win, use_tma ? (Tap *)nullptr : ws.taps,
+                             use_tma ? ws.axes : (RoiAxes *)nullptr, ws.st_count, ws.lv_table, ws.queue,
+                             (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX)), ws.gid));
     SLN_LAUNCH_OK("crop_bwd_windows_kernel");
     if (N > 0 && n_st > 0) {
-        crop_bwd_group_kernel<<<B * n_levels, GROUP_THREADS, 0, st>>>(ws.gid, N, ws.glist, ws.gcount);
+        SLN_CUDA_OK(launch_chain(crop_bwd_group_kernel, dim3(B * n_levels), dim3(GROUP_THREADS), 0, st, true, (const int *)ws.gid, N,
+                                 ws.glist, ws.gcount));
         SLN_LAUNCH_OK("crop_bwd_group_kernel");
-        if (use_tma)
-            crop_bwd_fill_kernel<true><<<n_st, FILL_THREADS, 0, st>>>(ws.glist, ws.gcount, ws.win, ws.axes, N, P, ws.st_count,
-                                                                      ws.st_off, ws.entries);
-        else
-            crop_bwd_fill_kernel<false><<<n_st, FILL_THREADS, 0, st>>>(ws.glist, ws.gcount, ws.win, ws.axes, N, P, ws.st_count,
-                                                                       ws.st_off, ws.entries);
+        SLN_CUDA_OK(launch_chain(use_tma ? crop_bwd_fill_kernel<true> : crop_bwd_fill_kernel<false>, dim3(n_st), dim3(FILL_THREADS), 0, st,
+                                 true, (const int *)ws.glist, (const int *)ws.gcount, (const RoiWin *)ws.win, (const RoiAxes *)ws.axes, N, P,
+                                 (const int *)ws.st_count, ws.st_off, (void *)ws.entries));
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
     if (use_tma) {

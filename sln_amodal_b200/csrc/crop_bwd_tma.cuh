@@ -222,6 +222,7 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
     BwdLevel *lv = reinterpret_cast<BwdLevel *>(sdesc + NST);
     uint64_t *bars = reinterpret_cast<uint64_t *>(lv + BWD_MAX_LEVELS);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NST;
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
             mbar_init(full0 + 8 * i, 1);                   // the producer's arrive(.expect_tx) (+ the bytes)
@@ -230,6 +231,8 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // everything below reads what the prep launches wrote (level table, lists, ticket counter): wait for them here
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x < BWD_MAX_LEVELS) lv[threadIdx.x] = lv_table[threadIdx.x];
     __syncthreads();
 
