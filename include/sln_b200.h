@@ -81,6 +81,15 @@ SLN_API int sln_crop_and_resize_fwd(const float *image, int B, int C, int H, int
  * result bit-identical to the reference CPU backward (about 3x the arithmetic).
  * grad_image is fully written (zeros included); no memset needed.                 */
 #define SLN_BWD_EXACT 1          /* flags bit: round every product/sum like crop_and_resize.c:241-247 */
+/* sln_pyramid_crop_bwd only -- planning ahead.  The backward's ROI lists depend on the boxes, not on the gradients, so
+ * they can be built while the FORWARD of the same ROIs runs (on another stream of the caller's):
+ *   SLN_BWD_PLAN_ONLY : build the lists in `workspace` and return; grads may be NULL, grad_maps_host[l] only need to be
+ *                       non-NULL (nothing is read or written through them).
+ *   SLN_BWD_PLANNED   : `workspace` holds the lists of a PLAN_ONLY call with the same boxes, box_ind, level, N, C, ph, pw,
+ *                       B and map sizes (a plan can be used any number of times): the three prep launches are skipped.
+ * Shapes that do not take the bulk-async kernel ignore PLAN_ONLY and treat PLANNED as a plain call.                  */
+#define SLN_BWD_PLAN_ONLY 2
+#define SLN_BWD_PLANNED 4
 SLN_API size_t sln_crop_and_resize_bwd_workspace_bytes(int N, int B, int ph, int pw);
 SLN_API int sln_crop_and_resize_bwd(const float *grads, const float *boxes, const int *box_ind, int N,
                             int C, int ph, int pw,

@@ -15,6 +15,8 @@ OK = 0
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 BWD_EXACT = 1
+BWD_PLAN_ONLY = 2        # sln_pyramid_crop_bwd: build the ROI lists only
+BWD_PLANNED = 4          # ... the workspace already holds them
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 

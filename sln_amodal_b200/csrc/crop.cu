@@ -377,6 +377,16 @@ __global__ void crop_bwd_windows_kernel(const float *__restrict__ boxes, const i
 constexpr int GROUP_THREADS = 1024;
 constexpr int GROUP_PER_THREAD = 8;
 
+// SLN_BWD_PLANNED: the lists in the workspace were built by an earlier SLN_BWD_PLAN_ONLY call on the same ROIs; only the
+// level table (it carries the gradient maps' addresses, unknown at plan time) and the ticket counter are refreshed.
+__global__ void crop_bwd_republish_kernel(BwdParams P, BwdLevel *__restrict__ lv_table, int *__restrict__ queue, int queue_init)
+{
+    pdl_prologue();
+    const int r = threadIdx.x;
+    if (r < BWD_MAX_LEVELS) lv_table[r] = pick_level(P, r);
+    if (r == 0) *queue = queue_init;
+}
+
 __global__ void __launch_bounds__(GROUP_THREADS)
 crop_bwd_group_kernel(const int *__restrict__ gid, int N, int *__restrict__ glist, int *__restrict__ gcount)
 {
@@ -1275,9 +1285,13 @@ static int dispatch_bwd(const float *grads, const BwdWs &ws, const BwdParams &P,
 }
 
 // grads [N,ph,pw,C]; one grad map per level (NHWC); level[i] selects the map of ROI i (null: level 0)
+// mode 0: plan + run; 1 (SLN_BWD_PLAN_ONLY): build the lists only (grads / maps are not touched; maps[l] only need to be
+// plausible addresses); 2 (SLN_BWD_PLANNED): the workspace holds the lists of a mode-1 call with the same boxes, box_ind,
+// level, N, C, ph, pw, B and map sizes -- skip the three prep launches.  Only the bulk-async form plans ahead; the other
+// forms ignore mode 1 and treat mode 2 as mode 0.
 static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_ind, const int *level, int N, int C,
                          int ph, int pw, float *const *maps, const int *Hs, const int *Ws, int n_levels, int B,
-                         bool exact, void *wsp, size_t ws_bytes, cudaStream_t st)
+                         bool exact, void *wsp, size_t ws_bytes, cudaStream_t st, int mode = 0)
 {
     if (B == 0 || C == 0) return SLN_OK;
     SLN_REQUIRE(ws_bytes >= bwd_ws_bytes(N, B, n_levels, ph, pw), SLN_ERR_WORKSPACE,
@@ -1287,9 +1301,13 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     P.n_levels = n_levels;
     int n_st = 0;
     long long tiles = 0;
-    bool vec4 = (C % 4 == 0) && aligned16(grads);
-    for (int l = 0; l < n_levels; ++l) vec4 = vec4 && aligned16(maps[l]);
+    bool vec4 = (C % 4 == 0) && (mode == 1 || aligned16(grads));
+    for (int l = 0; l < n_levels; ++l) vec4 = vec4 && (mode == 1 || aligned16(maps[l]));
     const bool use_tma = bwd_use_tma(ph, pw, vec4);
+    if (!use_tma) {
+        if (mode == 1) return SLN_OK;
+        mode = 0;
+    }
     for (int l = 0; l < n_levels; ++l) {
         BwdLevel &L = P.lv[l];
         L.out = maps[l];
@@ -1347,6 +1365,13 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
     ws.glist = reinterpret_cast<int *>(p);         p += align_up(sizeof(int) * (size_t)B * n_levels * (size_t)N, 256);
     ws.entries = reinterpret_cast<ListEntry *>(p);
 
+    if (mode == 2) {
+        SLN_CUDA_OK(launch_chain(crop_bwd_republish_kernel, dim3(1), dim3(32), 0, st, true, P, ws.lv_table, ws.queue,
+                                 (int)bwd_tma_grid(tiles * cdiv(C, bwdtma::CH_MAX))));
+        SLN_LAUNCH_OK("crop_bwd_republish_kernel");
+        if (exact) return launch_bwd_tma<true>(grads, ws, P, tiles, C, ph, pw, st);
+        return launch_bwd_tma<false>(grads, ws, P, tiles, C, ph, pw, st);
+    }
     SLN_CUDA_OK(cudaMemsetAsync(ws.st_count, 0, sizeof(int) * (size_t)(n_st + 1), st));
     // the windows kernel also publishes the level table, so it always runs (>= 1 CTA)
     // the bulk-async kernel plans from the ROI's sampling grid (axes), the strip / tile forms from tap tables
@@ -1364,6 +1389,7 @@ static int crop_bwd_nhwc(const float *grads, const float *boxes, const int *box_
                                  (const int *)ws.st_count, ws.st_off, (void *)ws.entries));
         SLN_LAUNCH_OK("crop_bwd_fill_kernel");
     }
+    if (mode == 1) return SLN_OK;
     if (use_tma) {
         if (exact) return launch_bwd_tma<true>(grads, ws, P, tiles, C, ph, pw, st);
         return launch_bwd_tma<false>(grads, ws, P, tiles, C, ph, pw, st);
@@ -1470,9 +1496,10 @@ extern "C" int sln_pyramid_crop_bwd(const float *grads, const float *boxes, cons
         int rc = check_crop_args(grad_maps_host[l], boxes, box_ind, grad_maps_host[l], B, C, H_host[l], W_host[l], N, ph, pw);
         if (rc != SLN_OK) return rc;
     }
-    SLN_REQUIRE(N == 0 || C == 0 || grads, SLN_ERR_ARG, "null grads");
+    const int mode = (flags & SLN_BWD_PLAN_ONLY) ? 1 : ((flags & SLN_BWD_PLANNED) ? 2 : 0);
+    SLN_REQUIRE(N == 0 || C == 0 || grads || mode == 1, SLN_ERR_ARG, "null grads");
     return crop_bwd_nhwc(grads, boxes, box_ind, level, N, C, ph, pw, grad_maps_host, H_host, W_host, n_levels, B,
-                         (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                         (flags & SLN_BWD_EXACT) != 0, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), mode);
 }
 
 // FPN level of every ROI, modal/modals.py:53-64, with the exact fp32 operation sequence the reference's torch

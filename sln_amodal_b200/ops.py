@@ -44,6 +44,18 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device):
+    """One side stream per device for work that runs beside the caller's stream (the backward's planning launches)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    s = _AUX_STREAMS.get(idx)
+    if s is None:
+        s = _AUX_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return s
+
+
 # ---------------------------------------------------------------------------
 # layout converters
 # ---------------------------------------------------------------------------
@@ -192,9 +204,58 @@ def crop_and_resize_backward(grads, boxes, box_ind, image_size, channels_last_ou
     return out
 
 
-def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last_out=None, exact=None):
+class BackwardPlan:
+    """The backward's ROI lists for one (boxes, box_ind, level, map sizes, channels, pool) -- they do not depend on the
+    gradients, so they can be built while the forward of the same ROIs runs.  Holds the workspace and the event that marks
+    the lists ready; valid while boxes / box_ind / level are unchanged."""
+
+    def __init__(self, ws, event, key):
+        self.ws, self.event, self.key = ws, event, key
+
+
+def _plan_key(boxes, box_ind, level, map_sizes, Cc, ph, pw):
+    return (boxes.data_ptr(), boxes._version, box_ind.data_ptr(), box_ind._version, level.data_ptr(), level._version,
+            int(boxes.shape[0]), tuple(tuple(int(v) for v in sz) for sz in map_sizes), int(Cc), int(ph), int(pw))
+
+
+def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_height, crop_width, stream=None):
+    """Build the lists of pyramid_crop_backward ahead of time (sln_pyramid_crop_bwd with SLN_BWD_PLAN_ONLY) on `stream`
+    (default: this module's side stream, forked from the current stream) and return a BackwardPlan to pass as `plan=`.
+    Three small latency-bound launches that then run BESIDE the bandwidth-bound forward instead of in front of the
+    backward's main kernel."""
+    _require_cuda(boxes, "boxes")
+    boxes = _f32c(boxes).view(-1, 4)
+    box_ind = _i32c(box_ind).view(-1)
+    level = _i32c(level).view(-1)
+    N = boxes.shape[0]
+    nl = len(map_sizes)
+    B = int(map_sizes[0][0])
+    ph, pw = int(crop_height), int(crop_width)
+    dev = boxes.device
+    cur = torch.cuda.current_stream(dev)
+    side = stream if stream is not None else _aux_stream(dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), dev)     # allocated on the current stream
+        mp = (C.c_void_p * nl)(*[boxes.data_ptr()] * nl)          # plausible addresses: nothing is accessed through them
+        hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
+        ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
+        ws.record_stream(side)           # a plan dropped without its backward must not hand the block back early
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            check(lib().sln_pyramid_crop_bwd(None, ptr(boxes), ptr(box_ind), ptr(level), N, int(channels), ph, pw, mp, hs, ws_, nl,
+                                             B, _lib.BWD_PLAN_ONLY, ptr(ws), ws.numel(), C.c_void_p(side.cuda_stream)),
+                  "sln_pyramid_crop_bwd(plan)")
+            ev = torch.cuda.Event()
+            ev.record(side)
+    if N:
+        _lib.count_launches(3)
+    return BackwardPlan(ws, ev, _plan_key(boxes, box_ind, level, map_sizes, channels, ph, pw))
+
+
+def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last_out=None, exact=None, plan=None):
     """Backward of pyramid_crop_forward for all levels in one call.  map_sizes: list of (B,C,H_l,W_l).
-    Returns the list of grad maps (channels_last unless channels_last_out[l] is False)."""
+    Returns the list of grad maps (channels_last unless channels_last_out[l] is False).
+    plan: a BackwardPlan from pyramid_crop_backward_plan for the same ROIs (ignored when it does not match)."""
     _require_cuda(grads, "grads")
     if exact is None:
         exact = EXACT_BACKWARD
@@ -211,11 +272,17 @@ def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last
     mp = (C.c_void_p * nl)(*[o.data_ptr() for o in outs])
     hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
     ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
+    planned = plan is not None and plan.key == _plan_key(boxes, box_ind, level, map_sizes, Cc, ph, pw)
     with torch.cuda.device(grads.device):
-        ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), grads.device)
+        if planned:
+            torch.cuda.current_stream(grads.device).wait_event(plan.event)
+            ws = plan.ws
+            flags |= _lib.BWD_PLANNED
+        else:
+            ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), grads.device)
         check(lib().sln_pyramid_crop_bwd(ptr(g), ptr(boxes), ptr(box_ind), ptr(level), N, Cc, ph, pw, mp, hs, ws_, nl, B,
                                          flags, ptr(ws), ws.numel(), stream_ptr()), "sln_pyramid_crop_bwd")
-    _lib.count_launches(4 if N else 1)
+    _lib.count_launches((2 if planned else 4) if N else 1)
     if channels_last_out is not None:
         outs = [o if cl else to_contiguous_nchw(o) for o, cl in zip(outs, channels_last_out)]
     return outs

@@ -13,6 +13,10 @@ from . import ops
 from .crop_and_resize import CropAndResizeFunction
 
 
+# Training: plan the backward (its three ROI-list launches) beside the forward kernel; False restores plan-in-backward.
+PLAN_BACKWARD_IN_FORWARD = True
+
+
 def log2(x):
     """modals.py:8-13: log2 as log(x)/log(2)."""
     ln2 = torch.log(torch.tensor([2.0], dtype=torch.float32, device=x.device))
@@ -35,17 +39,21 @@ def roi_level(boxes, image_shape):
 class _PyramidCrop(torch.autograd.Function):
     @staticmethod
     def forward(ctx, boxes, box_ind, level, pool, *maps):
-        out = ops.pyramid_crop_forward(list(maps), boxes, box_ind, level, pool, pool, 0.0)
-        ctx.save_for_backward(boxes, box_ind, level)
         ctx.sizes = [tuple(m.shape) for m in maps]
         ctx.cl = [ops.is_channels_last(m) for m in maps]
         ctx.needs = [m.requires_grad for m in maps]
+        ctx.plan = None
+        if PLAN_BACKWARD_IN_FORWARD and any(ctx.needs) and boxes.shape[0] and not torch.cuda.is_current_stream_capturing():
+            # the backward's ROI lists only depend on the boxes: build them on a side stream while the forward kernel runs
+            ctx.plan = ops.pyramid_crop_backward_plan(boxes, box_ind, level, ctx.sizes, maps[0].shape[1], pool, pool)
+        out = ops.pyramid_crop_forward(list(maps), boxes, box_ind, level, pool, pool, 0.0)
+        ctx.save_for_backward(boxes, box_ind, level)
         return out
 
     @staticmethod
     def backward(ctx, grad):
         boxes, box_ind, level = ctx.saved_tensors
-        outs = ops.pyramid_crop_backward(grad, boxes, box_ind, level, ctx.sizes, channels_last_out=ctx.cl)
+        outs = ops.pyramid_crop_backward(grad, boxes, box_ind, level, ctx.sizes, channels_last_out=ctx.cl, plan=ctx.plan)
         grads = [o if need else None for o, need in zip(outs, ctx.needs)]
         return (None, None, None, None) + tuple(grads)
 

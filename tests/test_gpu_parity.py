@@ -918,6 +918,54 @@ def test_backward_kernel_forms_agree(impl, monkeypatch):
         assert_close_rel(got, want, rtol=2e-6)
 
 
+@pytest.mark.parametrize("pool", [7, 14])
+def test_backward_planned_ahead_is_bit_identical(pool):
+    """SLN_BWD_PLAN_ONLY + SLN_BWD_PLANNED: the ROI lists built ahead on a side stream give the same bits as the plain
+    call (exact and default mode), a plan can be replayed, a plan for other boxes is ignored, and the autograd path
+    (which plans beside the forward) matches the path that plans inside the backward."""
+    from sln_amodal_b200 import ops, pyramid, pyramid_roi_align
+    rng = np.random.default_rng(pool)
+    B, C, N = 2, 256, 700
+    sides = (64, 32, 16, 8)
+    sizes = [(B, C, s, s) for s in sides]
+    boxes = synth.roi_boxes(N, seed=31 + pool, outside_frac=0.1, degenerate_frac=0.05)
+    ind = rng.integers(0, B, N).astype(np.int32)
+    level = rng.integers(0, 4, N).astype(np.int32)
+    g = cuda(rng.standard_normal((N, C, pool, pool), dtype=np.float32)).contiguous(memory_format=torch.channels_last)
+    tb, ti, tl = cuda(boxes), cuda(ind), cuda(level)
+    for exact in (True, False):
+        plain = ops.pyramid_crop_backward(g, tb, ti, tl, sizes, exact=exact)
+        plan = ops.pyramid_crop_backward_plan(tb, ti, tl, sizes, C, pool, pool)
+        for _ in range(2):                                  # a plan is reusable
+            got = ops.pyramid_crop_backward(g, tb, ti, tl, sizes, exact=exact, plan=plan)
+            assert all(torch.equal(a, b) for a, b in zip(plain, got))
+        other = cuda(synth.roi_boxes(N, seed=5))
+        want_other = ops.pyramid_crop_backward(g, other, ti, tl, sizes, exact=exact)
+        got_other = ops.pyramid_crop_backward(g, other, ti, tl, sizes, exact=exact, plan=plan)   # key mismatch: plain call
+        assert all(torch.equal(a, b) for a, b in zip(want_other, got_other))
+    # exact mode against the oracle, level by level
+    got = ops.pyramid_crop_backward(g, tb, ti, tl, sizes, exact=True, plan=ops.pyramid_crop_backward_plan(tb, ti, tl, sizes, C, pool, pool))
+    gn = g.contiguous().cpu().numpy()
+    for l, s in enumerate(sides):
+        ix = np.nonzero(level == l)[0]
+        want = oracle.crop_and_resize_bwd(gn[ix], boxes[ix], ind[ix], (B, C, s, s))
+        assert got[l].contiguous().cpu().numpy().tobytes() == want.tobytes()
+    # the autograd operator: planning beside the forward vs inside the backward
+    maps_np = [rng.standard_normal((1, 64, s, s), dtype=np.float32) for s in sides]
+    roi = cuda(synth.roi_boxes(300, seed=3)).unsqueeze(0)
+    res = []
+    for flag in (True, False):
+        pyramid.PLAN_BACKWARD_IN_FORWARD = flag
+        try:
+            tm = [cuda(m).contiguous(memory_format=torch.channels_last).requires_grad_(True) for m in maps_np]
+            out = pyramid_roi_align([roi] + tm, pool, (256, 256, 3))
+            (out * out).sum().backward()
+            res.append([t.grad.clone() for t in tm])
+        finally:
+            pyramid.PLAN_BACKWARD_IN_FORWARD = True
+    assert all(torch.equal(a, b) for a, b in zip(*res))
+
+
 # --------------------------------------------------------------------------- SURVEY 8(f)-2: extract_bboxes
 def _extract_bboxes_reference(mask):
     """utils.py:28-54 restated in numpy (same RNG draws)."""
