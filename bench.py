@@ -313,8 +313,14 @@ def run_ours(args):
     for p in POOLS:
         for l, ix in enumerate(lvl_sel):
             h_grads[p][l].copy_(grads[p][: len(ix)])
-    h_out = {p: [pinned_like(grads[p][: len(ix)]) for ix in lvl_sel] for p in POOLS}
-    h_gmaps = [pinned_like(m) for m in maps]
+    # results land in one of two sets of host buffers (steps alternate), so a step's results stay readable while the next
+    # step's copies are already under way
+    h_out_sets = [{p: [pinned_like(grads[p][: len(ix)]) for ix in lvl_sel] for p in POOLS} for _ in range(2)]
+    h_gmaps_sets = [[pinned_like(m) for m in maps] for _ in range(2)]
+    h_out, h_gmaps = h_out_sets[0], h_gmaps_sets[0]
+    step_no = [0]
+    # SLN_BENCH_E2E_SERIAL=1: every step drains its device->host copies before the next step's host->device copies start
+    pipelined = os.environ.get("SLN_BENCH_E2E_SERIAL", "0") != "1"
     h2d = (sum(hm.numel() for hm in h_maps) + sum(t.numel() for t in h_boxes) + sum(t.numel() for t in h_ind)
            + sum(t.numel() for p in POOLS for t in h_grads[p])) * 4
     d2h = (sum(t.numel() for p in POOLS for t in h_out[p]) + sum(hm.numel() for hm in h_gmaps)) * 4
@@ -326,7 +332,10 @@ def run_ours(args):
         # backward.  Host->device copies run on their own stream, device->host copies on another, so the two PCIe
         # directions and the kernels overlap; every byte still moves inside the timed region.
         cur = torch.cuda.current_stream()
-        s_in.wait_stream(cur)
+        if not pipelined:
+            s_in.wait_stream(cur)
+        h_out, h_gmaps = h_out_sets[step_no[0] % 2], h_gmaps_sets[step_no[0] % 2]
+        step_no[0] += 1
         order = [(p, l) for p in POOLS for l in (3, 2, 1, 0)]      # small maps first: kernels and D2H start at once
         d_maps, d_boxes, d_ind, ev_lvl, d_g, ev_g = {}, {}, {}, {}, {}, {}
         with torch.cuda.stream(s_in):
@@ -363,7 +372,8 @@ def run_ours(args):
             if last:
                 gm.record_stream(s_out)
                 d_maps[l].grad = None
-        cur.wait_stream(s_out)
+        if not pipelined:
+            cur.wait_stream(s_out)
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -372,6 +382,7 @@ def run_ours(args):
     a.record()
     for _ in range(e2e_steps):
         e2e_step()
+    torch.cuda.current_stream().wait_stream(s_out)           # the last step's results are on the host before the clock stops
     b.record()
     barrier()
     e2e_ms = sdist.max_over_ranks(a.elapsed_time(b)) / e2e_steps
@@ -379,8 +390,10 @@ def run_ours(args):
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
            "api": "CropAndResizeFunction(ph,pw,0)(image,boxes,box_ind) + .backward per FPN level; pinned host buffers in and out; "
                   "H2D, kernels and D2H on three streams (both PCIe directions overlap); the gradient maps of the two pools are summed "
-                  "on the device by autograd and copied once"}
-    del h_maps, h_grads, h_out, h_gmaps
+                  "on the device by autograd and copied once; " +
+                  ("steps pipelined: step k+1's H2D runs while step k's D2H drains into the other of two host result sets, the "
+                   "clock stops after the last D2H" if pipelined else "every step drains its D2H before the next H2D starts")}
+    del h_maps, h_grads, h_out, h_gmaps, h_out_sets, h_gmaps_sets
 
     # ---- config 1 on every rank: images/s of the detection-head path over rank-sharded images (BASELINE metric 3)
     images = head_throughput(dev, rank, world, barrier, sdist)
