@@ -329,7 +329,9 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                     const float *gr = grads + ((size_t)r * S + (size_t)sy0 * pw + sx0) * C + c0;
                     // stages: whole sample rows, as many as fit; a row longer than a stage takes several stages
                     const int n_s_full = min(nsx, STG_S);
-                    const int rows_per = nsx <= STG_S ? STG_S / nsx : 1;
+                    // STG_S / nsx without the integer divide (~25 dependent instructions on the producer's critical path):
+                    // floor((STG_S + 0.5) / nsx) is exact for 1 <= nsx <= STG_S <= 32 under the approximate divide's 2 ulp
+                    const int rows_per = nsx <= STG_S ? __float2int_rz(__fdividef((float)STG_S + 0.5f, (float)nsx)) : 1;
                     for (int ra = 0; ra < nsy; ra += rows_per) {
                         const int n_rows = min(rows_per, nsy - ra);
                         for (int sb = 0; sb < nsx; sb += STG_S) {
@@ -341,10 +343,9 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                             const bool row_mine = rrow >= 0 && rrow < n_rows;
                             if (row_mine) d->rowd[rrow] = my_row;
                             if (rcol >= 0 && rcol < n_s) d->x[rcol] = my_col;
-                            __syncwarp();
                             const uint32_t bar = full0 + 8 * s;
-                            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(n_rows * n_s * chb));
-                            __syncwarp();
+                            // the copies go out first; the stage's phase cannot complete before lane 0's arrival below (one
+                            // pending arrival), so bytes landing ahead of the expect_tx only drive the count negative for a while
                             if (row_mine) {                  // lane ra + i fetches stage row i
                                 const uint32_t dst = smem_u32(stages + (size_t)s * STAGE_BYTES) + rrow * n_s * chb;
                                 const float *src = gr + ((size_t)lane * pw + sb) * C;
@@ -354,6 +355,8 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                                     for (int k = 0; k < n_s; ++k) bulk_g2s(dst + k * chb, src + (size_t)k * C, (uint32_t)chb, bar);
                                 }
                             }
+                            __syncwarp();                    // the descriptor stores of all lanes before the arrival
+                            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(n_rows * n_s * chb));
                             ++sc;
                         }
                     }

@@ -7,20 +7,28 @@ sys.path.insert(0, %r)
 import bench
 from sln_amodal_b200 import ops
 dev = torch.device("cuda", 0)
-boxes_np, ind_np, level_np = bench.make_workload()
-maps = [torch.randn((8, 256, s, s), device=dev).contiguous(memory_format=torch.channels_last) for s in bench.LEVEL_SIDES]
-boxes, box_ind, level = (torch.from_numpy(a).to(dev) for a in (boxes_np, ind_np, level_np))
-sizes = [tuple(m.shape) for m in maps]
+import hashlib
 res = {}
-for p in (7, 14):
-    g = torch.randn((8000, 256, p, p), device=dev).contiguous(memory_format=torch.channels_last)
-    for _ in range(3): ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10): ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes)
-    b.record(); torch.cuda.synchronize()
-    res[p] = round(a.elapsed_time(b) / 10, 4)
+for per in [int(v) for v in os.environ.get('AB_PER', '1000,4000').split(',')]:
+    bench.ROIS_PER_IMAGE = per
+    boxes_np, ind_np, level_np = bench.make_workload()
+    maps = [torch.randn((8, 256, s, s), device=dev).contiguous(memory_format=torch.channels_last) for s in bench.LEVEL_SIDES]
+    boxes, box_ind, level = (torch.from_numpy(a).to(dev) for a in (boxes_np, ind_np, level_np))
+    sizes = [tuple(m.shape) for m in maps]
+    gen = torch.Generator(device=dev); gen.manual_seed(per)
+    for p in (7, 14, 16):
+        g = torch.randn((8 * per, 256, p, p), device=dev, generator=gen).contiguous(memory_format=torch.channels_last)
+        plan = ops.pyramid_crop_backward_plan(boxes, box_ind, level, sizes, 256, p, p)
+        for _ in range(3): out = ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes, plan=plan)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10): ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes, plan=plan)
+        b.record(); torch.cuda.synchronize()
+        ex = ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes, exact=True)
+        h = hashlib.sha1(b"".join(o.cpu().numpy().tobytes() for o in out + ex)).hexdigest()[:8]
+        res["%%d/%%d" %% (per, p)] = (round(a.elapsed_time(b) / 10, 4), h)
+        del g, out, ex
 print(res)
 ''' % ROOT
 for lib in sys.argv[1:]:

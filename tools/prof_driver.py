@@ -25,8 +25,11 @@ if what == "crop":
     for _ in range(reps):
         for p in bench.POOLS:
             g = torch.randn((boxes.shape[0], bench.CHANNELS, p, p), device=dev).contiguous(memory_format=torch.channels_last)
+            sizes = [tuple(m.shape) for m in maps]
+            # the bench step: ROI lists planned ahead (side stream), forward, backward on the plan
+            plan = ops.pyramid_crop_backward_plan(boxes, box_ind, level, sizes, bench.CHANNELS, p, p)
             ops.pyramid_crop_forward(maps, boxes, box_ind, level, p, p, 0.0)
-            ops.pyramid_crop_backward(g, boxes, box_ind, level, [tuple(m.shape) for m in maps])
+            ops.pyramid_crop_backward(g, boxes, box_ind, level, sizes, plan=plan)
             del g
 elif what == "nms":
     for _ in range(reps):
