@@ -912,7 +912,10 @@ __device__ __forceinline__ void st_zero16(int *p)
     asm volatile("st.global.cs.v4.s32 [%0], {0, 0, 0, 0};" ::"l"(p) : "memory");
 }
 
-__global__ void __launch_bounds__(EB_WARPS * 32, 5)
+#ifndef SLN_EB_CTAS
+#define SLN_EB_CTAS 5
+#endif
+__global__ void __launch_bounds__(EB_WARPS * 32, SLN_EB_CTAS)
 edt_band_build_kernel(const unsigned char *__restrict__ maps, int H, int W, int nb, unsigned *__restrict__ list,
                       unsigned *__restrict__ counters, uint2 *__restrict__ meta, unsigned *__restrict__ stk, int *__restrict__ out)
 {
@@ -1043,28 +1046,36 @@ edt_band_eval_kernel(const unsigned *__restrict__ list, unsigned *__restrict__ c
     __shared__ int s_best[EV_WARPS][eb::BAND][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = __ldcg(counters);
-    auto draw = [&]() {
+    auto draw = [&]() {                                    // lane 0 holds the ticket; broadcast where it is needed
         unsigned t = 0u;
         if (lane == 0) t = atomicAdd(counters + 1, 1u);
-        return __shfl_sync(FULL, t, 0);
+        return t;
     };
     // every lane copies ITS column's entries [kmin, kmax) of the stack at bp (kmin / kmax: over the lanes that need them);
     // a lane only ever reads back what it wrote itself, so no barrier is involved
     auto stage = [&](const unsigned *bp, int lo, int hi, bool need, const unsigned *&ptr, int &stride) {
         const int kmin = __reduce_min_sync(FULL, need ? lo : eb::SLOTS), kmax = __reduce_max_sync(FULL, need ? hi : 0);
+        // global -> shared without a register in between (LDGSTS): every entry of the range is in flight at once, where a
+        // load / store loop unrolled by four waited out one L2 round trip per four entries (26 % of this kernel's stall
+        // samples).  A lane waits for its own copies only -- it reads back nothing else.
         const unsigned *src = bp + (size_t)kmin * W;
-        unsigned *dst = &s_buf[warp][kmin][lane];
-#pragma unroll 4
-        for (int q = kmin; q < kmax; ++q, src += W, dst += 32) *dst = __ldg(src);
+        unsigned dst = (unsigned)__cvta_generic_to_shared(&s_buf[warp][kmin][lane]);
+        for (int q = kmin; q < kmax; ++q, src += W, dst += 32 * 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
         ptr = &s_buf[warp][0][lane];
         stride = 32;
     };
-    unsigned idx = draw();
+    // tickets are drawn two tiles ahead: the atomic's round trip (7 % of the stall samples when its result was needed at
+    // once) overlaps a whole tile; the list entry and the words of the next tile are fetched one tile ahead
+    unsigned idx = __shfl_sync(FULL, draw(), 0);
     if (idx >= count) return;
+    unsigned idx_next = draw();
     unsigned tile = __ldg(list + idx);
     uint2 mm = __ldg(meta + (size_t)(tile >> 5) * W + (tile & 31u) * 32 + lane);
     for (;;) {
-        const unsigned idx_n = draw();
+        const unsigned idx_n = __shfl_sync(FULL, idx_next, 0);
+        if (idx_n < count) idx_next = draw();              // (a warp that saw the end of the list stops drawing)
         unsigned tile_n = 0u;
         uint2 mm_n = make_uint2(0u, 0u);
         if (idx_n < count) {
