@@ -174,6 +174,15 @@ __device__ __forceinline__ void sample_run(float base, float scale, float em1, i
     if (b > a) { k0 = a; n = b - a; }
 }
 
+// whole sample rows of nsx samples that fit a stage of STG_S samples (1 for longer rows: they take several stages).
+// STG_S / nsx without the integer divide (~25 dependent instructions): floor((STG_S + 0.5) / nsx) is exact for
+// 1 <= nsx <= STG_S <= 32 under the approximate divide's 2 ulp.
+template <int STG_S>
+__device__ __forceinline__ int rows_per_stage(int nsx)
+{
+    return nsx <= STG_S ? __float2int_rz(__fdividef((float)STG_S + 0.5f, (float)nsx)) : 1;
+}
+
 struct TileGeom {
     int l, b, y0, x0, y1, x1, c0, st;
 };
@@ -239,11 +248,16 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
     if (warp == NCONS) {
         // =========================================================== producer
         const int S = ph * pw;
-        unsigned sc = 0;                                   // stages issued so far
+        unsigned slot = 0, epar = 1;                       // ring slot of the next stage; parity that marks it released
         auto acquire = [&]() -> unsigned {                 // next ring stage, released by all consumers
-            const unsigned s = sc % NST;
-            mbar_wait(empty0 + 8 * s, ((sc / NST) & 1) ^ 1);
-            return s;
+            mbar_wait(empty0 + 8 * slot, epar);
+            return slot;
+        };
+        auto advance = [&]() {                             // (no % and / by NST on the per-stage chain)
+            if (++slot == NST) {
+                slot = 0;
+                epar ^= 1u;
+            }
         };
         auto no_entry = []() {
             ListEntryA e;
@@ -312,11 +326,15 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, nky > 0 && nkx > 0);
                 const int packed = ky0 | (nky << 8) | (kx0 << 16) | (nkx << 24);
+                // per hit, still one ROI per lane: where its first staged sample lives and how its rows pack into stages --
+                // computed 32 at a time here instead of once per hit on the serial chain below
+                const long long goff = ((long long)e.roi * S + (long long)ky0 * pw + kx0) * C + c0;
+                const int pack2 = rows_per_stage<STG_S>(nkx > 0 ? nkx : 1) | (min(nkx, STG_S) << 8);
                 while (todo) {
                     const int bit = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const int r = __shfl_sync(0xffffffffu, e.roi, bit);
-                    const int pk = __shfl_sync(0xffffffffu, packed, bit);
+                    const long long go = __shfl_sync(0xffffffffu, goff, bit);
+                    const int pk = __shfl_sync(0xffffffffu, packed, bit), pk2 = __shfl_sync(0xffffffffu, pack2, bit);
                     const float by = __shfl_sync(0xffffffffu, e.ax.by, bit), sy = __shfl_sync(0xffffffffu, e.ax.sy, bit);
                     const float bx = __shfl_sync(0xffffffffu, e.ax.bx, bit), sx = __shfl_sync(0xffffffffu, e.ax.sx, bit);
                     const int sy0 = pk & 0xff, nsy = (pk >> 8) & 0xff, sx0 = (pk >> 16) & 0xff, nsx = (pk >> 24) & 0xff;
@@ -326,12 +344,10 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                     XEnt my_col;
                     my_col.pl = tx.lo - x0;
                     my_col.xl = tx.lerp;
-                    const float *gr = grads + ((size_t)r * S + (size_t)sy0 * pw + sx0) * C + c0;
+                    const float *gr = grads + go;
                     // stages: whole sample rows, as many as fit; a row longer than a stage takes several stages
-                    const int n_s_full = min(nsx, STG_S);
-                    // STG_S / nsx without the integer divide (~25 dependent instructions on the producer's critical path):
-                    // floor((STG_S + 0.5) / nsx) is exact for 1 <= nsx <= STG_S <= 32 under the approximate divide's 2 ulp
-                    const int rows_per = nsx <= STG_S ? __float2int_rz(__fdividef((float)STG_S + 0.5f, (float)nsx)) : 1;
+                    const int n_s_full = pk2 >> 8;
+                    const int rows_per = pk2 & 0xff;
                     for (int ra = 0; ra < nsy; ra += rows_per) {
                         const int n_rows = min(rows_per, nsy - ra);
                         for (int sb = 0; sb < nsx; sb += STG_S) {
@@ -357,7 +373,7 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                             }
                             __syncwarp();                    // the descriptor stores of all lanes before the arrival
                             if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(n_rows * n_s * chb));
-                            ++sc;
+                            advance();
                         }
                     }
                 }
@@ -378,7 +394,7 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
                     *reinterpret_cast<TileOut *>(d->rows) = o;
                     mbar_arrive(full0 + 8 * s);
                 }
-                ++sc;
+                advance();
             }
             wC = wB; cntC = cntB; offC = offB; eC = eB; gC = gB;
             wB = wA; cntB = cntA; offB = offA; gB = gA;
@@ -403,9 +419,8 @@ crop_bwd_tma_kernel(const float *__restrict__ grads, const ListEntryA *__restric
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (unsigned sc = 0;; ++sc) {
-        const unsigned s = sc % NST;
-        mbar_wait(full0 + 8 * s, (sc / NST) & 1);
+    for (unsigned s = 0, fpar = 0;; fpar ^= (++s == NST), s = s == NST ? 0u : s) {
+        mbar_wait(full0 + 8 * s, fpar);
         const Desc *d = sdesc + s;
         const int4 hdr = *reinterpret_cast<const int4 *>(d);        // flags, n_s, n_rows, chb
         if (hdr.x != ST_DATA) {
