@@ -67,7 +67,10 @@ for ln, (c, w, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     f, n = ln
     if f not in src:
         try:
-            src[f] = open(subprocess.run(["bash", "-c", f"ls /root/repo/sln_amodal_b200/csrc/{f}"], capture_output=True, text=True).stdout.strip()).read().split("\n")
+            # NCU_LINES_SRC: the source directory the profiled binary was built from (default: this tree's csrc)
+            import os
+            sdir = os.environ.get("NCU_LINES_SRC", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sln_amodal_b200", "csrc"))
+            src[f] = open(os.path.join(sdir, f)).read().split("\n")
         except Exception:
             src[f] = []
     text = src[f][n - 1].strip()[:90] if 0 < n <= len(src[f]) else ""
