@@ -16,6 +16,8 @@ for p in (7, 14):
     g = torch.randn_like(out)
     ops.pyramid_crop_backward(g, boxes, ind, level, [tuple(m.shape) for m in maps])
     ops.pyramid_crop_backward(g, boxes, ind, level, [tuple(m.shape) for m in maps], exact=True)
+    plan = ops.pyramid_crop_backward_plan(boxes, ind, level, [tuple(m.shape) for m in maps], 256, p, p)     # planned ahead (side stream)
+    ops.pyramid_crop_backward(g, boxes, ind, level, [tuple(m.shape) for m in maps], plan=plan)
 # NMS: sparse (plain, class-aware), bail-out to dense, dense only
 for n, kind in ((700, "rpn"), (3000, "uniform")):
     dets = torch.from_numpy(np.concatenate([synth.nms_boxes(n, seed=2, kind=kind), synth.nms_scores(n, seed=3)[:, None]], 1)).to(dev)
