@@ -239,7 +239,8 @@ def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_
         mp = (C.c_void_p * nl)(*[boxes.data_ptr()] * nl)          # plausible addresses: nothing is accessed through them
         hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
         ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
-        ws.record_stream(side)           # a plan dropped without its backward must not hand the block back early
+        for t in (ws, boxes, box_ind, level):       # read / written on the side stream: a tensor dropped right after this
+            t.record_stream(side)                   # call must not hand its block back before the plan launches are done
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             check(lib().sln_pyramid_crop_bwd(None, ptr(boxes), ptr(box_ind), ptr(level), N, int(channels), ph, pw, mp, hs, ws_, nl,
