@@ -33,6 +33,19 @@ def test_header_symbols_exported(built_lib):
     assert _lib.lib().sln_last_error_string() is not None
 
 
+def test_header_flag_values_match_the_python_constants():
+    """The flag / layout macros of include/sln_b200.h and the constants the ctypes layer passes are the same numbers
+    (SLN_BWD_PLAN_ONLY / SLN_BWD_PLANNED: the backward planned beside the forward)."""
+    from sln_amodal_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sln_b200.h")).read()
+    macros = {k: int(v) for k, v in re.findall(r"#define\s+(SLN_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    assert macros["SLN_BWD_EXACT"] == _lib.BWD_EXACT
+    assert macros["SLN_BWD_PLAN_ONLY"] == _lib.BWD_PLAN_ONLY
+    assert macros["SLN_BWD_PLANNED"] == _lib.BWD_PLANNED
+    assert len({macros["SLN_BWD_EXACT"], macros["SLN_BWD_PLAN_ONLY"], macros["SLN_BWD_PLANNED"]}) == 3     # distinct bits
+    assert macros["SLN_BWD_EXACT"] & macros["SLN_BWD_PLAN_ONLY"] == 0 and macros["SLN_BWD_PLAN_ONLY"] & macros["SLN_BWD_PLANNED"] == 0
+
+
 def test_workspace_queries_and_arg_errors(built_lib):
     """Pure host-side entry points: sizes and argument validation (no kernel is launched)."""
     from sln_amodal_b200 import _lib
