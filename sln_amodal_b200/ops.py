@@ -214,8 +214,9 @@ class BackwardPlan:
 
 
 def _plan_key(boxes, box_ind, level, map_sizes, Cc, ph, pw):
-    return (boxes.data_ptr(), boxes._version, box_ind.data_ptr(), box_ind._version, level.data_ptr(), level._version,
-            int(boxes.shape[0]), tuple(tuple(int(v) for v in sz) for sz in map_sizes), int(Cc), int(ph), int(pw))
+    return (boxes.data_ptr(), boxes._version, boxes.dtype, box_ind.data_ptr(), box_ind._version, box_ind.dtype,
+            level.data_ptr(), level._version, level.dtype, int(boxes.numel()),
+            tuple(tuple(int(v) for v in sz) for sz in map_sizes), int(Cc), int(ph), int(pw))
 
 
 def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_height, crop_width, stream=None):
@@ -224,13 +225,15 @@ def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_
     Three small latency-bound launches that then run BESIDE the bandwidth-bound forward instead of in front of the
     backward's main kernel."""
     _require_cuda(boxes, "boxes")
+    ph, pw = int(crop_height), int(crop_width)
+    # keyed on the CALLER's tensors (storage + version counter): an in-place change of any of them invalidates the plan
+    key = _plan_key(boxes, box_ind, level, map_sizes, channels, ph, pw)
     boxes = _f32c(boxes).view(-1, 4)
     box_ind = _i32c(box_ind).view(-1)
     level = _i32c(level).view(-1)
     N = boxes.shape[0]
     nl = len(map_sizes)
     B = int(map_sizes[0][0])
-    ph, pw = int(crop_height), int(crop_width)
     dev = boxes.device
     cur = torch.cuda.current_stream(dev)
     side = stream if stream is not None else _aux_stream(dev)
@@ -250,7 +253,7 @@ def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_
             ev.record(side)
     if N:
         _lib.count_launches(3)
-    return BackwardPlan(ws, ev, _plan_key(boxes, box_ind, level, map_sizes, channels, ph, pw))
+    return BackwardPlan(ws, ev, key)
 
 
 def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last_out=None, exact=None, plan=None):
@@ -261,6 +264,7 @@ def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last
     if exact is None:
         exact = EXACT_BACKWARD
     flags = _lib.BWD_EXACT if exact else 0
+    key_src = (boxes, box_ind, level)                    # the caller's tensors (the conversions below may copy)
     boxes = _f32c(boxes).view(-1, 4)
     box_ind = _i32c(box_ind).view(-1)
     level = _i32c(level).view(-1)
@@ -273,7 +277,7 @@ def pyramid_crop_backward(grads, boxes, box_ind, level, map_sizes, channels_last
     mp = (C.c_void_p * nl)(*[o.data_ptr() for o in outs])
     hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
     ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
-    planned = plan is not None and plan.key == _plan_key(boxes, box_ind, level, map_sizes, Cc, ph, pw)
+    planned = plan is not None and plan.key == _plan_key(*key_src, map_sizes, Cc, ph, pw)
     with torch.cuda.device(grads.device):
         if planned:
             torch.cuda.current_stream(grads.device).wait_event(plan.event)

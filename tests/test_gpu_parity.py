@@ -943,6 +943,19 @@ def test_backward_planned_ahead_is_bit_identical(pool):
         want_other = ops.pyramid_crop_backward(g, other, ti, tl, sizes, exact=exact)
         got_other = ops.pyramid_crop_backward(g, other, ti, tl, sizes, exact=exact, plan=plan)   # key mismatch: plain call
         assert all(torch.equal(a, b) for a, b in zip(want_other, got_other))
+    # a plan is keyed on the CALLER's tensors: converted copies (int64 box_ind) still match, an in-place change does not
+    from sln_amodal_b200 import _lib
+    ti64 = ti.to(torch.int64)
+    plan64 = ops.pyramid_crop_backward_plan(tb, ti64, tl, sizes, C, pool, pool)
+    l0 = _lib.launches()
+    got = ops.pyramid_crop_backward(g, tb, ti64, tl, sizes, plan=plan64)
+    assert _lib.launches() - l0 == 2                                   # republish + main kernel: the plan was taken
+    assert all(torch.equal(a, b) for a, b in zip(plain, got))
+    ti64.add_(0)                                                       # version bump
+    l0 = _lib.launches()
+    got = ops.pyramid_crop_backward(g, tb, ti64, tl, sizes, plan=plan64)
+    assert _lib.launches() - l0 == 4                                   # plan ignored: three prep launches + main kernel
+    assert all(torch.equal(a, b) for a, b in zip(plain, got))
     # exact mode against the oracle, level by level
     got = ops.pyramid_crop_backward(g, tb, ti, tl, sizes, exact=True, plan=ops.pyramid_crop_backward_plan(tb, ti, tl, sizes, C, pool, pool))
     gn = g.contiguous().cpu().numpy()
