@@ -239,7 +239,7 @@ def pyramid_crop_backward_plan(boxes, box_ind, level, map_sizes, channels, crop_
     side = stream if stream is not None else _aux_stream(dev)
     with torch.cuda.device(dev):
         ws = _workspace(lib().sln_pyramid_crop_bwd_workspace_bytes(N, B, nl, ph, pw), dev)     # allocated on the current stream
-        mp = (C.c_void_p * nl)(*[boxes.data_ptr()] * nl)          # plausible addresses: nothing is accessed through them
+        mp = (C.c_void_p * nl)(*[ws.data_ptr()] * nl)             # plausible (non-null) addresses: nothing is accessed through them
         hs = (C.c_int * nl)(*[int(sz[2]) for sz in map_sizes])
         ws_ = (C.c_int * nl)(*[int(sz[3]) for sz in map_sizes])
         for t in (ws, boxes, box_ind, level):       # read / written on the side stream: a tensor dropped right after this

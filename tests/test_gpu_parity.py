@@ -956,6 +956,16 @@ def test_backward_planned_ahead_is_bit_identical(pool):
     got = ops.pyramid_crop_backward(g, tb, ti64, tl, sizes, plan=plan64)
     assert _lib.launches() - l0 == 4                                   # plan ignored: three prep launches + main kernel
     assert all(torch.equal(a, b) for a, b in zip(plain, got))
+    # shapes that do not take the bulk-async kernel (ragged channel count) ignore the plan flags; an empty ROI set plans nothing
+    sizes6 = [(B, 6, s, s) for s in sides]
+    g6 = cuda(rng.standard_normal((N, 6, pool, pool), dtype=np.float32))
+    want6 = ops.pyramid_crop_backward(g6, tb, ti, tl, sizes6, exact=True)
+    got6 = ops.pyramid_crop_backward(g6, tb, ti, tl, sizes6, exact=True, plan=ops.pyramid_crop_backward_plan(tb, ti, tl, sizes6, 6, pool, pool))
+    assert all(torch.equal(a, b) for a, b in zip(want6, got6))
+    e_b, e_i = tb[:0], ti[:0]
+    plan0 = ops.pyramid_crop_backward_plan(e_b, e_i, tl[:0], sizes, C, pool, pool)
+    got0 = ops.pyramid_crop_backward(g[:0], e_b, e_i, tl[:0], sizes, plan=plan0)
+    assert all(float(o.abs().max()) == 0.0 for o in got0)
     # exact mode against the oracle, level by level
     got = ops.pyramid_crop_backward(g, tb, ti, tl, sizes, exact=True, plan=ops.pyramid_crop_backward_plan(tb, ti, tl, sizes, C, pool, pool))
     gn = g.contiguous().cpu().numpy()
